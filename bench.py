@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the SA backbone + rotated NMS hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                  # this repo's sm_100a path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                             # reference CPU arm (oracle port)
+
+A "step" = one pass of the hot path over one batch of synthetic frames per GPU:
+  config 2  KITTI SA stack 16384 -> 4096 -> 1024 -> 512 (radii 0.2/0.8/1.6, nsample 16/32/32,
+            MLPs [4,16,16,32] [35,64,64,128] [131,128,128,256]), batch 16 frames per GPU, plus
+  config 3  rotated NMS on 4096 proposals per frame, IoU 0.01 then 0.1 on the survivors; at N > 1 the
+            padded detections are all-gathered over NCCL (frames are sharded, weak scaling).
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
+through the host-buffer API (pinned H2D of the inputs + D2H of the results inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAMES_PER_GPU = 16
+N_POINTS = 16384
+N_PROPOSALS = 4096
+METRIC = "frames/sec (SA backbone+NMS, 16384 pts/frame)"
+WORKLOAD = ("KITTI SA stack 16384->4096->1024->512 (r 0.2/0.8/1.6, ns 16/32/32) batch 16/GPU + rotated NMS "
+            "4096 proposals/frame IoU 0.01 then 0.1")
+
+
+# ------------------------------------------------------------------------------------ inputs
+def make_inputs(frames: int, seed: int):
+    import numpy as np
+    import synth
+
+    xyz = np.concatenate([synth.cloud_ground_objects(frames // 2, N_POINTS, seed),
+                          synth.cloud_dup_padded(frames - frames // 2, N_POINTS, seed + 1)], 0)
+    feats = np.random.default_rng(seed + 2).uniform(0, 1, size=(frames, 1, N_POINTS)).astype(np.float32)
+    boxes = np.stack([synth.boxes_clustered(N_PROPOSALS, seed + 10 + i, centres=200) for i in range(frames)])
+    scores = np.stack([synth.scores_random(N_PROPOSALS, seed + 100 + i) for i in range(frames)])
+    return xyz, feats, boxes, scores
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_frames_per_second(frames: int, threads: int, seed: int = 0):
+    """The oracle port (this repo's C restatement of the reference kernels + torch-CPU fp32 MLP) on the
+    host cores, over `frames` frames of the same workload.  Returns (frames/s, seconds)."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as orc
+
+    orc.build()
+    orc.set_threads(threads)
+    torch.set_num_threads(threads)
+    from tsmdet_b200.pointnet2_modules import kitti_sa_stack  # module definitions only; no CUDA call below
+
+    xyz, feats, boxes, scores = make_inputs(max(frames, 2), seed)
+    xyz, feats, boxes, scores = xyz[:frames], feats[:frames], boxes[:frames], scores[:frames]
+    torch.manual_seed(0)
+    net = kitti_sa_stack(fused=False).eval()
+    t0 = time.perf_counter()
+    cur_xyz, cur_f = xyz, feats
+    with torch.no_grad():
+        for layer in net.layers:
+            npoint = layer.npoint_list[0]
+            idx = orc.fps(cur_xyz, npoint)
+            new_xyz = np.take_along_axis(cur_xyz, idx.astype(np.int64)[..., None], axis=1)
+            g = layer.groupers[0]
+            cnt, nf, _, _ = orc.query_and_group(cur_xyz, new_xyz, cur_f, g.radius, g.nsample)
+            x = torch.from_numpy(nf) * torch.from_numpy((cnt > 0).astype(np.float32))[:, None, :, None]
+            y = layer.point_mlps[0](x).max(dim=3)[0]
+            cur_xyz, cur_f = new_xyz, y.numpy()
+    for i in range(frames):
+        order = np.argsort(-scores[i], kind="stable")
+        k1 = orc.nms_sorted(boxes[i][order], 0.01)
+        orc.nms_sorted(boxes[i][order][k1], 0.1)
+    dt = time.perf_counter() - t0
+    return frames / dt, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (the pointnet2 ops are CUDA-only in
+    the reference, so this is the oracle port of those kernels + its rotated-IoU CPU code), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames_per_step = FRAMES_PER_GPU  # one full per-GPU batch, so the OpenMP loops over clouds use every core
+    for _ in range(args.warmup and 1):
+        cpu_frames_per_second(frames_per_step, cores)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        fps, _ = cpu_frames_per_second(frames_per_step, cores)
+        vals.append(fps)
+        if time.perf_counter() - t_all > 240:
+            break
+    value = len(vals) * frames_per_step / sum(frames_per_step / v for v in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * frames_per_step / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{frames_per_step} frame(s) of the same workload per step, {len(vals)} steps, "
+                                   f"OpenMP C oracle + torch-CPU fp32 MLP on {cores} threads"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="per-kernel CUDA-event breakdown to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tsmdet_b200 import _lib
+    from tsmdet_b200.pipeline import SABackboneNMS
+
+    try:
+        engine = SABackboneNMS(precision=args.precision).to(dev)
+        xyz_np, feats_np, boxes_np, scores_np = make_inputs(FRAMES_PER_GPU, seed=1000 * rank)
+        h = [torch.from_numpy(a).pin_memory() for a in (xyz_np, feats_np, boxes_np, scores_np)]
+        d = [t.to(dev) for t in h]
+        engine.forward_device(*d, gather=world > 1)  # probes the tensor-core path
+    except _lib.TsmdetError as e:
+        if args.precision == "bf16" and e.code == 1000001:
+            args.precision = "fp32"
+            engine = SABackboneNMS(precision="fp32").to(dev)
+        else:
+            raise
+
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush_buf.zero_()  # L2 flush between timed iterations (not timed)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize(dev)
+        return [s.elapsed_time(e) for s, e in evs]
+
+    gather = world > 1
+    h_out = engine.forward_host(*h, gather=gather)
+    dev_step = lambda: engine.forward_device(*d, gather=gather)  # noqa: E731
+    host_step = lambda: engine.forward_host(*h, h_out=h_out, gather=gather)  # noqa: E731
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count
+    t_wall = time.perf_counter()
+    ms = timed(dev_step, args.steps)
+    barrier()
+    wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop()
+    for _ in range(args.warmup):
+        host_step()
+    barrier()
+    ms_e2e = timed(host_step, args.steps)
+    barrier()
+
+    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)  # max over ranks
+    t_dev, t_e2e = float(tot[0]) / 1000.0, float(tot[1]) / 1000.0
+    frames_total = FRAMES_PER_GPU * world * args.steps
+    value = frames_total / t_dev
+    e2e = frames_total / t_e2e
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (CUDA events on the launching stream)
+    roof, kernels = kernel_breakdown(engine, d, dev, args)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": N_POINTS,
+                   "proposals_per_frame": N_PROPOSALS, "parallelism": f"frames sharded x{world}",
+                   "mlp_precision": args.precision, "l2": "256 MB buffer written between timed steps (untimed)"},
+        "e2e": {"value": e2e, "unit": "frames/s",
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h)),
+                "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out.values()))},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+        "wall_s_timed_region": wall,
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_frames_per_second(2, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"2 frames of the same workload ({dt:.1f} s): OpenMP C oracle of the reference "
+                                          f"kernels + torch-CPU fp32 MLP + oracle rotated NMS"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_breakdown(engine, d, dev, args):
+    """Times each stage of one step on its own (CUDA events, warm, 5 repeats) and derives the roofline
+    entry for the kernel with the largest share (algorithmic bytes: SURVEY.md 8d / DESIGN.md)."""
+    import torch
+
+    from tsmdet_b200 import iou3d_nms_utils, pointnet2_utils
+    from tsmdet_b200.pointnet2_modules import gather_xyz, sa_mlp_maxpool
+
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = dict(json.load(f), src="measured")
+    except OSError:
+        pass
+
+    xyz, feats, boxes, scores = d
+    b = xyz.shape[0]
+
+    def t(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize(dev)
+        return s.elapsed_time(e) / reps
+
+    kernels = []
+    cur_xyz, cur_f = xyz, feats
+    with torch.no_grad():
+        for li, layer in enumerate(engine.backbone.layers):
+            n = cur_xyz.shape[1]
+            m = layer.npoint_list[0]
+            g = layer.groupers[0]
+            ns = g.nsample
+            c = cur_f.shape[1]
+            idx = pointnet2_utils.farthest_point_sample(cur_xyz, m)
+            ms_fps = t(lambda: pointnet2_utils.farthest_point_sample(cur_xyz, m))
+            new_xyz = gather_xyz(cur_xyz, idx)
+            cnt, bidx = pointnet2_utils.ball_query(g.radius, ns, cur_xyz, new_xyz)
+            ms_bq = t(lambda: pointnet2_utils.ball_query(g.radius, ns, cur_xyz, new_xyz))
+            layers = layer._folded_layers()[0]
+            out = torch.empty((b, layers[-1][0].shape[0], m), device=dev)
+            ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, cur_f, bidx, cnt, layers, out, 0, precision=layer.precision))
+            fps_bytes = b * (12 * n + 4 * m)
+            bq_bytes = b * (12 * n + 12 * m + 4 * m * ns + 4 * m)
+            chans = [3 + c] + [w.shape[0] for w, _ in layers]
+            flops = b * 2 * m * ns * sum(chans[i] * chans[i + 1] for i in range(len(chans) - 1))
+            sa_bytes = b * (12 * n + 4 * c * n + 12 * m + 4 * chans[-1] * m + 4 * m * ns)
+            kernels += [
+                {"name": f"fps_L{li + 1}", "ms": ms_fps, "alg_bytes": fps_bytes, "gbs": fps_bytes / ms_fps / 1e6,
+                 "us_per_iter": 1000.0 * ms_fps / max(m - 1, 1), "point_updates_per_s": b * n * (m - 1) / ms_fps * 1e3},
+                {"name": f"ball_query_L{li + 1}", "ms": ms_bq, "alg_bytes": bq_bytes, "gbs": bq_bytes / ms_bq / 1e6,
+                 "tests_per_s": b * n * m / ms_bq * 1e3},
+                {"name": f"sa_mlp_maxpool_L{li + 1}", "ms": ms_mlp, "alg_bytes": sa_bytes, "gbs": sa_bytes / ms_mlp / 1e6,
+                 "tflops": flops / ms_mlp / 1e9},
+            ]
+            cur_xyz, cur_f = new_xyz, out
+        ms_nms = t(lambda: iou3d_nms_utils.nms_gpu_batch(boxes, scores, 0.01))
+        p = boxes.shape[1]
+        kernels.append({"name": "nms_batch(0.01)", "ms": ms_nms, "alg_bytes": b * 36 * p, "gbs": b * 36 * p / ms_nms / 1e6,
+                        "pairs_per_s": b * p * (p - 1) / 2 / ms_nms * 1e3})
+    top = max(kernels, key=lambda k: k["ms"])
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": top["gbs"] / peak, "traffic": None, "peak_source": peaks["src"],
+            "note": "FPS is a serial-latency chain (one argmax per selected point); its HBM traffic is the "
+                    "compulsory 12N+4M bytes per cloud, so the HBM fraction is tiny by construction -- see us_per_iter"}
+    if args.profile_kernels:
+        for k in kernels:
+            print(json.dumps(k), file=sys.stderr)
+    return roof, kernels
+
+
+if __name__ == "__main__":
+    main()

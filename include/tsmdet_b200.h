@@ -1,0 +1,149 @@
+/*
+ * tsmdet_b200.h -- C ABI of libtsmdet_b200.so: the B200 (sm_100a) implementation of the
+ * PointNet++ set-abstraction ops and rotated IoU / NMS of blindopen/TSM-Det-Pointcloud-.
+ *
+ * This is the drop-in boundary.  Every entry point takes raw DEVICE pointers, plain
+ * ints/floats and a CUDA stream (cudaStream_t passed as void*; NULL = legacy default
+ * stream, which is what the reference launches on).  No torch / ATen types.  All
+ * functions return 0 on success, a cudaError_t value on a CUDA failure, or one of the
+ * TSMDET_ERR_* codes; tsmdet_error_string() explains any of them.  Nothing here calls
+ * exit(): the reference's fprintf+exit(-1) error paths (e.g. sampling_gpu.cu:255-259,
+ * ball_query.cpp:20-32) become return codes that the Python shims raise as exceptions.
+ *
+ * Ownership (same as the reference): the CALLER allocates every output.
+ * Layouts are the reference's: contiguous row-major float32 / int32 tensors.
+ *
+ * "ref:" comments name the reference interface each function replaces; paths are
+ * relative to /root/reference/pcdet/ops/.
+ */
+#ifndef TSMDET_B200_H_
+#define TSMDET_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSMDET_OK 0
+#define TSMDET_ERR_INVALID 1000001  /* bad argument / unsupported size */
+#define TSMDET_ERR_WATCHDOG 1000002 /* an in-kernel wait timed out */
+
+const char* tsmdet_version(void);
+const char* tsmdet_error_string(int code);
+/* Reads and clears the per-device watchdog word (0 = clean). */
+int tsmdet_read_status(void);
+
+/* ---------------------------------------------------------------- sampling ----------
+ * xyz (B,N,3) f32, temp (B,N) f32 scratch [in: initial min-distance, normally 1e10;
+ * out: final min-distance; may be NULL], idxs (B,M) i32 out.
+ * ref: pointnet2/pointnet2_batch/src/pointnet2_api.cpp:22,26  farthest_/furthest_point_sampling_wrapper
+ *      (sampling.cpp:43-52, 58-67; kernels sampling_gpu.cu:100-260, 588-748) */
+int tsmdet_farthest_point_sampling(int b, int n, int m, const float* xyz, float* temp, int* idxs, void* stream);
+
+/* weights (B,N) f32.  ref: pointnet2_api.cpp:28 furthest_point_sampling_weights_wrapper
+ *      (sampling.cpp:112-122; sampling_gpu.cu:901-1067) */
+int tsmdet_furthest_point_sampling_weights(int b, int n, int m, const float* xyz, const float* weights, float* temp,
+                                           int* idxs, void* stream);
+
+/* matrix (B,N,N) f32 pairwise distances; temp (B,N) REQUIRED.
+ * ref: pointnet2_api.cpp:23,27 furthest_point_sampling_with_dist_wrapper /
+ *      furthest_point_sampling_matrix_wrapper (sampling_gpu.cu:262-422, 750-899) */
+int tsmdet_furthest_point_sampling_matrix(int b, int n, int m, const float* matrix, float* temp, int* idxs,
+                                          void* stream);
+
+/* ref: pointnet2_api.cpp:25 furthest_point_sampling_with_weighted_dist_wrapper (sampling_gpu.cu:424-586) */
+int tsmdet_furthest_point_sampling_with_weighted_dist(int b, int n, int m, const float* matrix, const float* weights,
+                                                      float* temp, int* idxs, void* stream);
+
+/* Introspection: the cluster size / block size / points per thread the sampler would use. */
+int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread, int* smem_xyz);
+
+/* points (B,C,N), idx (B,npoints) -> out (B,C,npoints).
+ * ref: pointnet2_api.cpp:20-21 gather_points(_grad)_wrapper (sampling_gpu.cu:15-90) */
+int tsmdet_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out,
+                         void* stream);
+int tsmdet_gather_points_grad(int b, int c, int n, int npoints, const float* grad_out, const int* idx,
+                              float* grad_points, void* stream);
+/* xyz (B,N,3), idx (B,M) -> out (B,M,3): the transpose->gather->transpose chain of
+ * pointnet2_modules.py:1143,1212-1215 in one pass. */
+int tsmdet_gather_xyz(int b, int n, int m, const float* xyz, const int* idx, float* out, void* stream);
+
+/* ---------------------------------------------------------------- ball query --------
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx_cnt (B,M) i32, idx (B,M,nsample) i32.
+ * ref: pointnet2_api.cpp:11,13 ball_query_wrapper / ball_query_dilated_wrapper
+ *      (ball_query.cpp:47-71; ball_query_gpu.cu:75-199) */
+int tsmdet_ball_query(int b, int n, int m, float radius, int nsample, const float* new_xyz, const float* xyz,
+                      int* idx_cnt, int* idx, void* stream);
+int tsmdet_ball_query_dilated(int b, int n, int m, float radius_in, float radius_out, int nsample,
+                              const float* new_xyz, const float* xyz, int* idx_cnt, int* idx, void* stream);
+
+/* ---------------------------------------------------------------- grouping ----------
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample).
+ * ref: pointnet2_api.cpp:14-15 group_points(_grad)_wrapper (group_points_gpu.cu:14-92) */
+int tsmdet_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out,
+                        void* stream);
+int tsmdet_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out, const int* idx,
+                             float* grad_points, void* stream);
+/* QueryAndGroup(.Dilated).forward after the query (pointnet2_utils.py:516-530, 554-568) in one
+ * pass: xyz (B,N,3), new_xyz (B,M,3), features (B,C,N)|NULL, idx (B,M,S)
+ *   -> new_features (B, 3*use_xyz + C, M, S) [may be NULL], grouped_xyz (B,3,M,S) [may be NULL] */
+int tsmdet_group_concat(int b, int c, int n, int m, int nsample, int use_xyz, const float* xyz, const float* new_xyz,
+                        const float* features, const int* idx, float* new_features, float* grouped_xyz, void* stream);
+
+/* ---------------------------------------------------------------- interpolation -----
+ * ref: pointnet2_api.cpp:30-32 three_nn_wrapper / three_interpolate(_grad)_wrapper
+ *      (interpolate.cpp; interpolate_gpu.cu:16-168).  dist2 is SQUARED distance, as in the
+ *      reference (the Python caller takes the sqrt, pointnet2_utils.py:282). */
+int tsmdet_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx,
+                    void* stream);
+int tsmdet_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight,
+                             float* out, void* stream);
+int tsmdet_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
+                                  const float* weight, float* grad_points, void* stream);
+
+/* ---------------------------------------------------------------- fused SA layer ----
+ * Set-abstraction scale of _VoxelPointnetSAModuleFS(Distillation)Base.forward's layer-0
+ * branch (pointnet2/pointnet2_batch/pointnet2_modules.py:1259-1268, 1297-1300):
+ * group (xyz offsets + features) -> mask empty balls -> up to 3 x [1x1 conv (BN folded) + ReLU]
+ * -> max over nsample, without materialising the (B,C,npoint,nsample) tensors.
+ *   xyz (B,N,3), new_xyz (B,M,3), features (B,C,N)|NULL, idx (B,M,S) i32, idx_cnt (B,M) i32
+ *   w[l]  (cout_l, cin_l) f32 row-major folded weights, bias[l] (cout_l) f32 folded bias
+ *   out (B, out_stride_c... ) : written at out[b, out_c0 + co, p] with channel stride M and batch
+ *   stride out_ctot*M, so several scales can write into one concatenated tensor.
+ * precision: 0 = fp32 FMA (1e-5 parity mode), 1 = bf16 tensor cores (tcgen05), fp32 accumulate. */
+int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
+                          const float* new_xyz, const float* features, const int* idx, const int* idx_cnt,
+                          int num_layers, const int* channels, const float* const* weights,
+                          const float* const* biases, float* out, int out_ctot, int out_c0, int precision,
+                          void* stream);
+
+/* ---------------------------------------------------------------- IoU / NMS ---------
+ * boxes (N,7) f32 [x,y,z,dx,dy,dz,heading] on the device.
+ * ref: iou3d_nms/src/iou3d_nms_api.cpp:12-13 boxes_overlap_bev_gpu / boxes_iou_bev_gpu
+ *      (iou3d_nms.cpp:49-88; iou3d_nms_kernel.cu:236-265, 378-398) */
+int tsmdet_boxes_overlap_bev(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_overlap,
+                             void* stream);
+int tsmdet_boxes_iou_bev(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_iou,
+                         void* stream);
+
+/* HOST memory in and out (the reference keeps this variant on the CPU for its data pipeline).
+ * ref: iou3d_nms_api.cpp:16 boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252) */
+int tsmdet_boxes_iou_bev_cpu(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_iou);
+
+/* ref: iou3d_nms_api.cpp:14-15 nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-186).
+ * boxes (n,7) device, score order; keep_host (n) int64 on the HOST (as in the reference);
+ * *num_out = number kept.  Synchronises the stream, like the reference. */
+int tsmdet_nms_gpu(int n, const float* boxes, float thresh, long long* keep_host, int* num_out, void* stream);
+int tsmdet_nms_normal_gpu(int n, const float* boxes, float thresh, long long* keep_host, int* num_out, void* stream);
+
+/* Device-resident, batched over frames (no host round trip):
+ * boxes (frames, nmax, box_stride>=7) score-sorted per frame, counts (frames) i32 | NULL,
+ * keep (frames, nmax) int64 device out, num_keep (frames) i32 device out. */
+int tsmdet_nms_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
+                     long long* keep, int* num_keep, void* stream);
+int tsmdet_nms_normal_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
+                            long long* keep, int* num_keep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSMDET_B200_H_ */

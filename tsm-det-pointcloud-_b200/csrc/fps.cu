@@ -1,0 +1,514 @@
+// fps.cu -- furthest point sampling for sm_100a.
+//
+// Replaces (same results, bit for bit):
+//   farthest_point_sampling_kernel / furthest_point_sampling_kernel
+//       /root/reference/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:100-216, 588-704
+//   furthest_point_sampling_weights_kernel                       sampling_gpu.cu:901-1022
+//   furthest_point_sampling_matrix_kernel / _with_dist_kernel    sampling_gpu.cu:750-855, 262-377
+//   furthest_point_sampling_with_weighted_dist_kernel            sampling_gpu.cu:424-541
+//
+// Design (B200-first, not a translation):
+//  * One thread-block CLUSTER per cloud (1..16 CTAs).  Every point and its running
+//    min-distance live in REGISTERS for the whole kernel (shared memory for the
+//    coordinates only when a CTA owns more than 8192 points); HBM is touched once
+//    to load the cloud and once per selected index.
+//  * Per iteration: P fused distance/min/argmax updates per thread, a two-instruction
+//    warp argmax (redux.sync max on the order-preserving key, redux.sync min on the
+//    tie-break rank), one CTA barrier, then the per-CTA winners are exchanged with
+//    st.async (DSMEM store + remote mbarrier complete_tx) -- no cluster-wide barrier
+//    on the critical path.
+//  * Tie-breaking reproduces the reference exactly.  The reference's thread `t`
+//    scans k = t, t+bs, ... keeping the first strict maximum, and its shared-memory
+//    tree keeps the lower slot on ties, which orders threads by the BIT-REVERSAL of
+//    t.  So among equal maxima the winner minimises
+//        rank(k) = (bitrev_L(k mod bs) << (32-L)) | (k / bs),  bs = 2^L = opt_n_threads(N)
+//    and the whole argmax is a max over the 64-bit key (ordered(value), ~rank).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace tsm {
+
+struct FpsArgs {
+    const float* xyz;      // (B,N,3)
+    const float* weights;  // (B,N) or nullptr
+    float* temp;           // (B,N) or nullptr; in: initial min-dist, out: final min-dist
+    int* idxs;             // (B,M)
+    int n, m;
+    int log2bs;  // log2 of the reference block size (cuda_utils.h:10-14)
+    int* status;
+};
+
+struct __align__(16) FpsRec {
+    uint32_t u, rank;
+    float x, y;
+    float z;
+    uint32_t pad[3];
+};
+static_assert(sizeof(FpsRec) == 32, "FpsRec must be 32 bytes");
+
+constexpr uint32_t kRecBytes = 20;  // u, rank, x, y (v4) + z (b32)
+
+__device__ __forceinline__ void wait_records(uint32_t bar, uint32_t phase, int* status) {
+    if (mbar_try_wait_cluster(bar, phase)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, phase)) {
+        if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
+    }
+}
+
+// (u desc, rank asc) warp argmax; returns true in exactly one lane (the winner).
+__device__ __forceinline__ bool warp_pick(uint32_t u, uint32_t rk, uint32_t& wu, uint32_t& wrk) {
+    wu = __reduce_max_sync(FULL, u);
+    wrk = __reduce_min_sync(FULL, (u == wu) ? rk : 0xffffffffu);
+    return (u == wu) && (rk == wrk);
+}
+
+template <int T, int P, bool CLUSTER, bool WEIGHTED, bool SMEM>
+__global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
+    constexpr int NW = T / 32;
+    __shared__ FpsRec slots[CLUSTER ? 1 : 2][NW];
+    __shared__ FpsRec recs[2][16];
+    __shared__ __align__(8) uint64_t mbar[2];
+    extern __shared__ float dyn_xyz[];  // SMEM variant: 3 * P * T floats (SoA planes)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t crank = 0, csize = 1;
+    if (CLUSTER) {
+        crank = cluster_ctarank();
+        csize = cluster_nctarank();
+    }
+    const int cloud = blockIdx.x / csize;
+    const int L = a.log2bs;
+    const int bs = 1 << L;
+    const int n = a.n, m = a.m;
+    const int g = (int)crank * T + tid;  // thread id within the cluster
+    const int r = g & (bs - 1);          // reference thread this thread stands in for
+    const int q = g >> L;                // which chunk of that thread's strided scan
+    const float* __restrict__ xyz = a.xyz + (size_t)cloud * n * 3;
+    const uint32_t lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
+    const uint32_t rbase = ((L == 0) ? 0u : __brev((uint32_t)r)) | (uint32_t)(q * P);
+
+    if (CLUSTER) {
+        if (tid == 0) {
+            mbar_init(smem_u32(&mbar[0]), 1);
+            mbar_init(smem_u32(&mbar[1]), 1);
+            mbar_fence_init_cluster();
+        }
+    }
+
+    float px[SMEM ? 1 : P], py[SMEM ? 1 : P], pz[SMEM ? 1 : P];
+    float md[P];
+    float wf[WEIGHTED ? P : 1];
+    float* sx = dyn_xyz;
+    float* sy = dyn_xyz + P * T;
+    float* sz = dyn_xyz + 2 * P * T;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const long long k = (long long)r + ((long long)(q * P + p) << L);
+        float x = 0.f, y = 0.f, z = 0.f, d0 = -2.f, w0 = -2.f;
+        if (k < n) {
+            x = __ldg(xyz + k * 3 + 0);
+            y = __ldg(xyz + k * 3 + 1);
+            z = __ldg(xyz + k * 3 + 2);
+            d0 = a.temp ? a.temp[(size_t)cloud * n + k] : 1e10f;
+            if (WEIGHTED) w0 = __ldg(a.weights + (size_t)cloud * n + k);
+        }
+        if (SMEM) {
+            sx[p * T + tid] = x;
+            sy[p * T + tid] = y;
+            sz[p * T + tid] = z;
+        } else {
+            px[p] = x;
+            py[p] = y;
+            pz[p] = z;
+        }
+        md[p] = d0;
+        if (WEIGHTED) wf[p] = w0;
+    }
+
+    float x1 = __ldg(xyz + 0), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
+    int* __restrict__ idxs = a.idxs + (size_t)cloud * m;
+    if (!WEIGHTED && g == 0 && m > 0) idxs[0] = 0;
+
+    if (CLUSTER) cluster_sync_all();  // peers' mbarriers are initialised past this point
+
+    int it = 0;
+    for (int j = WEIGHTED ? 0 : 1; j < m; ++j, ++it) {
+        const int par = it & 1;
+        if (CLUSTER && tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), csize * kRecBytes);
+
+        // ---- per-thread scan: first strict maximum in ascending k, as the reference thread does
+        float best = -1.f;
+        int bp = 0;
+        if (WEIGHTED && j == 0) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float v = wf[p] + 0.0f;  // canonicalise -0.0
+                const bool valid = md[p] != -2.f;
+                if (valid && v > best) {
+                    best = v;
+                    bp = p;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float X = SMEM ? sx[p * T + tid] : px[p];
+                const float Y = SMEM ? sy[p * T + tid] : py[p];
+                const float Z = SMEM ? sz[p * T + tid] : pz[p];
+                const float d = sqdist3(x1, y1, z1, X, Y, Z);
+                const float mm = fminf(d, md[p]);  // invalid slots stay at -2
+                md[p] = mm;
+                float score = mm;
+                if (WEIGHTED) score = (mm == -2.f) ? -2.f : (float)((double)mm * fmax((double)wf[p], 1e-12));
+                if (score > best) {
+                    best = score;
+                    bp = p;
+                }
+            }
+        }
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (SMEM) {
+            bx = sx[bp * T + tid];
+            by = sy[bp * T + tid];
+            bz = sz[bp * T + tid];
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (p == bp) {
+                    bx = px[p];
+                    by = py[p];
+                    bz = pz[p];
+                }
+        }
+        const uint32_t u = (best > -1.f) ? f32_ordered(best) : 0u;
+        const uint32_t rk = rbase + (uint32_t)bp;
+
+        // ---- warp argmax, one record per warp
+        uint32_t wu, wrk;
+        const int sb = CLUSTER ? 0 : par;
+        if (warp_pick(u, rk, wu, wrk)) {
+            FpsRec& s = slots[sb][warp];
+            *reinterpret_cast<uint4*>(&s) = make_uint4(u, rk, __float_as_uint(bx), __float_as_uint(by));
+            s.z = bz;
+        }
+        __syncthreads();
+
+        uint32_t gu, grk;
+        if (CLUSTER) {
+            if (warp == 0) {
+                const uint32_t su = (lane < NW) ? slots[0][lane].u : 0u;
+                const uint32_t sr = (lane < NW) ? slots[0][lane].rank : 0xffffffffu;
+                uint32_t cu, crk;
+                const bool mine = warp_pick(su, sr, cu, crk) && (lane < NW);
+                const int wl = __ffs(__ballot_sync(FULL, mine)) - 1;
+                if (lane < (int)csize) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&slots[0][wl]);
+                    const uint32_t zz = __float_as_uint(slots[0][wl].z);
+                    const uint32_t dst = mapa_u32(smem_u32(&recs[par][crank]), (uint32_t)lane);
+                    const uint32_t bar = mapa_u32(smem_u32(&mbar[par]), (uint32_t)lane);
+                    st_async_v4(dst, bar, v.x, v.y, v.z, v.w);
+                    st_async_b32(dst + 16, bar, zz);
+                }
+            }
+            wait_records(smem_u32(&mbar[par]), (uint32_t)((it >> 1) & 1), a.status);
+            gu = 0u;
+            grk = 0xffffffffu;
+            int bc = 0;
+            for (int c = 0; c < (int)csize; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&recs[par][c]);
+                const bool better = (v.x > gu) || (v.x == gu && v.y < grk);
+                if (better) {
+                    gu = v.x;
+                    grk = v.y;
+                    x1 = __uint_as_float(v.z);
+                    y1 = __uint_as_float(v.w);
+                    bc = c;
+                }
+            }
+            z1 = recs[par][bc].z;
+        } else {
+            const uint32_t su = (lane < NW) ? slots[par][lane].u : 0u;
+            const uint32_t sr = (lane < NW) ? slots[par][lane].rank : 0xffffffffu;
+            const bool mine = warp_pick(su, sr, gu, grk) && (lane < NW);
+            const int wl = __ffs(__ballot_sync(FULL, mine)) - 1;
+            const uint4 v = *reinterpret_cast<const uint4*>(&slots[par][wl]);
+            x1 = __uint_as_float(v.z);
+            y1 = __uint_as_float(v.w);
+            z1 = slots[par][wl].z;
+        }
+
+        int k = 0;
+        if (gu == 0u) {  // no eligible candidate anywhere: the reference yields index 0
+            x1 = __ldg(xyz + 0);
+            y1 = __ldg(xyz + 1);
+            z1 = __ldg(xyz + 2);
+        } else {
+            const uint32_t rr = (L == 0) ? 0u : __brev(grk & ~lowmask);
+            k = (int)(rr + ((grk & lowmask) << L));
+        }
+        if (g == 0) idxs[j] = k;
+    }
+
+    if (a.temp) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const long long k = (long long)r + ((long long)(q * P + p) << L);
+            if (k < n) a.temp[(size_t)cloud * n + k] = md[p];
+        }
+    }
+    if (CLUSTER) cluster_sync_all();  // no CTA leaves while a peer may still address its smem
+}
+
+// ------------------------------------------------------------------------------------------
+// Distance-matrix variants ('f-fps'): the distances come from row `old` of a (N,N)
+// matrix, so each iteration is one coalesced row read from L2/HBM; min-distances stay
+// in the caller's temp (any N).  One CTA per cloud; same (value, rank) argmax.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(1024, 1)
+    fps_matrix_kernel(const float* __restrict__ matrix, const float* __restrict__ weights, float* __restrict__ temp,
+                      int* __restrict__ idxs, int n, int m, int log2bs) {
+    constexpr int T = 1024, NW = 32;
+    __shared__ FpsRec slots[2][NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const int L = log2bs, bs = 1 << L;
+    matrix += (size_t)cloud * n * n;
+    temp += (size_t)cloud * n;
+    idxs += (size_t)cloud * m;
+    if (WEIGHTED) weights += (size_t)cloud * n;
+    const uint32_t lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
+    if (!WEIGHTED && tid == 0 && m > 0) idxs[0] = 0;
+    int old = 0;
+    int it = 0;
+    for (int j = WEIGHTED ? 0 : 1; j < m; ++j, ++it) {
+        const int par = it & 1;
+        uint32_t u = 0u, rk = 0xffffffffu;
+        // thread `tid` plays reference threads r = tid, tid+T, ... (only r = tid when bs <= T)
+        for (int r = tid; r < bs; r += T) {
+            float best = -1.f;
+            int bk = 0;
+            for (int k = r; k < n; k += bs) {
+                float score;
+                if (WEIGHTED && j == 0) {
+                    score = weights[k] + 0.0f;
+                } else {
+                    const float d = fminf(matrix[(size_t)old * n + k], temp[k]);
+                    temp[k] = d;
+                    score = WEIGHTED ? (float)((double)d * fmax((double)weights[k], 1e-12)) : d;
+                }
+                if (score > best) {
+                    best = score;
+                    bk = k;
+                }
+            }
+            const uint32_t cu = (best > -1.f) ? f32_ordered(best) : 0u;
+            const uint32_t crk = ((L == 0) ? 0u : __brev((uint32_t)r)) | (uint32_t)(bk >> L);
+            if (cu > u || (cu == u && crk < rk)) {
+                u = cu;
+                rk = crk;
+            }
+        }
+        uint32_t wu, wrk;
+        if (warp_pick(u, rk, wu, wrk)) {
+            slots[par][warp].u = u;
+            slots[par][warp].rank = rk;
+        }
+        __syncthreads();
+        uint32_t gu, grk;
+        warp_pick(slots[par][lane].u, slots[par][lane].rank, gu, grk);
+        old = 0;
+        if (gu != 0u) {
+            const uint32_t rr = (L == 0) ? 0u : __brev(grk & ~lowmask);
+            old = (int)(rr + ((grk & lowmask) << L));
+        }
+        if (tid == 0) idxs[j] = old;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int T, int P, bool CLUSTER, bool WEIGHTED, bool SMEM>
+static int launch_fps(const FpsArgs& a, int b, int csize, cudaStream_t stream) {
+    auto kern = fps_kernel<T, P, CLUSTER, WEIGHTED, SMEM>;
+    const size_t dyn = SMEM ? (size_t)3 * P * T * sizeof(float) : 0;
+    if (dyn > 0) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    if (csize > 8) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * csize));
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (CLUSTER) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    return TSM_OK;
+}
+
+template <bool WEIGHTED>
+static int dispatch_fps(const FpsArgs& a, int b, int csize, int T, int P, bool smem, cudaStream_t s) {
+#define FPS_CASE(TT, PP)                                                                             \
+    if (T == TT && P == PP && !smem)                                                                 \
+        return csize > 1 ? launch_fps<TT, PP, true, WEIGHTED, false>(a, b, csize, s)                 \
+                         : launch_fps<TT, PP, false, WEIGHTED, false>(a, b, csize, s);
+#define FPS_CASE_SMEM(TT, PP)                                                                        \
+    if (T == TT && P == PP && smem)                                                                  \
+        return csize > 1 ? launch_fps<TT, PP, true, WEIGHTED, true>(a, b, csize, s)                  \
+                         : launch_fps<TT, PP, false, WEIGHTED, true>(a, b, csize, s);
+    FPS_CASE(128, 1) FPS_CASE(128, 2) FPS_CASE(128, 4) FPS_CASE(128, 8) FPS_CASE(128, 16) FPS_CASE(128, 32)
+    FPS_CASE(256, 1) FPS_CASE(256, 2) FPS_CASE(256, 4) FPS_CASE(256, 8) FPS_CASE(256, 16) FPS_CASE(256, 32)
+    FPS_CASE(512, 1) FPS_CASE(512, 2) FPS_CASE(512, 4) FPS_CASE(512, 8) FPS_CASE(512, 16)
+    FPS_CASE(1024, 1) FPS_CASE(1024, 2) FPS_CASE(1024, 4) FPS_CASE(1024, 8)
+    FPS_CASE_SMEM(1024, 16) FPS_CASE_SMEM(512, 32)
+#undef FPS_CASE
+#undef FPS_CASE_SMEM
+    return TSM_ERR_INVALID;
+}
+
+}  // namespace tsm
+
+// cuda_utils.h:10-14, bit for bit (same libm double log on the host).
+static int ref_log2_block(int n) {
+    const int pow_2 = (int)(log((double)n) / log(2.0));
+    int t = 1 << pow_2;
+    if (t > 1024) t = 1024;
+    if (t < 1) t = 1;
+    int l = 0;
+    while ((1 << l) < t) ++l;
+    return l;
+}
+
+struct FpsPlan {
+    int csize, T, P;
+    bool smem;
+};
+
+// Pick cluster size / block size / points per thread.  Overridable for tuning with
+// TSMDET_FPS_CLUSTER / TSMDET_FPS_THREADS (values outside the valid set are ignored).
+static bool plan_for(int c, int want_t, int bs, int J, FpsPlan* out) {
+    static const int Ts[4] = {128, 256, 512, 1024};
+    static const int Ps[6] = {1, 2, 4, 8, 16, 32};
+    FpsPlan fallback = {0, 0, 0, false};
+    for (int ti = 0; ti < 4; ++ti) {
+        const int T = Ts[ti];
+        if (want_t && T != want_t) continue;
+        const long G = (long)c * T;
+        if (G < bs) continue;
+        const int need = tsm::divup(J, (int)(G / bs));
+        for (int pi = 0; pi < 6; ++pi) {
+            const int P = Ps[pi];
+            if (P < need) continue;
+            bool smem = false;
+            if ((long)T * P > 8192) {
+                smem = (T == 1024 && P == 16) || (T == 512 && P == 32);
+                if (!smem) break;
+            }
+            const FpsPlan pl = {c, T, P, smem};
+            if (P <= 8 && !smem) {  // smallest block that keeps <= 8 points per thread
+                *out = pl;
+                return true;
+            }
+            fallback = pl;  // keeps the largest feasible T
+            break;
+        }
+    }
+    if (fallback.T) {
+        *out = fallback;
+        return true;
+    }
+    return false;
+}
+
+static bool plan_fps(int b, int n, int log2bs, FpsPlan* out) {
+    const int bs = 1 << log2bs;
+    const int J = tsm::divup(n, bs);
+    const int sms = tsm_num_sms();
+    int cmax = 1;
+    while (cmax * 2 <= 8 && b * cmax * 2 <= sms) cmax *= 2;
+    // a 16-CTA (non-portable) cluster only when a portable one cannot hold the cloud
+    int want_c = 0, want_t = 0;
+    if (const char* e = getenv("TSMDET_FPS_CLUSTER")) want_c = atoi(e);
+    if (const char* e = getenv("TSMDET_FPS_THREADS")) want_t = atoi(e);
+    if (want_t != 128 && want_t != 256 && want_t != 512 && want_t != 1024) want_t = 0;
+    int order[8], no = 0;
+    if (want_c == 1 || want_c == 2 || want_c == 4 || want_c == 8 || want_c == 16) order[no++] = want_c;
+    for (int c = cmax; c >= 1; c >>= 1) order[no++] = c;
+    for (int c = cmax * 2; c <= 16; c <<= 1) order[no++] = c;  // too big for fewer CTAs
+    for (int oi = 0; oi < no && oi < 8; ++oi)
+        if (plan_for(order[oi], want_t, bs, J, out)) return true;
+    if (want_t) {
+        for (int oi = 0; oi < no && oi < 8; ++oi)
+            if (plan_for(order[oi], 0, bs, J, out)) return true;
+    }
+    return false;
+}
+
+static int run_fps(int b, int n, int m, const float* xyz, const float* weights, float* temp, int* idxs,
+                   cudaStream_t stream) {
+    if (b <= 0 || m <= 0) return TSM_OK;
+    if (n <= 0) return TSM_ERR_INVALID;
+    tsm::FpsArgs a;
+    a.xyz = xyz;
+    a.weights = weights;
+    a.temp = temp;
+    a.idxs = idxs;
+    a.n = n;
+    a.m = m;
+    a.log2bs = ref_log2_block(n);
+    a.status = tsm_status_word(stream);
+    FpsPlan pl;
+    if (!plan_fps(b, n, a.log2bs, &pl)) return TSM_ERR_INVALID;
+    if (weights) return tsm::dispatch_fps<true>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
+    return tsm::dispatch_fps<false>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
+}
+
+extern "C" {
+
+int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread, int* smem_xyz) {
+    FpsPlan pl;
+    if (n <= 0 || !plan_fps(b, n, ref_log2_block(n), &pl)) return TSM_ERR_INVALID;
+    if (csize) *csize = pl.csize;
+    if (threads) *threads = pl.T;
+    if (pts_per_thread) *pts_per_thread = pl.P;
+    if (smem_xyz) *smem_xyz = pl.smem ? 1 : 0;
+    return TSM_OK;
+}
+
+int tsmdet_farthest_point_sampling(int b, int n, int m, const float* xyz, float* temp, int* idxs, void* stream) {
+    return run_fps(b, n, m, xyz, nullptr, temp, idxs, (cudaStream_t)stream);
+}
+
+int tsmdet_furthest_point_sampling_weights(int b, int n, int m, const float* xyz, const float* weights, float* temp,
+                                           int* idxs, void* stream) {
+    if (!weights) return TSM_ERR_INVALID;
+    return run_fps(b, n, m, xyz, weights, temp, idxs, (cudaStream_t)stream);
+}
+
+int tsmdet_furthest_point_sampling_matrix(int b, int n, int m, const float* matrix, float* temp, int* idxs,
+                                          void* stream) {
+    if (b <= 0 || m <= 0) return TSM_OK;
+    if (n <= 0 || !temp) return TSM_ERR_INVALID;
+    tsm::fps_matrix_kernel<false><<<b, 1024, 0, (cudaStream_t)stream>>>(matrix, nullptr, temp, idxs, n, m,
+                                                                        ref_log2_block(n));
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+int tsmdet_furthest_point_sampling_with_weighted_dist(int b, int n, int m, const float* matrix, const float* weights,
+                                                      float* temp, int* idxs, void* stream) {
+    if (b <= 0 || m <= 0) return TSM_OK;
+    if (n <= 0 || !temp || !weights) return TSM_ERR_INVALID;
+    tsm::fps_matrix_kernel<true><<<b, 1024, 0, (cudaStream_t)stream>>>(matrix, weights, temp, idxs, n, m,
+                                                                       ref_log2_block(n));
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// interpolate.cu -- three_nn / three_interpolate for sm_100a.
+//
+// Replaces (same dist2 / idx / features, bit for bit):
+//   three_nn_kernel_fast               /root/reference/pcdet/ops/pointnet2/pointnet2_batch/src/interpolate_gpu.cu:16-59
+//   three_interpolate_kernel_fast      interpolate_gpu.cu:84-104
+//   three_interpolate_grad_kernel_fast interpolate_gpu.cu:127-149
+//
+// three_nn keeps the reference's strict-< cascade (ties keep the earlier index).  The
+// reference compares in double; a float widened to double compares exactly like the
+// float, so the cascade runs in f32 and only the 1e40 initial value (-> +inf when fewer
+// than three known points exist) is kept from the double formulation.
+// Known points are streamed through shared memory in their native (M,3) layout; every
+// thread of a warp reads the same point (a broadcast), so the tile costs one
+// shared-memory wavefront per coordinate per warp.
+#include "common.cuh"
+
+namespace tsm {
+
+constexpr int NN_THREADS = 256;
+constexpr int NN_TILE = 2048;  // known points per tile (24 KB)
+constexpr int NN_UPT = 2;      // unknown points per thread (amortises the tile reads)
+
+__global__ void __launch_bounds__(NN_THREADS)
+    three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
+                    float* __restrict__ dist2, int* __restrict__ idx) {
+    __shared__ float tile[NN_TILE * 3];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    known += (size_t)b * m * 3;
+    float ux[NN_UPT], uy[NN_UPT], uz[NN_UPT];
+    float b1[NN_UPT], b2[NN_UPT], b3[NN_UPT];
+    int i1[NN_UPT], i2[NN_UPT], i3[NN_UPT];
+    int pi[NN_UPT];
+#pragma unroll
+    for (int u = 0; u < NN_UPT; ++u) {
+        pi[u] = (blockIdx.x * NN_UPT + u) * NN_THREADS + tid;
+        const int pc = pi[u] < n ? pi[u] : 0;
+        const float* q = unknown + ((size_t)b * n + pc) * 3;
+        ux[u] = n > 0 ? q[0] : 0.f;
+        uy[u] = n > 0 ? q[1] : 0.f;
+        uz[u] = n > 0 ? q[2] : 0.f;
+        b1[u] = b2[u] = b3[u] = __int_as_float(0x7f800000);  // (float)1e40 == +inf
+        i1[u] = i2[u] = i3[u] = 0;
+    }
+    for (int start = 0; start < m; start += NN_TILE) {
+        const int np = min(NN_TILE, m - start);
+        __syncthreads();
+        for (int e = tid; e < np * 3; e += NN_THREADS) tile[e] = known[(size_t)start * 3 + e];
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < np; ++k) {
+            const float x = tile[k * 3 + 0], y = tile[k * 3 + 1], z = tile[k * 3 + 2];
+#pragma unroll
+            for (int u = 0; u < NN_UPT; ++u) {
+                const float d = sqdist3(x, y, z, ux[u], uy[u], uz[u]);
+                if (d < b3[u]) {
+                    const int kk = start + k;
+                    if (d < b1[u]) {
+                        b3[u] = b2[u]; i3[u] = i2[u];
+                        b2[u] = b1[u]; i2[u] = i1[u];
+                        b1[u] = d; i1[u] = kk;
+                    } else if (d < b2[u]) {
+                        b3[u] = b2[u]; i3[u] = i2[u];
+                        b2[u] = d; i2[u] = kk;
+                    } else {
+                        b3[u] = d; i3[u] = kk;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NN_UPT; ++u) {
+        if (pi[u] < n) {
+            float* od = dist2 + ((size_t)b * n + pi[u]) * 3;
+            int* oi = idx + ((size_t)b * n + pi[u]) * 3;
+            od[0] = b1[u]; od[1] = b2[u]; od[2] = b3[u];
+            oi[0] = i1[u]; oi[1] = i2[u]; oi[2] = i3[u];
+        }
+    }
+}
+
+// points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N)
+// compiled form of the reference expression: fma(w2,p2, fma(w0,p0, w1*p1))
+__global__ void __launch_bounds__(256)
+    three_interpolate_kernel(int c, int m, int n, const float* __restrict__ points, const int* __restrict__ idx,
+                             const float* __restrict__ weight, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    const int* ii = idx + ((size_t)b * n + p) * 3;
+    const float* w = weight + ((size_t)b * n + p) * 3;
+    const int j0 = ii[0], j1 = ii[1], j2 = ii[2];
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    points += (size_t)b * c * m;
+    out += (size_t)b * c * n + p;
+#pragma unroll 4
+    for (int ci = 0; ci < c; ++ci) {
+        const float* src = points + (size_t)ci * m;
+        const float v = __fmaf_rn(w2, __ldg(src + j2), __fmaf_rn(w0, __ldg(src + j0), __fmul_rn(w1, __ldg(src + j1))));
+        __stcs(out + (size_t)ci * n, v);
+    }
+}
+
+// grad_out (B,C,N), idx/weight (B,N,3) -> grad_points (B,C,M) += (atomic)
+__global__ void __launch_bounds__(256)
+    three_interpolate_grad_kernel(int c, int n, int m, const float* __restrict__ grad_out,
+                                  const int* __restrict__ idx, const float* __restrict__ weight,
+                                  float* __restrict__ grad_points) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    const int* ii = idx + ((size_t)b * n + p) * 3;
+    const float* w = weight + ((size_t)b * n + p) * 3;
+    const int j0 = ii[0], j1 = ii[1], j2 = ii[2];
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    grad_out += (size_t)b * c * n + p;
+    grad_points += (size_t)b * c * m;
+    for (int ci = 0; ci < c; ++ci) {
+        const float g = grad_out[(size_t)ci * n];
+        float* dst = grad_points + (size_t)ci * m;
+        atomicAdd(dst + j0, __fmul_rn(g, w0));
+        atomicAdd(dst + j1, __fmul_rn(g, w1));
+        atomicAdd(dst + j2, __fmul_rn(g, w2));
+    }
+}
+
+}  // namespace tsm
+
+extern "C" {
+
+int tsmdet_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx,
+                    void* stream) {
+    if (b <= 0 || n <= 0) return TSM_OK;
+    if (b > 65535 || m < 0) return TSM_ERR_INVALID;
+    dim3 grid((unsigned)tsm::divup(n, tsm::NN_THREADS * tsm::NN_UPT), (unsigned)b);
+    tsm::three_nn_kernel<<<grid, tsm::NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+int tsmdet_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight,
+                             float* out, void* stream) {
+    if (b <= 0 || c <= 0 || n <= 0) return TSM_OK;
+    if (b > 65535) return TSM_ERR_INVALID;
+    dim3 grid((unsigned)tsm::divup(n, 256), (unsigned)b);
+    tsm::three_interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+int tsmdet_three_interpolate_grad(int b, int c, int n, int m, const float* grad_out, const int* idx,
+                                  const float* weight, float* grad_points, void* stream) {
+    if (b <= 0 || c <= 0 || n <= 0) return TSM_OK;
+    if (b > 65535) return TSM_ERR_INVALID;
+    dim3 grid((unsigned)tsm::divup(n, 256), (unsigned)b);
+    tsm::three_interpolate_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, m, grad_out, idx, weight,
+                                                                                grad_points);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,572 @@
+// iou3d.cu -- rotated BEV overlap / IoU and NMS for sm_100a.
+//
+// Replaces:
+//   boxes_overlap_kernel / boxes_iou_bev_kernel  /root/reference/pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu:236-265
+//   nms_kernel / nms_normal_kernel               iou3d_nms_kernel.cu:267-311, 328-372
+//   host greedy sweep of nms_gpu/nms_normal_gpu  iou3d_nms.cpp:90-136, 139-186
+//
+// What is kept from the reference is the ARITHMETIC of one box pair (polygon clipping
+// by segment intersection + corner containment, angular sort about the centroid,
+// shoelace area; EPS 1e-8, MARGIN 1e-2, IoU = s / max(sa + sb - s, EPS), suppress iff
+// IoU > thresh) because keep-lists must be bit-exact.  Everything around it is new:
+//   * per-box quantities (rotated corners, cos/sin of -heading, margins, area) are
+//     computed ONCE per box by a prep kernel instead of once per pair;
+//   * a conservative bounding-circle test rejects far pairs to an exact 0 (the
+//     reference's result for disjoint boxes) and the survivors of a 64x64 tile are
+//     compacted with warp ballots into a shared-memory queue, so the expensive path
+//     runs on dense warps;
+//   * only tiles on or above the diagonal are evaluated (the sweep never reads the rest);
+//   * the greedy sweep runs on the device, batched over frames: no 2 MiB mask copy, no
+//     host loop, no cudaMalloc/cudaFree per call.
+#include <math.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tsm {
+
+constexpr float kEps = 1e-8f;
+constexpr float kMargin = 1e-2f;
+
+struct __align__(16) BoxPrep {
+    float cx, cy;        // centre
+    float px[4], py[4];  // rotated corners, reference order
+    float ci, si;        // cosf(-heading), sinf(-heading)
+    float mx, my;        // dx/2 + MARGIN, dy/2 + MARGIN
+    float area;          // dx * dy
+    float rad;           // conservative bounding radius (fast reject only)
+    float x1, y1, x2, y2;  // axis-aligned extents (nms_normal)
+};
+static_assert(sizeof(BoxPrep) == 80, "BoxPrep is 20 floats");
+
+__host__ __device__ __forceinline__ void prep_box(const float* __restrict__ box, BoxPrep& o) {
+    const float bx = box[0], by = box[1], dx = box[3], dy = box[4], ang = box[6];
+    const float hx = dx / 2, hy = dy / 2;
+    const float x1 = bx - hx, y1 = by - hy;
+    const float x2 = bx + hx, y2 = by + hy;
+    const float c = cosf(ang), s = sinf(ang);
+    const float qx[4] = {x1, x2, x2, x1};
+    const float qy[4] = {y1, y1, y2, y2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float nx = (qx[k] - bx) * c + (qy[k] - by) * (-s) + bx;
+        const float ny = (qx[k] - bx) * s + (qy[k] - by) * c + by;
+        o.px[k] = nx;
+        o.py[k] = ny;
+    }
+    o.cx = bx;
+    o.cy = by;
+    o.ci = cosf(-ang);
+    o.si = sinf(-ang);
+    o.mx = dx / 2 + kMargin;
+    o.my = dy / 2 + kMargin;
+    o.area = dx * dy;
+    o.rad = 0.5f * sqrtf(dx * dx + dy * dy) * 1.0001f + 0.03f + 4e-6f * (fabsf(bx) + fabsf(by));
+    o.x1 = x1; o.y1 = y1; o.x2 = x2; o.y2 = y2;
+}
+
+// true when the two rectangles (grown by the containment margin) certainly do not touch:
+// the reference then finds no intersection and no contained corner and returns exactly 0.
+__host__ __device__ __forceinline__ bool surely_disjoint(const BoxPrep& a, const BoxPrep& b) {
+    const float ddx = a.cx - b.cx, ddy = a.cy - b.cy;
+    const float r = a.rad + b.rad;
+    return ddx * ddx + ddy * ddy > r * r;  // NaN compares false -> full path
+}
+
+__host__ __device__ __forceinline__ float cross3(float p1x, float p1y, float p2x, float p2y, float p0x, float p0y) {
+    return (p1x - p0x) * (p2y - p0y) - (p2x - p0x) * (p1y - p0y);
+}
+
+__host__ __device__ __forceinline__ bool corner_inside(const BoxPrep& bx, float x, float y) {
+    const float rx = (x - bx.cx) * bx.ci + (y - bx.cy) * (-bx.si);
+    const float ry = (x - bx.cx) * bx.si + (y - bx.cy) * bx.ci;
+    return fabsf(rx) < bx.mx && fabsf(ry) < bx.my;
+}
+
+// Intersection area of rotated rectangles A (first argument of the reference's
+// box_overlap) and B.
+__host__ __device__ inline float overlap_area(const BoxPrep& A, const BoxPrep& B) {
+    float vx[16], vy[16];
+    int cnt = 0;
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float p0x = A.px[i], p0y = A.py[i];
+        const float p1x = A.px[(i + 1) & 3], p1y = A.py[(i + 1) & 3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float q0x = B.px[j], q0y = B.py[j];
+            const float q1x = B.px[(j + 1) & 3], q1y = B.py[(j + 1) & 3];
+            const bool boxes_touch = fminf(p0x, p1x) <= fmaxf(q0x, q1x) && fminf(q0x, q1x) <= fmaxf(p0x, p1x) &&
+                                     fminf(p0y, p1y) <= fmaxf(q0y, q1y) && fminf(q0y, q1y) <= fmaxf(p0y, p1y);
+            if (!boxes_touch) continue;
+            const float s1 = cross3(q0x, q0y, p1x, p1y, p0x, p0y);
+            const float s2 = cross3(p1x, p1y, q1x, q1y, p0x, p0y);
+            const float s3 = cross3(p0x, p0y, q1x, q1y, q0x, q0y);
+            const float s4 = cross3(q1x, q1y, p1x, p1y, q0x, q0y);
+            if (!(s1 * s2 > 0 && s3 * s4 > 0)) continue;
+            const float s5 = cross3(q1x, q1y, p1x, p1y, p0x, p0y);
+            float ix, iy;
+            if (fabsf(s5 - s1) > kEps) {
+                ix = (s5 * q0x - s1 * q1x) / (s5 - s1);
+                iy = (s5 * q0y - s1 * q1y) / (s5 - s1);
+            } else {
+                const float a0 = p0y - p1y, b0 = p1x - p0x, c0 = p0x * p1y - p1x * p0y;
+                const float a1 = q0y - q1y, b1 = q1x - q0x, c1 = q0x * q1y - q1x * q0y;
+                const float D = a0 * b1 - a1 * b0;
+                ix = (b0 * c1 - b1 * c0) / D;
+                iy = (a1 * c0 - a0 * c1) / D;
+            }
+            sx = sx + ix;
+            sy = sy + iy;
+            vx[cnt] = ix;
+            vy[cnt] = iy;
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (corner_inside(A, B.px[k], B.py[k])) {
+            sx = sx + B.px[k];
+            sy = sy + B.py[k];
+            vx[cnt] = B.px[k];
+            vy[cnt] = B.py[k];
+            ++cnt;
+        }
+        if (corner_inside(B, A.px[k], A.py[k])) {
+            sx = sx + A.px[k];
+            sy = sy + A.py[k];
+            vx[cnt] = A.px[k];
+            vy[cnt] = A.py[k];
+            ++cnt;
+        }
+    }
+    if (cnt < 3) return 0.f;  // fewer than 3 vertices: the shoelace sum below is exactly 0
+    sx /= cnt;
+    sy /= cnt;
+    // angular bubble sort: same comparator and swap sequence as the reference, with each
+    // vertex's atan2f evaluated once (it is a pure function of the vertex and the centre)
+    float ang[16];
+    for (int k = 0; k < cnt; ++k) ang[k] = atan2f(vy[k] - sy, vx[k] - sx);
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (ang[i] > ang[i + 1]) {
+                float t;
+                t = ang[i]; ang[i] = ang[i + 1]; ang[i + 1] = t;
+                t = vx[i]; vx[i] = vx[i + 1]; vx[i + 1] = t;
+                t = vy[i]; vy[i] = vy[i + 1]; vy[i + 1] = t;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ax = vx[k] - vx[0], ay = vy[k] - vy[0];
+        const float bx = vx[k + 1] - vx[0], by = vy[k + 1] - vy[0];
+        area += ax * by - ay * bx;
+    }
+    return fabsf(area) / 2.0;
+}
+
+__host__ __device__ __forceinline__ float iou_rotated(const BoxPrep& A, const BoxPrep& B) {
+    const float so = overlap_area(A, B);
+    return so / fmaxf(A.area + B.area - so, kEps);
+}
+
+__device__ __forceinline__ float iou_axis(const BoxPrep& a, const BoxPrep& b) {
+    const float left = fmaxf(a.x1, b.x1), right = fminf(a.x2, b.x2);
+    const float top = fmaxf(a.y1, b.y1), bottom = fminf(a.y2, b.y2);
+    const float w = fmaxf(right - left, 0.f), h = fmaxf(bottom - top, 0.f);
+    const float inter = w * h;
+    return inter / fmaxf(a.area + b.area - inter, kEps);
+}
+
+// ------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) prep_boxes_kernel(int total, const float* __restrict__ boxes, int stride,
+                                                         BoxPrep* __restrict__ out) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= total) return;
+    BoxPrep p;
+    prep_box(boxes + (size_t)i * stride, p);
+    out[i] = p;
+}
+
+// Dense (N,M) overlap or IoU matrix.  64x64 tile per CTA, survivors of the fast reject
+// are queued and evaluated by dense warps; rejected pairs are written as exact zeros.
+template <bool IOU>
+__global__ void __launch_bounds__(256)
+    pair_matrix_kernel(int na, const BoxPrep* __restrict__ A, int nb, const BoxPrep* __restrict__ B,
+                       float* __restrict__ out) {
+    __shared__ BoxPrep sa[64], sb[64];
+    __shared__ unsigned short queue[4096];
+    __shared__ int qn;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int nr = min(64, na - r0), nc = min(64, nb - c0);
+    for (int e = tid; e < 64 * 20; e += 256) {
+        const int bi = e / 20, w = e - bi * 20;
+        if (bi < nr) reinterpret_cast<float*>(&sa[bi])[w] = reinterpret_cast<const float*>(&A[r0 + bi])[w];
+        if (bi < nc) reinterpret_cast<float*>(&sb[bi])[w] = reinterpret_cast<const float*>(&B[c0 + bi])[w];
+    }
+    if (tid == 0) qn = 0;
+    __syncthreads();
+    for (int p = tid; p < 4096; p += 256) {
+        const int r = p >> 6, c = p & 63;
+        const bool in = r < nr && c < nc;
+        const bool heavy = in && !surely_disjoint(sa[r], sb[c]);
+        if (in && !heavy) out[(size_t)(r0 + r) * nb + c0 + c] = 0.f;
+        const unsigned bal = __ballot_sync(FULL, heavy);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&qn, __popc(bal));
+            base = __shfl_sync(FULL, base, 0);
+            if (heavy) queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)p;
+        }
+    }
+    __syncthreads();
+    const int total = qn;
+    for (int q = tid; q < total; q += 256) {
+        const int p = queue[q];
+        const int r = p >> 6, c = p & 63;
+        const float v = IOU ? iou_rotated(sa[r], sb[c]) : overlap_area(sa[r], sb[c]);
+        out[(size_t)(r0 + r) * nb + c0 + c] = v;
+    }
+}
+
+// Suppression words for the tiles on/above the diagonal.
+//   prep (F, nmax) per-frame prepared boxes in score order, counts (F) or null (= nmax)
+//   mask (F, nmax, cbmax) 64-bit words; only words with column block >= row block are written.
+template <bool NORMAL>
+__global__ void __launch_bounds__(256)
+    nms_mask_kernel(int nmax, const int* __restrict__ counts, float thresh, const BoxPrep* __restrict__ prep,
+                    unsigned long long* __restrict__ mask) {
+    __shared__ BoxPrep srow[64], scol[64];
+    __shared__ unsigned short queue[4096];
+    __shared__ unsigned long long words[64];
+    __shared__ int qn;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int f = blockIdx.y;
+    const int n = counts ? min(counts[f], nmax) : nmax;
+    const int cbmax = divup(nmax, 64);
+    const int cb = divup(n, 64);
+    // linear tile id -> (rb, cbk) with rb <= cbk over the cbmax grid; skip tiles outside this frame
+    int t = blockIdx.x;
+    int rb = 0;
+    {
+        // row rb holds (cbmax - rb) tiles
+        int rem = t;
+        while (rem >= cbmax - rb) {
+            rem -= cbmax - rb;
+            ++rb;
+        }
+        t = rb + rem;
+    }
+    const int cbk = t;
+    if (rb >= cb || cbk >= cb) return;
+    const BoxPrep* P = prep + (size_t)f * nmax;
+    const int r0 = rb * 64, c0 = cbk * 64;
+    const int nr = min(64, n - r0), nc = min(64, n - c0);
+    for (int e = tid; e < 64 * 20; e += 256) {
+        const int bi = e / 20, w = e - bi * 20;
+        if (bi < nr) reinterpret_cast<float*>(&srow[bi])[w] = reinterpret_cast<const float*>(&P[r0 + bi])[w];
+        if (bi < nc) reinterpret_cast<float*>(&scol[bi])[w] = reinterpret_cast<const float*>(&P[c0 + bi])[w];
+    }
+    if (tid < 64) words[tid] = 0ull;
+    if (tid == 0) qn = 0;
+    __syncthreads();
+    const bool diag = rb == cbk;
+    const bool all_heavy = !(thresh >= 0.f);  // negative/NaN threshold: a zero IoU may still suppress
+    for (int p = tid; p < 4096; p += 256) {
+        const int r = p >> 6, c = p & 63;
+        const bool in = r < nr && c < nc && (!diag || c > r);
+        bool heavy = in;
+        if (in && !all_heavy) {
+            if (NORMAL)
+                heavy = true;  // the axis-aligned IoU is cheap: evaluate directly below
+            else
+                heavy = !surely_disjoint(srow[r], scol[c]);
+        }
+        if (NORMAL) {
+            if (heavy && iou_axis(srow[r], scol[c]) > thresh) atomicOr(&words[r], 1ull << c);
+        } else {
+            const unsigned bal = __ballot_sync(FULL, heavy);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&qn, __popc(bal));
+                base = __shfl_sync(FULL, base, 0);
+                if (heavy) queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)p;
+            }
+        }
+    }
+    __syncthreads();
+    if (!NORMAL) {
+        const int total = qn;
+        for (int q = tid; q < total; q += 256) {
+            const int p = queue[q];
+            const int r = p >> 6, c = p & 63;
+            if (iou_rotated(srow[r], scol[c]) > thresh) atomicOr(&words[r], 1ull << c);
+        }
+        __syncthreads();
+    }
+    if (tid < nr) mask[((size_t)f * nmax + r0 + tid) * cbmax + cbk] = words[tid];
+}
+
+// Greedy sweep (iou3d_nms.cpp:116-131) on the device, one CTA per frame.
+//   keep (F, nmax) int64: kept indices (into the score-sorted boxes) in ascending order
+//   num_keep (F) int32
+__global__ void __launch_bounds__(1024)
+    nms_sweep_kernel(int nmax, const int* __restrict__ counts, const unsigned long long* __restrict__ mask,
+                     long long* __restrict__ keep, int* __restrict__ num_keep) {
+    extern __shared__ unsigned long long remv[];  // cbmax words
+    __shared__ unsigned long long diagw[64];
+    __shared__ unsigned long long kept_s;
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x;
+    const int n = counts ? min(counts[f], nmax) : nmax;
+    const int cbmax = divup(nmax, 64);
+    const int cb = divup(n, 64);
+    const unsigned long long* M = mask + (size_t)f * nmax * cbmax;
+    long long* K = keep + (size_t)f * nmax;
+    for (int j = tid; j < cb; j += 1024) remv[j] = 0ull;
+    int base = 0;
+    __syncthreads();
+    for (int b = 0; b < cb; ++b) {
+        const int rows = min(64, n - b * 64);
+        if (tid < 64) diagw[tid] = tid < rows ? M[(size_t)(b * 64 + tid) * cbmax + b] : 0ull;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long cur = remv[b], kept = 0ull;
+            for (int r = 0; r < rows; ++r) {
+                if (!((cur >> r) & 1ull)) {
+                    kept |= 1ull << r;
+                    cur |= diagw[r];
+                }
+            }
+            kept_s = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = kept_s;
+        if (tid < 64 && ((kept >> tid) & 1ull)) {
+            const int pos = base + __popcll(kept & ((1ull << tid) - 1ull));
+            K[pos] = (long long)(b * 64 + tid);
+        }
+        base += __popcll(kept);
+        // OR the rows of the boxes kept in this block into remv[j], j > b:
+        // thread = (column word j, row group g of 4 rows)
+        {
+            const int ncol = cb - b - 1;
+            const int g = tid >> 6;        // 0..15
+            const int jc = tid & 63;
+            for (int j0 = 0; j0 < ncol; j0 += 64) {
+                const int j = b + 1 + j0 + jc;
+                if (j < cb) {
+                    unsigned long long acc = 0ull;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int r = g * 4 + rr;
+                        if ((kept >> r) & 1ull) acc |= M[(size_t)(b * 64 + r) * cbmax + j];
+                    }
+                    if (acc) atomicOr(&remv[j], acc);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) num_keep[f] = base;
+}
+
+}  // namespace tsm
+
+// --------------------------------------------------------------------------------- host
+namespace {
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    unsigned long long tick = 0;
+};
+// Grow-only scratch for prepared boxes + masks, one per (device, stream) so that calls on
+// different streams never share a buffer; stream-ordered (cudaMallocAsync), so repeated
+// NMS calls allocate nothing.
+constexpr int kScratchSlots = 16;
+Scratch g_scratch[kScratchSlots];
+unsigned long long g_tick = 0;
+std::mutex g_scratch_mu;
+
+int scratch_get(size_t bytes, cudaStream_t s, void** out) {
+    int dev = 0;
+    TSM_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    Scratch* sc = nullptr;
+    for (auto& e : g_scratch)
+        if (e.p && e.dev == dev && e.stream == s) sc = &e;
+    if (!sc) {  // empty slot, else evict the least recently used one
+        for (auto& e : g_scratch)
+            if (!e.p && !sc) sc = &e;
+        if (!sc) {
+            sc = &g_scratch[0];
+            for (auto& e : g_scratch)
+                if (e.tick < sc->tick) sc = &e;
+            if (sc->dev == dev) {
+                TSM_CUDA_TRY(cudaFreeAsync(sc->p, sc->stream));
+            } else {
+                int cur = dev;
+                cudaSetDevice(sc->dev);
+                cudaFreeAsync(sc->p, sc->stream);
+                cudaSetDevice(cur);
+            }
+            sc->p = nullptr;
+            sc->cap = 0;
+        }
+        sc->dev = dev;
+        sc->stream = s;
+    }
+    sc->tick = ++g_tick;
+    if (sc->cap < bytes) {
+        if (sc->p) TSM_CUDA_TRY(cudaFreeAsync(sc->p, s));
+        sc->p = nullptr;
+        sc->cap = 0;
+        const size_t want = bytes + bytes / 4;
+        TSM_CUDA_TRY(cudaMallocAsync(&sc->p, want, s));
+        sc->cap = want;
+    }
+    *out = sc->p;
+    return TSM_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int box_stride, const int* counts,
+                   float thresh, long long* keep, int* num_keep, cudaStream_t s) {
+    if (frames <= 0) return TSM_OK;
+    if (nmax <= 0) {
+        TSM_CUDA_TRY(cudaMemsetAsync(num_keep, 0, sizeof(int) * frames, s));
+        return TSM_OK;
+    }
+    if (frames > 65535 || box_stride < 7) return TSM_ERR_INVALID;
+    const int cbmax = tsm::divup(nmax, 64);
+    const size_t prep_bytes = align_up((size_t)frames * nmax * sizeof(tsm::BoxPrep), 256);
+    const size_t mask_bytes = (size_t)frames * nmax * cbmax * sizeof(unsigned long long);
+    void* scratch = nullptr;
+    int rc = scratch_get(prep_bytes + mask_bytes, s, &scratch);
+    if (rc != TSM_OK) return rc;
+    tsm::BoxPrep* prep = (tsm::BoxPrep*)scratch;
+    unsigned long long* mask = (unsigned long long*)((char*)scratch + prep_bytes);
+    const int total = frames * nmax;
+    tsm::prep_boxes_kernel<<<tsm::divup(total, 128), 128, 0, s>>>(total, boxes, box_stride, prep);
+    TSM_LAUNCH_CHECK();
+    const long tiles = (long)cbmax * (cbmax + 1) / 2;
+    if (tiles > 0x7fffffffL) return TSM_ERR_INVALID;
+    dim3 grid((unsigned)tiles, (unsigned)frames);
+    if (normal)
+        tsm::nms_mask_kernel<true><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask);
+    else
+        tsm::nms_mask_kernel<false><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask);
+    TSM_LAUNCH_CHECK();
+    const size_t dyn = (size_t)cbmax * sizeof(unsigned long long);
+    if (dyn > 200 * 1024) return TSM_ERR_INVALID;
+    if (dyn > 48 * 1024)
+        TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    tsm::nms_sweep_kernel<<<frames, 1024, dyn, s>>>(nmax, counts, mask, keep, num_keep);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+int pair_matrix_impl(bool iou, int na, const float* a, int nb, const float* b, float* out, cudaStream_t s) {
+    if (na <= 0 || nb <= 0) return TSM_OK;
+    const size_t pa = align_up((size_t)na * sizeof(tsm::BoxPrep), 256);
+    const size_t pb = (size_t)nb * sizeof(tsm::BoxPrep);
+    void* scratch = nullptr;
+    int rc = scratch_get(pa + pb, s, &scratch);
+    if (rc != TSM_OK) return rc;
+    tsm::BoxPrep* A = (tsm::BoxPrep*)scratch;
+    tsm::BoxPrep* B = (tsm::BoxPrep*)((char*)scratch + pa);
+    tsm::prep_boxes_kernel<<<tsm::divup(na, 128), 128, 0, s>>>(na, a, 7, A);
+    tsm::prep_boxes_kernel<<<tsm::divup(nb, 128), 128, 0, s>>>(nb, b, 7, B);
+    TSM_LAUNCH_CHECK();
+    dim3 grid((unsigned)tsm::divup(nb, 64), (unsigned)tsm::divup(na, 64));
+    if (grid.y > 65535) return TSM_ERR_INVALID;
+    if (iou)
+        tsm::pair_matrix_kernel<true><<<grid, 256, 0, s>>>(na, A, nb, B, out);
+    else
+        tsm::pair_matrix_kernel<false><<<grid, 256, 0, s>>>(na, A, nb, B, out);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tsmdet_boxes_overlap_bev(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_overlap,
+                             void* stream) {
+    return pair_matrix_impl(false, num_a, boxes_a, num_b, boxes_b, ans_overlap, (cudaStream_t)stream);
+}
+
+int tsmdet_boxes_iou_bev(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_iou,
+                         void* stream) {
+    return pair_matrix_impl(true, num_a, boxes_a, num_b, boxes_b, ans_iou, (cudaStream_t)stream);
+}
+
+// Device-resident batched NMS: boxes (frames, nmax, box_stride>=7) already sorted by
+// descending score per frame; counts (frames) valid boxes per frame or NULL (= nmax).
+int tsmdet_nms_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
+                     long long* keep, int* num_keep, void* stream) {
+    return nms_batch_impl(false, frames, nmax, boxes, box_stride, counts, thresh, keep, num_keep,
+                          (cudaStream_t)stream);
+}
+
+int tsmdet_nms_normal_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
+                            long long* keep, int* num_keep, void* stream) {
+    return nms_batch_impl(true, frames, nmax, boxes, box_stride, counts, thresh, keep, num_keep,
+                          (cudaStream_t)stream);
+}
+
+// Reference-shaped entry (iou3d_nms.cpp:90-136): boxes (n,7) on the device in score
+// order, keep_host (n) int64 on the HOST; returns through *num_out.  Synchronous like the
+// reference, but only the keep list (8n bytes) crosses PCIe, not the n*ceil(n/64) mask.
+static int nms_single(bool normal, int n, const float* boxes, float thresh, long long* keep_host, int* num_out,
+                      cudaStream_t s) {
+    *num_out = 0;
+    if (n <= 0) return TSM_OK;
+    long long* keep_dev = nullptr;
+    TSM_CUDA_TRY(cudaMallocAsync(&keep_dev, (size_t)n * sizeof(long long) + 16, s));
+    int* num_dev = (int*)(keep_dev + n);
+    int rc = nms_batch_impl(normal, 1, n, boxes, 7, nullptr, thresh, keep_dev, num_dev, s);
+    if (rc == TSM_OK) {
+        cudaError_t e = cudaMemcpyAsync(num_out, num_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess && *num_out > 0)
+            e = cudaMemcpyAsync(keep_host, keep_dev, (size_t)(*num_out) * sizeof(long long), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        rc = (int)e;
+    }
+    cudaFreeAsync(keep_dev, s);
+    return rc;
+}
+
+// Host-side rotated BEV IoU (the reference keeps a CPU variant for its data pipeline):
+// boxes_a (N,7), boxes_b (M,7), ans_iou (N,M) all in HOST memory.  Same per-pair arithmetic as
+// the device path, evaluated with the host libm.
+// ref: iou3d_nms_api.cpp:16 boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252)
+int tsmdet_boxes_iou_bev_cpu(int num_a, const float* boxes_a, int num_b, const float* boxes_b, float* ans_iou) {
+    if (num_a <= 0 || num_b <= 0) return TSM_OK;
+    std::vector<tsm::BoxPrep> A((size_t)num_a), B((size_t)num_b);
+    for (int i = 0; i < num_a; ++i) tsm::prep_box(boxes_a + (size_t)i * 7, A[i]);
+    for (int j = 0; j < num_b; ++j) tsm::prep_box(boxes_b + (size_t)j * 7, B[j]);
+    for (int i = 0; i < num_a; ++i)
+        for (int j = 0; j < num_b; ++j)
+            ans_iou[(size_t)i * num_b + j] = tsm::surely_disjoint(A[i], B[j]) ? 0.f : tsm::iou_rotated(A[i], B[j]);
+    return TSM_OK;
+}
+
+int tsmdet_nms_gpu(int n, const float* boxes, float thresh, long long* keep_host, int* num_out, void* stream) {
+    return nms_single(false, n, boxes, thresh, keep_host, num_out, (cudaStream_t)stream);
+}
+
+int tsmdet_nms_normal_gpu(int n, const float* boxes, float thresh, long long* keep_host, int* num_out, void* stream) {
+    return nms_single(true, n, boxes, thresh, keep_host, num_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// sa_mlp.cuh -- argument block shared by the fused set-abstraction kernels.
+#pragma once
+#include "common.cuh"
+
+namespace tsm {
+
+struct SaMlpArgs {
+    const float* xyz;       // (B,N,3)
+    const float* new_xyz;   // (B,M,3)
+    const float* features;  // (B,C,N) or null
+    const int* idx;         // (B,M,S)
+    const int* idx_cnt;     // (B,M) or null (no masking)
+    float* out;             // (B,out_ctot,M)
+    const float* w[4];
+    const float* bias[4];
+    int ch[5];  // ch[0] = input channels (3*use_xyz + C), ch[l+1] = outputs of layer l
+    int num_layers;
+    int n, m, s, c_feat, use_xyz;
+    int out_ctot, out_c0;
+    long long total_rows;  // B*M*S
+};
+
+
+}  // namespace tsm
+
+int tsm_sa_mlp_fp32(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);
+int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);  // TSM_ERR_INVALID if the shape is unsupported

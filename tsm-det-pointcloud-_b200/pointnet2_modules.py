@@ -1,0 +1,310 @@
+"""Set-abstraction (layer-0 branch) and feature-propagation modules on the sm_100a kernels.
+
+Mirrors, for the part of the reference that runs on ``pointnet2_batch`` ops,
+``/root/reference/pcdet/ops/pointnet2/pointnet2_batch/pointnet2_modules.py``:
+
+  * ``PointnetFPModule``                     :130-178  (three_nn -> inverse-distance weights -> three_interpolate -> MLP)
+  * ``PointnetSAModuleFSMSG`` (this file)    the ``sa_layer_idx == 0`` / ``sp_tensor is None`` branch of
+    ``_VoxelPointnetSAModuleFS(Distillation)Base.forward`` :1143, 1153-1221, 1259-1268, 1297-1321 with the
+    MLPs built as in ``VoxelPointnetSAModuleFSMSGDistillation.__init__`` :1517-1558, 1589-1603:
+    sample (d-fps / f-fps / s-fps / s-topk) -> gather centres -> per scale {ball query (plain or
+    dilated) -> group -> mask empty balls -> [Conv2d 1x1, BN, ReLU]* -> max over nsample}
+    -> concat scales -> aggregation MLP.
+
+What happens after the aggregation MLP in the reference (centroid voxelisation, spconv) is a
+different algorithm family and outside this package.
+
+Two execution modes give the same numbers within the stated tolerances:
+  ``fused=False``  the reference's eager sequence (materialised (B,C,npoint,nsample) tensors, torch
+                   Conv2d/BatchNorm2d/ReLU/max_pool2d) -- kept as the behavioural reference;
+  ``fused=True``   (eval mode only) BatchNorm folded into the 1x1 convs, one fused kernel per scale
+                   (gather + MLP + max-pool, nothing materialised).  ``precision='fp32'`` is the
+                   1e-5 parity mode, ``precision='bf16'`` runs the contraction on tcgen05 tensor cores.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils
+from ._lib import call, ptr, stream_ptr
+
+
+def build_shared_mlp(spec: Sequence[int], bn: bool = True, dims: int = 2) -> nn.Sequential:
+    """[Conv{dims}d 1x1 (bias iff no BN), BatchNorm, ReLU] per consecutive pair of ``spec`` (ref :1549-1555)."""
+    conv = nn.Conv2d if dims == 2 else nn.Conv1d
+    norm = nn.BatchNorm2d if dims == 2 else nn.BatchNorm1d
+    layers: List[nn.Module] = []
+    for k in range(len(spec) - 1):
+        layers.append(conv(spec[k], spec[k + 1], kernel_size=1, bias=not bn))
+        if bn:
+            layers.append(norm(spec[k + 1]))
+        layers.append(nn.ReLU())
+    return nn.Sequential(*layers)
+
+
+@torch.no_grad()
+def fold_conv_bn(seq: nn.Sequential):
+    """Collapse an eval-mode [Conv1x1, (BN), ReLU]* stack into per-layer (W (cout,cin), b (cout)) fp32."""
+    out = []
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, (nn.Conv1d, nn.Conv2d)) and all(k == 1 for k in conv.kernel_size)
+        w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+        b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+        i += 1
+        if i < len(mods) and isinstance(mods[i], (nn.BatchNorm1d, nn.BatchNorm2d)):
+            bn = mods[i]
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            w = w * scale[:, None]
+            b = (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+            i += 1
+        assert i < len(mods) and isinstance(mods[i], nn.ReLU), "fused path expects Conv-(BN)-ReLU triples"
+        i += 1
+        out.append((w.contiguous(), b.contiguous()))
+    return out
+
+
+def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: int, use_xyz: bool = True,
+                   precision: str = "fp32"):
+    """One fused set-abstraction scale (C ABI ``tsmdet_sa_mlp_maxpool``): writes
+    ``out[:, out_c0:out_c0+cout, :]`` (out is (B, Ctot, npoint) fp32 contiguous)."""
+    b, n, _ = xyz.shape
+    _, m, s = idx.shape
+    c_feat = 0 if features is None else features.shape[1]
+    nl = len(layers)
+    chans = [(3 if use_xyz else 0) + c_feat] + [w.shape[0] for w, _ in layers]
+    for l, (w, bias) in enumerate(layers):
+        assert w.shape == (chans[l + 1], chans[l]) and w.is_contiguous() and bias.is_contiguous()
+    ch_arr = (ctypes.c_int * (nl + 1))(*chans)
+    w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
+    b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
+    prec = {"fp32": 0, "bf16": 1}[precision]
+    call("tsmdet_sa_mlp_maxpool", b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features), ptr(idx),
+         ptr(idx_cnt), nl, ch_arr, w_arr, b_arr, ptr(out), out.shape[1], out_c0, prec, stream_ptr(xyz.device))
+    return out
+
+
+def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """new_xyz[b,p,:] = xyz[b,idx[b,p],:] -- the transpose/gather_operation/transpose chain (:1143, 1212-1215)."""
+    b, n, _ = xyz.shape
+    m = idx.shape[1]
+    out = torch.empty((b, m, 3), dtype=torch.float32, device=xyz.device)
+    call("tsmdet_gather_xyz", b, n, m, ptr(xyz), ptr(idx), ptr(out), stream_ptr(xyz.device))
+    return out
+
+
+class PointnetFPModule(nn.Module):
+    r"""Propagates the features of one set to another (ref :130-178)."""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = build_shared_mlp(mlp, bn=True) if bn else build_shared_mlp(mlp, bn=False)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n)|None, known_feats (B,C2,m) -> (B,mlp[-1],n)"""
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+
+        if unknow_feats is not None:
+            new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
+        else:
+            new_features = interpolated_feats
+        new_features = self.mlp(new_features.unsqueeze(-1))
+        return new_features.squeeze(-1)
+
+
+class PointnetSAModuleFSMSG(nn.Module):
+    """Fusion-sampling, multi-scale-grouping set abstraction on the dense-batch ops (reference layer 0).
+
+    Constructor arguments follow ``VoxelPointnetSAModuleFSMSGDistillation.__init__`` (:1442-1466) for the
+    options that the layer-0 branch reads; ``mlps[i]`` lists the channels WITHOUT the +3 for xyz, as in
+    the reference's config (it adds 3 itself when ``use_xyz``, :1538-1540).
+    """
+
+    def __init__(self, *, npoint_list: List[int] = None, sample_range_list: List[List[int]] = None,
+                 sample_method_list: List[str] = None, radii: List[float], nsamples: List[int],
+                 mlps: List[List[int]], bn: bool = True, use_xyz: bool = True, pool_method: str = 'max_pool',
+                 dilated_radius_group: bool = False, skip_connection: bool = False, weight_gamma: float = 1.0,
+                 aggregation_mlp: Optional[List[int]] = None, fused: bool = True, precision: str = "fp32"):
+        super().__init__()
+        assert npoint_list is None or len(npoint_list) == len(sample_range_list) == len(sample_method_list)
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint_list = npoint_list
+        self.sample_range_list = sample_range_list
+        self.sample_method_list = sample_method_list
+        self.radii, self.nsamples = list(radii), list(nsamples)
+        self.use_xyz = use_xyz
+        self.pool_method = pool_method
+        self.dilated_radius_group = dilated_radius_group
+        self.skip_connection = skip_connection
+        self.weight_gamma = weight_gamma
+        self.fused = fused
+        self.precision = precision
+
+        self.groupers = nn.ModuleList()
+        self.point_mlps = nn.ModuleList()
+        former_radius = 0.0
+        in_channels, out_channels = 0, 0
+        for radius, nsample, spec in zip(radii, nsamples, mlps):
+            if dilated_radius_group:
+                self.groupers.append(pointnet2_utils.QueryAndGroupDilated(former_radius, radius, nsample, use_xyz=use_xyz))
+            else:
+                self.groupers.append(pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz))
+            former_radius = radius
+            spec = list(spec)
+            in_channels = spec[0]
+            if use_xyz:
+                spec[0] += 3
+            self.point_mlps.append(build_shared_mlp(spec, bn=bn))
+            out_channels += spec[-1]
+        self.feature_channels = in_channels
+        if skip_connection:
+            out_channels += in_channels
+        if aggregation_mlp:
+            self.aggregation_mlp = build_shared_mlp([out_channels] + list(aggregation_mlp), bn=bn, dims=1)
+            out_channels = aggregation_mlp[-1]
+        else:
+            self.aggregation_mlp = None
+        self.out_channels = out_channels
+        self._folded = None  # cache of folded (W, b) per scale, built lazily in eval mode
+
+    # ------------------------------------------------------------------ sampling (ref :1153-1210)
+    def sample(self, xyz, features=None, scores=None):
+        sample_idx_list = []
+        for (lo, hi), method, npoint in zip(self.sample_range_list, self.sample_method_list, self.npoint_list):
+            xyz_slice = xyz[:, lo:hi, :].contiguous()
+            if method == 'd-fps':
+                sample_idx = pointnet2_utils.furthest_point_sample(xyz_slice, npoint)
+            elif method == 'f-fps':
+                features_slice = features[:, :, lo:hi]
+                dist_matrix = pointnet2_utils.calc_dist_matrix_for_sampling(
+                    xyz_slice, features_slice.permute(0, 2, 1), self.weight_gamma)
+                sample_idx = pointnet2_utils.furthest_point_sample_matrix(dist_matrix.contiguous(), npoint)
+            elif method == 's-fps':
+                assert scores is not None
+                scores_slice = scores[:, lo:hi].contiguous()
+                scores_slice = scores_slice.sigmoid() ** self.weight_gamma
+                sample_idx = pointnet2_utils.furthest_point_sample_weights(xyz_slice, scores_slice, npoint)
+            elif method == 's-topk':
+                assert scores is not None
+                _, sample_idx = torch.topk(scores[:, lo:hi], k=npoint, dim=-1)
+                sample_idx = sample_idx.int()
+            else:
+                raise NotImplementedError(method)
+            sample_idx_list.append(sample_idx + lo)
+        return torch.cat(sample_idx_list, dim=-1).contiguous()
+
+    def _folded_layers(self):
+        if self._folded is None:
+            self._folded = [fold_conv_bn(m) for m in self.point_mlps]
+        return self._folded
+
+    def train(self, mode: bool = True):
+        self._folded = None
+        return super().train(mode)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz: torch.Tensor = None,
+                scores: torch.Tensor = None):
+        """xyz (B,N,3), features (B,C,N)|None, scores (B,N)|None
+        -> (new_xyz (B,npoint,3), new_features (B,Cout,npoint), sample_idx (B,npoint) int32 | None)"""
+        sample_idx = None
+        old_features = None
+        if new_xyz is None:
+            sample_idx = self.sample(xyz, features, scores)
+            new_xyz = gather_xyz(xyz.contiguous(), sample_idx)
+            if self.skip_connection and features is not None:
+                old_features = pointnet2_utils.gather_operation(features.contiguous(), sample_idx)
+
+        use_fused = self.fused and not self.training and self.pool_method == 'max_pool'
+        b, npoint, _ = new_xyz.shape
+        if use_fused:
+            folded = self._folded_layers()
+            widths = [layers[-1][0].shape[0] for layers in folded]
+            extra = old_features.shape[1] if old_features is not None else 0
+            new_features = torch.empty((b, sum(widths) + extra, npoint), dtype=torch.float32, device=xyz.device)
+            c0 = 0
+            for grouper, layers, w in zip(self.groupers, folded, widths):
+                if isinstance(grouper, pointnet2_utils.QueryAndGroupDilated):
+                    idx_cnt, idx = pointnet2_utils.ball_query_dilated(
+                        grouper.radius_in, grouper.radius_out, grouper.nsample, xyz, new_xyz)
+                else:
+                    idx_cnt, idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
+                sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, new_features, c0,
+                               use_xyz=self.use_xyz or features is None, precision=self.precision)
+                c0 += w
+            if old_features is not None:
+                new_features[:, c0:] = old_features
+        else:
+            new_features_list = []
+            for grouper, mlp in zip(self.groupers, self.point_mlps):
+                idx_cnt, grouped_features, _ = grouper(xyz, new_xyz, features)  # (B, C, npoint, nsample)
+                idx_cnt_mask = (idx_cnt > 0).float().unsqueeze(1).unsqueeze(-1)   # (B, 1, npoint, 1)
+                grouped_features = grouped_features * idx_cnt_mask                # mask the INPUT (ref :1265-1267)
+                y = mlp(grouped_features)
+                if self.pool_method == 'max_pool':
+                    y = F.max_pool2d(y, kernel_size=[1, y.size(3)])
+                elif self.pool_method == 'avg_pool':
+                    y = F.avg_pool2d(y, kernel_size=[1, y.size(3)])
+                else:
+                    raise NotImplementedError(self.pool_method)
+                new_features_list.append(y.squeeze(-1))
+            if old_features is not None:
+                new_features_list.append(old_features)
+            new_features = torch.cat(new_features_list, dim=1)
+
+        if self.aggregation_mlp is not None:
+            new_features = self.aggregation_mlp(new_features)
+        return new_xyz.contiguous(), new_features.contiguous(), sample_idx
+
+
+# The name the reference's backbone config resolves for this layer (sa_layer_idx == 0 only).
+VoxelPointnetSAModuleFSMSGDistillation = PointnetSAModuleFSMSG
+
+
+class PointNet2SAStack(nn.Module):
+    """A plain stack of single- or multi-scale SA layers -- BASELINE.json config 2
+    (16384 -> 4096 -> 1024 -> 512, radii 0.2/0.8/1.6, nsample 16/32/32)."""
+
+    def __init__(self, npoints: Sequence[int], radii: Sequence[Sequence[float]], nsamples: Sequence[Sequence[int]],
+                 mlps: Sequence[Sequence[Sequence[int]]], in_channels: int = 1, fused: bool = True,
+                 precision: str = "fp32"):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        c = in_channels
+        for npoint, r, ns, specs in zip(npoints, radii, nsamples, mlps):
+            specs = [[c] + list(s) for s in specs]
+            layer = PointnetSAModuleFSMSG(
+                npoint_list=[npoint], sample_range_list=[[0, None]], sample_method_list=['d-fps'],
+                radii=list(r), nsamples=list(ns), mlps=specs, fused=fused, precision=precision)
+            self.layers.append(layer)
+            c = layer.out_channels
+        self.out_channels = c
+
+    def forward(self, xyz, features=None):
+        outs = []
+        for layer in self.layers:
+            xyz, features, idx = layer(xyz, features)
+            outs.append((xyz, features, idx))
+        return outs
+
+
+def kitti_sa_stack(fused: bool = True, precision: str = "fp32") -> PointNet2SAStack:
+    """L1 16384->4096 r=0.2 ns=16 [1+3,16,16,32]; L2 4096->1024 r=0.8 ns=32
+    [32+3,64,64,128]; L3 1024->512 r=1.6 ns=32 [128+3,128,128,256]."""
+    return PointNet2SAStack(
+        npoints=[4096, 1024, 512], radii=[[0.2], [0.8], [1.6]], nsamples=[[16], [32], [32]],
+        mlps=[[[16, 16, 32]], [[64, 64, 128]], [[128, 128, 256]]], in_channels=1, fused=fused, precision=precision)

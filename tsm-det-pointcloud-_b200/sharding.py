@@ -1,0 +1,76 @@
+"""Frame sharding across GPUs and the one collective of this path: gathering detections.
+
+Frames are independent (every op here is per cloud; NMS is per frame), so a batch is split by
+frame across ranks exactly like the reference's DistributedSampler splits the dataset
+(``/root/reference/pcdet/datasets/__init__.py:24-44``), with no collective inside the SA stack or NMS.
+The reference merges results through pickle files on a shared tmpdir plus two barriers
+(``pcdet/utils/common_utils.py:224-245``); here the per-frame detections are padded to a fixed
+``(K, 9)`` record [x,y,z,dx,dy,dz,heading,score,label] and exchanged with ONE all_gather (NCCL over
+NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_frames: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block of frames owned by ``rank`` (sizes differ by at most one)."""
+    base, rem = divmod(num_frames, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_frames(x: torch.Tensor, world_size: int, rank: int) -> torch.Tensor:
+    lo, hi = shard_bounds(x.shape[0], world_size, rank)
+    return x[lo:hi]
+
+
+def pad_detections(boxes: Sequence[torch.Tensor], scores: Sequence[torch.Tensor], labels: Sequence[torch.Tensor],
+                   k_post: int, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-frame variable-length detections -> (F, k_post, 9) float32 zero-padded + (F,) int32 counts."""
+    f = len(boxes)
+    device = device if device is not None else (boxes[0].device if f else torch.device("cpu"))
+    out = torch.zeros((f, k_post, 9), dtype=torch.float32, device=device)
+    cnt = torch.zeros((f,), dtype=torch.int32, device=device)
+    for i in range(f):
+        k = min(int(boxes[i].shape[0]), k_post)
+        if k:
+            out[i, :k, :7] = boxes[i][:k, :7]
+            out[i, :k, 7] = scores[i][:k]
+            out[i, :k, 8] = labels[i][:k].to(torch.float32)
+        cnt[i] = k
+    return out, cnt
+
+
+def gather_detections(padded: torch.Tensor, counts: torch.Tensor, frames_total: Optional[int] = None,
+                      group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All ranks receive every rank's (F_local, K, 9) records and counts, concatenated in rank order
+    (= original frame order for ``shard_bounds`` sharding).  Ranks may own different numbers of
+    frames; shards are padded to the largest one for the fixed-size collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return padded, counts
+    world = dist.get_world_size(group)
+    k = padded.shape[1]
+    f_local = torch.tensor([padded.shape[0]], dtype=torch.int64, device=padded.device)
+    f_all = [torch.zeros_like(f_local) for _ in range(world)]
+    if frames_total is None:
+        dist.all_gather(f_all, f_local, group=group)
+        sizes = [int(t.item()) for t in f_all]
+    else:
+        sizes = [shard_bounds(frames_total, world, r)[1] - shard_bounds(frames_total, world, r)[0] for r in range(world)]
+    fmax = max(sizes)
+    # one flat buffer per rank: records then counts (as float32 bit patterns) -> a single collective
+    buf = torch.zeros((fmax * k * 9 + fmax,), dtype=torch.float32, device=padded.device)
+    buf[: padded.numel()] = padded.reshape(-1)
+    buf[fmax * k * 9: fmax * k * 9 + counts.numel()] = counts.to(torch.int32).view(torch.float32)
+    out = torch.empty((world, buf.numel()), dtype=torch.float32, device=padded.device)
+    dist.all_gather_into_tensor(out, buf, group=group) if hasattr(dist, "all_gather_into_tensor") and padded.is_cuda \
+        else dist.all_gather(list(out.unbind(0)), buf, group=group)
+    recs, cnts = [], []
+    for r in range(world):
+        recs.append(out[r, : sizes[r] * k * 9].view(sizes[r], k, 9))
+        cnts.append(out[r, fmax * k * 9: fmax * k * 9 + sizes[r]].contiguous().view(torch.int32))
+    return torch.cat(recs, 0), torch.cat(cnts, 0)
