@@ -145,3 +145,5 @@ __host__ __device__ __forceinline__ int divup(int a, int b) { return (a + b - 1)
 // Host-side: number of SMs of the current device (cached).
 int tsm_num_sms();
 int* tsm_status_word(cudaStream_t stream);  // device int, zero-initialised, one per process
+// Stream-ordered grow-only scratch, keyed by (device, stream, tag): tag 0 = IoU/NMS, 1 = SA MLP.
+int tsm_scratch_get(int tag, size_t bytes, cudaStream_t stream, void** out);

@@ -379,62 +379,6 @@ __global__ void __launch_bounds__(1024)
 // --------------------------------------------------------------------------------- host
 namespace {
 
-struct Scratch {
-    void* p = nullptr;
-    size_t cap = 0;
-    int dev = -1;
-    cudaStream_t stream = nullptr;
-    unsigned long long tick = 0;
-};
-// Grow-only scratch for prepared boxes + masks, one per (device, stream) so that calls on
-// different streams never share a buffer; stream-ordered (cudaMallocAsync), so repeated
-// NMS calls allocate nothing.
-constexpr int kScratchSlots = 16;
-Scratch g_scratch[kScratchSlots];
-unsigned long long g_tick = 0;
-std::mutex g_scratch_mu;
-
-int scratch_get(size_t bytes, cudaStream_t s, void** out) {
-    int dev = 0;
-    TSM_CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
-    Scratch* sc = nullptr;
-    for (auto& e : g_scratch)
-        if (e.p && e.dev == dev && e.stream == s) sc = &e;
-    if (!sc) {  // empty slot, else evict the least recently used one
-        for (auto& e : g_scratch)
-            if (!e.p && !sc) sc = &e;
-        if (!sc) {
-            sc = &g_scratch[0];
-            for (auto& e : g_scratch)
-                if (e.tick < sc->tick) sc = &e;
-            if (sc->dev == dev) {
-                TSM_CUDA_TRY(cudaFreeAsync(sc->p, sc->stream));
-            } else {
-                int cur = dev;
-                cudaSetDevice(sc->dev);
-                cudaFreeAsync(sc->p, sc->stream);
-                cudaSetDevice(cur);
-            }
-            sc->p = nullptr;
-            sc->cap = 0;
-        }
-        sc->dev = dev;
-        sc->stream = s;
-    }
-    sc->tick = ++g_tick;
-    if (sc->cap < bytes) {
-        if (sc->p) TSM_CUDA_TRY(cudaFreeAsync(sc->p, s));
-        sc->p = nullptr;
-        sc->cap = 0;
-        const size_t want = bytes + bytes / 4;
-        TSM_CUDA_TRY(cudaMallocAsync(&sc->p, want, s));
-        sc->cap = want;
-    }
-    *out = sc->p;
-    return TSM_OK;
-}
-
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int box_stride, const int* counts,
@@ -449,7 +393,7 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     const size_t prep_bytes = align_up((size_t)frames * nmax * sizeof(tsm::BoxPrep), 256);
     const size_t mask_bytes = (size_t)frames * nmax * cbmax * sizeof(unsigned long long);
     void* scratch = nullptr;
-    int rc = scratch_get(prep_bytes + mask_bytes, s, &scratch);
+    int rc = tsm_scratch_get(0, prep_bytes + mask_bytes, s, &scratch);
     if (rc != TSM_OK) return rc;
     tsm::BoxPrep* prep = (tsm::BoxPrep*)scratch;
     unsigned long long* mask = (unsigned long long*)((char*)scratch + prep_bytes);
@@ -478,7 +422,7 @@ int pair_matrix_impl(bool iou, int na, const float* a, int nb, const float* b, f
     const size_t pa = align_up((size_t)na * sizeof(tsm::BoxPrep), 256);
     const size_t pb = (size_t)nb * sizeof(tsm::BoxPrep);
     void* scratch = nullptr;
-    int rc = scratch_get(pa + pb, s, &scratch);
+    int rc = tsm_scratch_get(0, pa + pb, s, &scratch);
     if (rc != TSM_OK) return rc;
     tsm::BoxPrep* A = (tsm::BoxPrep*)scratch;
     tsm::BoxPrep* B = (tsm::BoxPrep*)((char*)scratch + pa);

@@ -34,6 +34,65 @@ int* tsm_status_word(cudaStream_t) {
     return g_status[dev];
 }
 
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    int tag = 0;
+    unsigned long long tick = 0;
+};
+// Grow-only device scratch, one buffer per (device, stream, user tag) so that calls on
+// different streams never share a buffer; stream-ordered (cudaMallocAsync), so repeated
+// NMS calls allocate nothing.
+constexpr int kScratchSlots = 16;
+static Scratch g_scratch[kScratchSlots];
+static unsigned long long g_tick = 0;
+static std::mutex g_scratch_mu;
+
+int tsm_scratch_get(int tag, size_t bytes, cudaStream_t s, void** out) {
+    int dev = 0;
+    TSM_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    Scratch* sc = nullptr;
+    for (auto& e : g_scratch)
+        if (e.p && e.dev == dev && e.stream == s && e.tag == tag) sc = &e;
+    if (!sc) {  // empty slot, else evict the least recently used one
+        for (auto& e : g_scratch)
+            if (!e.p && !sc) sc = &e;
+        if (!sc) {
+            sc = &g_scratch[0];
+            for (auto& e : g_scratch)
+                if (e.tick < sc->tick) sc = &e;
+            if (sc->dev == dev) {
+                TSM_CUDA_TRY(cudaFreeAsync(sc->p, sc->stream));
+            } else {
+                int cur = dev;
+                cudaSetDevice(sc->dev);
+                cudaFreeAsync(sc->p, sc->stream);
+                cudaSetDevice(cur);
+            }
+            sc->p = nullptr;
+            sc->cap = 0;
+        }
+        sc->dev = dev;
+        sc->stream = s;
+        sc->tag = tag;
+    }
+    sc->tick = ++g_tick;
+    if (sc->cap < bytes) {
+        if (sc->p) TSM_CUDA_TRY(cudaFreeAsync(sc->p, s));
+        sc->p = nullptr;
+        sc->cap = 0;
+        const size_t want = bytes + bytes / 4;
+        TSM_CUDA_TRY(cudaMallocAsync(&sc->p, want, s));
+        sc->cap = want;
+    }
+    *out = sc->p;
+    return TSM_OK;
+}
+
+
 extern "C" {
 
 const char* tsmdet_version() { return "tsmdet_b200 0.1 (sm_100a)"; }
