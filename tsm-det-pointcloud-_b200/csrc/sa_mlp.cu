@@ -31,6 +31,7 @@ extern "C" int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_fea
     a.out_ctot = out_ctot;
     a.out_c0 = out_c0;
     a.total_rows = (long long)b * m * nsample;
+    a.status = nullptr;
     if (out_c0 < 0 || out_c0 + a.ch[num_layers] > out_ctot) return TSM_ERR_INVALID;
     if (precision == 0) return tsm_sa_mlp_fp32(a, b, (cudaStream_t)stream);
     if (precision == 1) return tsm_sa_mlp_tc(a, b, (cudaStream_t)stream);

@@ -18,6 +18,7 @@ struct SaMlpArgs {
     int n, m, s, c_feat, use_xyz;
     int out_ctot, out_c0;
     long long total_rows;  // B*M*S
+    int* status;           // watchdog word (device) or nullptr
 };
 
 

@@ -1,3 +1,373 @@
-// sa_mlp_tc.cu -- placeholder until the tcgen05 kernel lands in this file.
+// sa_mlp_tc.cu -- fused set-abstraction scale on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Same operator as sa_mlp_fp32.cu (gather -> mask -> [1x1 conv + ReLU]* -> max over nsample, see
+// /root/reference/pcdet/ops/pointnet2/pointnet2_batch/pointnet2_modules.py:1259-1268, 1297-1300),
+// with the contraction in bf16 x bf16 -> fp32 on tcgen05.mma (SASS: UTCHMMA), accumulators in
+// TMEM, and the max-pool fused into the last epilogue.  The only dense contraction on this
+// path, hence the only place tensor cores are used.
+//
+// One CTA = 128 threads = one 128-row tile of (centre, sample) rows, persistent over tiles:
+//   gather   : thread r builds row r of the layer-0 operand in shared memory, straight in the UMMA
+//              K-major "no swizzle" core-matrix layout (8 rows x 16 B cores; row stride 16 B, K-chunk
+//              stride 128 rows x 16 B) -- features come from a bf16 (B,N,Cp) transpose of the input,
+//              so a row is one contiguous run of 16-byte chunks; xyz offsets fill one extra chunk;
+//   layer l  : one thread issues K_l/16 tcgen05.mma (M=128, N=N_l) reading A (activations) and
+//              B (weights, resident in shared memory for the whole kernel) through smem descriptors,
+//              commits to an mbarrier; the 4 warps then read their 32 TMEM lanes (tcgen05.ld
+//              32x32b), add bias, ReLU, repack to bf16 and write the next layer's A operand in place;
+//   last     : bias + ReLU, then max over the S rows of each centre: values are >= 0, so the float
+//              max is an unsigned max on the bit pattern -> ONE redux.sync per channel per warp.
+#include <cuda_bf16.h>
+
 #include "sa_mlp.cuh"
-int tsm_sa_mlp_tc(const tsm::SaMlpArgs&, int, cudaStream_t) { return TSM_ERR_INVALID; }
+
+namespace tsm {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_THREADS = 128;
+constexpr int TC_MAX_LAYERS = 4;
+
+struct TcPlan {
+    int nl;
+    int K[TC_MAX_LAYERS];      // padded input channels of layer l (multiple of 16)
+    int Npad[TC_MAX_LAYERS];   // padded output channels (multiple of 16, 16..256)
+    int w_off[TC_MAX_LAYERS];  // byte offset of layer l's weights in dynamic smem
+    int b_off[TC_MAX_LAYERS];  // byte offset of layer l's bias (fp32)
+    int a_off;                 // activation operand buffer
+    int o_off;                 // pooled output staging (uint32 [Nlast][centres per tile])
+    int smem_bytes;
+    int cp;                    // feature channels padded to 8 (width of the bf16 transpose)
+    int xyz_chunk;             // 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
+    int tmem_cols;             // power of two >= 32
+    int d_off;                 // TMEM column of the odd layers' accumulator (even layers use column 0)
+};
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+    // | base_offset=0 | lbo_mode=0 | layout_type=SWIZZLE_NONE(0) [61,64)
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ uint32_t instr_desc_bf16(int n) {
+    // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6) | a_format BF16=1 [7,10) | b_format BF16=1 [10,13)
+    // | a_major K=0 [15] | b_major K=0 [16] | n_dim N>>3 [17,23) | m_dim M>>4 [24,29)
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(int c, int cp, int n, const float* __restrict__ f,
+                                                             __nv_bfloat16* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float* src = f + (size_t)b * c * n + i;
+    __nv_bfloat16* dst = out + ((size_t)b * n + i) * cp;
+    for (int c0 = 0; c0 < cp; c0 += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ca = c0 + 2 * j, cb = ca + 1;
+            const float a = ca < c ? __ldg(src + (size_t)ca * n) : 0.f;
+            const float bb = cb < c ? __ldg(src + (size_t)cb * n) : 0.f;
+            w[j] = pack_bf16(a, bb);
+        }
+        *reinterpret_cast<uint4*>(dst + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    sa_mlp_tc_kernel(const SaMlpArgs a, const TcPlan pl, const __nv_bfloat16* __restrict__ featT, int num_tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.s, M = a.m;
+    const int cpt = TC_ROWS / S;  // whole centres per tile (S divides 128)
+    const int nl = pl.nl;
+
+    // ---- one-time setup: weights -> bf16 UMMA layout, biases, barrier, TMEM
+    for (int l = 0; l < nl; ++l) {
+        const int K = pl.K[l], Np = pl.Npad[l];
+        const int cin = a.ch[l], cout = a.ch[l + 1];
+        __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(smem + pl.w_off[l]);
+        const float* __restrict__ W = a.w[l];
+        for (int e = tid; e < Np * K; e += TC_THREADS) {
+            const int n = e / K, k = e - n * K;
+            float v = 0.f;
+            if (n < cout) {
+                int src = -1;
+                if (l == 0) {
+                    // operand channel order: [features 0..C-1 | pad to cp | dx,dy,dz | pad]; the weights'
+                    // input order is the reference's [dx,dy,dz, features...] (pointnet2_utils.py:523)
+                    if (k < a.c_feat)
+                        src = (a.use_xyz ? 3 : 0) + k;
+                    else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
+                        src = k - pl.xyz_chunk * 8;
+                } else if (k < cin) {
+                    src = k;
+                }
+                if (src >= 0) v = __ldg(W + (size_t)n * cin + src);
+            }
+            ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        }
+        float* bs = reinterpret_cast<float*>(smem + pl.b_off[l]);
+        for (int e = tid; e < Np; e += TC_THREADS) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&mma_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)pl.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t a_smem = smem_u32(smem + pl.a_off);
+    unsigned char* a_ptr = smem + pl.a_off;
+    uint32_t* omax = reinterpret_cast<uint32_t*>(smem + pl.o_off);
+    uint32_t phase = 0;
+    const int Nlast = pl.Npad[nl - 1];
+    const int cout_last = a.ch[nl];
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---- gather: row `tid`
+        {
+            const long long g = (long long)tile * TC_ROWS + tid;
+            const bool rv = g < a.total_rows;
+            const long long cpi = rv ? g / S : 0;
+            const int b = (int)(cpi / M);
+            bool live = rv;
+            int id = 0;
+            if (rv) {
+                id = __ldg(a.idx + g);
+                if (a.idx_cnt && __ldg(a.idx_cnt + cpi) <= 0) live = false;  // empty ball -> zero input row
+            }
+            const int nchunk0 = pl.K[0] >> 3;
+            const int fchunks = pl.cp >> 3;
+            const uint4* frow = reinterpret_cast<const uint4*>(featT + ((size_t)b * a.n + id) * pl.cp);
+            for (int kc = 0; kc < nchunk0; ++kc) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (live) {
+                    if (kc < fchunks) {
+                        v = __ldg(frow + kc);
+                    } else if (kc == pl.xyz_chunk) {
+                        const float* p = a.xyz + ((size_t)b * a.n + id) * 3;
+                        const float* q = a.new_xyz + (size_t)cpi * 3;
+                        const float dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
+                        const float dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+                        const float dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+                        v.x = pack_bf16(dx, dy);
+                        v.y = pack_bf16(dz, 0.f);
+                    }
+                }
+                *reinterpret_cast<uint4*>(a_ptr + (size_t)kc * (TC_ROWS * 16) + tid * 16) = v;
+            }
+            if (S > 32)
+                for (int e = tid; e < Nlast * cpt; e += TC_THREADS) omax[e] = 0u;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+
+        for (int l = 0; l < nl; ++l) {
+            const int K = pl.K[l], Np = pl.Npad[l];
+            const uint32_t d_tmem = tmem_base + (uint32_t)((l & 1) ? pl.d_off : 0);
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
+                const uint32_t idesc = instr_desc_bf16(Np);
+                const uint32_t a_lbo = TC_ROWS * 16, b_lbo = (uint32_t)Np * 16;
+                for (int kk = 0; kk < (K >> 4); ++kk) {
+                    const uint64_t ad = smem_desc(a_smem + (uint32_t)kk * 2u * a_lbo, a_lbo, 128);
+                    const uint64_t bd = smem_desc(w_smem + (uint32_t)kk * 2u * b_lbo, b_lbo, 128);
+                    umma_bf16(d_tmem, ad, bd, idesc, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&mma_bar));
+            }
+            {
+                const uint32_t bar = smem_u32(&mma_bar);
+                if (!mbar_try_wait_cta(bar, phase)) {
+                    const long long t0 = clock64();
+                    while (!mbar_try_wait_cta(bar, phase))
+                        if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+                }
+                phase ^= 1u;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
+            const uint32_t t_row = d_tmem + ((uint32_t)(warp * 32) << 16);
+            if (l + 1 < nl) {
+                // bias + ReLU -> bf16 -> next layer's A operand (written over the consumed one)
+                for (int c0 = 0; c0 < Np; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + (uint32_t)c0, v);
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float x0 = fmaxf(__uint_as_float(v[2 * j]) + bs[c0 + 2 * j], 0.f);
+                        const float x1 = fmaxf(__uint_as_float(v[2 * j + 1]) + bs[c0 + 2 * j + 1], 0.f);
+                        w[j] = pack_bf16(x0, x1);
+                    }
+                    unsigned char* dst = a_ptr + (size_t)(c0 >> 3) * (TC_ROWS * 16) + tid * 16;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(dst + TC_ROWS * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            } else {
+                // bias + ReLU + max over the S rows of each centre
+                const int ci = tid / S;  // centre within the tile
+                for (int c0 = 0; c0 < Np; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f);
+                        uint32_t u = __float_as_uint(x);
+                        if (S >= 32) {
+                            u = __reduce_max_sync(FULL, u);
+                            if (lane == j) {
+                                if (S == 32)
+                                    omax[(c0 + j) * cpt + ci] = u;
+                                else
+                                    atomicMax(&omax[(c0 + j) * cpt + ci], u);
+                            }
+                        } else {
+                            for (int o = S >> 1; o >= 1; o >>= 1) u = max(u, __shfl_xor_sync(FULL, u, o));
+                            if ((lane & (S - 1)) == 0) omax[(c0 + j) * cpt + ci] = u;
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                // pooled tile -> out[b, out_c0 + c, p]; consecutive threads write consecutive centres
+                const long long cbase = (long long)tile * cpt;
+                const long long ctot = a.total_rows / S;
+                for (int e = tid; e < cout_last * cpt; e += TC_THREADS) {
+                    const int c = e / cpt, cc = e - c * cpt;
+                    const long long cg = cbase + cc;
+                    if (cg >= ctot) continue;
+                    const int b2 = (int)(cg / M);
+                    const int p2 = (int)(cg - (long long)b2 * M);
+                    a.out[((size_t)b2 * a.out_ctot + a.out_c0 + c) * M + p2] = __uint_as_float(omax[c * cpt + cc]);
+                }
+                __syncthreads();  // omax / A buffer are reused by the next tile
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)pl.tmem_cols)
+                     : "memory");
+    }
+}
+
+}  // namespace tsm
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
+    using namespace tsm;
+    const int S = a.s;
+    if (S > TC_ROWS || (TC_ROWS % S) != 0 || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile
+    if (a.num_layers < 1 || a.num_layers > TC_MAX_LAYERS) return TSM_ERR_INVALID;
+    TcPlan pl;
+    pl.nl = a.num_layers;
+    pl.cp = round_up(a.c_feat, 8);
+    pl.xyz_chunk = a.use_xyz ? (pl.cp >> 3) : -1;
+    pl.K[0] = round_up(pl.cp + (a.use_xyz ? 8 : 0), 16);
+    int off = 0, kmax = pl.K[0], nmax = 0;
+    for (int l = 0; l < pl.nl; ++l) {
+        pl.Npad[l] = round_up(a.ch[l + 1], 16);
+        if (pl.Npad[l] > 256) return TSM_ERR_INVALID;
+        if (l > 0) pl.K[l] = pl.Npad[l - 1];
+        kmax = pl.K[l] > kmax ? pl.K[l] : kmax;
+        nmax = pl.Npad[l] > nmax ? pl.Npad[l] : nmax;
+        pl.w_off[l] = off;
+        off += pl.Npad[l] * pl.K[l] * 2;
+    }
+    if (kmax > 512) return TSM_ERR_INVALID;
+    for (int l = 0; l < pl.nl; ++l) {
+        pl.b_off[l] = off;
+        off += pl.Npad[l] * 4;
+    }
+    off = round_up(off, 128);
+    pl.a_off = off;
+    off += TC_ROWS * kmax * 2;
+    off = round_up(off, 16);
+    pl.o_off = off;
+    off += pl.Npad[pl.nl - 1] * (TC_ROWS / S) * 4;
+    pl.smem_bytes = off;
+    if (pl.smem_bytes > 227 * 1024 - 64) return TSM_ERR_INVALID;
+    // layer l accumulates at TMEM column (l & 1) * d_off, so an epilogue never races the next MMA
+    pl.d_off = pl.nl > 1 ? round_up(nmax, 32) : 0;
+    pl.tmem_cols = 32;
+    while (pl.tmem_cols < pl.d_off + nmax) pl.tmem_cols <<= 1;
+    if (pl.tmem_cols > 512) return TSM_ERR_INVALID;
+
+    // bf16 (B,N,Cp) transpose of the features
+    __nv_bfloat16* featT = nullptr;
+    if (a.c_feat > 0) {
+        void* p = nullptr;
+        const size_t bytes = (size_t)b * a.n * pl.cp * sizeof(__nv_bfloat16);
+        int rc = tsm_scratch_get(1, bytes, stream, &p);
+        if (rc != TSM_OK) return rc;
+        featT = (__nv_bfloat16*)p;
+        dim3 grid((unsigned)divup(a.n, 256), (unsigned)b);
+        transpose_bf16_kernel<<<grid, 256, 0, stream>>>(a.c_feat, pl.cp, a.n, a.features, featT);
+        TSM_LAUNCH_CHECK();
+    }
+    const long long tiles = (a.total_rows + TC_ROWS - 1) / TC_ROWS;
+    if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
+    TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    int occ = (227 * 1024) / (pl.smem_bytes + 2048);
+    const int tmem_occ = 512 / pl.tmem_cols;
+    if (occ > tmem_occ) occ = tmem_occ;
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    long long grid = (long long)tsm_num_sms() * occ;
+    if (grid > tiles) grid = tiles;
+    SaMlpArgs args = a;
+    args.status = tsm_status_word(stream);
+    sa_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, (int)tiles);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
