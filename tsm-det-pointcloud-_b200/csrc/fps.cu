@@ -48,36 +48,72 @@ struct __align__(16) FpsRec {
 static_assert(sizeof(FpsRec) == 32, "FpsRec must be 32 bytes");
 
 constexpr uint32_t kRecBytes = 20;  // u, rank, x, y (v4) + z (b32)
+constexpr int kMaxRecs = 512;       // warps per cluster (cluster size x warps per CTA)
 
 __device__ __forceinline__ void wait_records(uint32_t bar, uint32_t phase, int* status) {
-    if (mbar_try_wait_cluster(bar, phase)) return;
+    if (mbar_try_wait_cta(bar, phase)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, phase)) {
+    while (!mbar_try_wait_cta(bar, phase)) {
         if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
     }
 }
 
-// (u desc, rank asc) warp argmax; returns true in exactly one lane (the winner).
-__device__ __forceinline__ bool warp_pick(uint32_t u, uint32_t rk, uint32_t& wu, uint32_t& wrk) {
+// (u desc, rank asc) argmax across the warp.  Returns the winning lane; wu / wrk are warp-uniform.
+// The common case (a unique maximum) costs one redux + one ballot.
+__device__ __forceinline__ int warp_pick(uint32_t u, uint32_t rk, uint32_t& wu, uint32_t& wrk) {
     wu = __reduce_max_sync(FULL, u);
+    const unsigned tie = __ballot_sync(FULL, u == wu);
+    if (__popc(tie) == 1) {
+        const int wl = __ffs(tie) - 1;
+        wrk = __shfl_sync(FULL, rk, wl);
+        return wl;
+    }
     wrk = __reduce_min_sync(FULL, (u == wu) ? rk : 0xffffffffu);
-    return (u == wu) && (rk == wrk);
+    return __ffs(__ballot_sync(FULL, u == wu && rk == wrk)) - 1;
 }
 
-template <int T, int P, bool CLUSTER, bool WEIGHTED, bool SMEM>
+// Per-thread argmax over P register slots as a balanced tree (short dependency chains; one warp per
+// SM sub-partition has to hide its own latency).  Ties keep the lower slot = lower k, as the
+// reference thread's ascending strict-> scan does.
+template <int P>
+__device__ __forceinline__ void slot_argmax(const float (&v)[P], float& best, int& bp) {
+    float val[P];
+    int idx[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        val[p] = v[p];
+        idx[p] = p;
+    }
+#pragma unroll
+    for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+        for (int p = 0; p + w < P; p += 2 * w) {
+            const bool take = val[p + w] > val[p];  // strict: the lower slot wins ties
+            val[p] = take ? val[p + w] : val[p];
+            idx[p] = take ? idx[p + w] : idx[p];
+        }
+    }
+    best = val[0];
+    bp = idx[0];
+}
+
+// One cluster (1..16 CTAs) per cloud.  No CTA barrier inside the loop: every WARP publishes its
+// own candidate to every CTA of the cluster (st.async into recs[parity][warp id in cluster] +
+// complete_tx on that CTA's mbarrier), and every warp reduces the R = csize * NW records itself.
+template <int T, int P, bool WEIGHTED, bool SMEM>
 __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     constexpr int NW = T / 32;
-    __shared__ FpsRec slots[CLUSTER ? 1 : 2][NW];
-    __shared__ FpsRec recs[2][16];
     __shared__ __align__(8) uint64_t mbar[2];
-    extern __shared__ float dyn_xyz[];  // SMEM variant: 3 * P * T floats (SoA planes)
+    // dynamic smem: recs[2][R] (32 B each), then 3 * P * T floats: SoA planes of this CTA's points
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t crank = 0, csize = 1;
-    if (CLUSTER) {
-        crank = cluster_ctarank();
-        csize = cluster_nctarank();
-    }
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t csize = cluster_nctarank();
+    const int R = (int)csize * NW;  // records per iteration
+    FpsRec* recs0 = reinterpret_cast<FpsRec*>(dyn_smem);
+    FpsRec* recs1 = recs0 + R;
+    float* dyn_xyz = reinterpret_cast<float*>(recs1 + R);
     const int cloud = blockIdx.x / csize;
     const int L = a.log2bs;
     const int bs = 1 << L;
@@ -89,12 +125,10 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     const uint32_t lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
     const uint32_t rbase = ((L == 0) ? 0u : __brev((uint32_t)r)) | (uint32_t)(q * P);
 
-    if (CLUSTER) {
-        if (tid == 0) {
-            mbar_init(smem_u32(&mbar[0]), 1);
-            mbar_init(smem_u32(&mbar[1]), 1);
-            mbar_fence_init_cluster();
-        }
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
+        mbar_fence_init_cluster();
     }
 
     float px[SMEM ? 1 : P], py[SMEM ? 1 : P], pz[SMEM ? 1 : P];
@@ -114,11 +148,10 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
             d0 = a.temp ? a.temp[(size_t)cloud * n + k] : 1e10f;
             if (WEIGHTED) w0 = __ldg(a.weights + (size_t)cloud * n + k);
         }
-        if (SMEM) {
-            sx[p * T + tid] = x;
-            sy[p * T + tid] = y;
-            sz[p * T + tid] = z;
-        } else {
+        sx[p * T + tid] = x;  // every thread only ever reads back its own slots
+        sy[p * T + tid] = y;
+        sz[p * T + tid] = z;
+        if (!SMEM) {
             px[p] = x;
             py[p] = y;
             pz[p] = z;
@@ -131,25 +164,28 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     int* __restrict__ idxs = a.idxs + (size_t)cloud * m;
     if (!WEIGHTED && g == 0 && m > 0) idxs[0] = 0;
 
-    if (CLUSTER) cluster_sync_all();  // peers' mbarriers are initialised past this point
+    // destination of this warp's record in CTA `lane` (lanes < csize send): slot = cluster warp id
+    const uint32_t my_slot = crank * NW + warp;
+    const uint32_t peer = (uint32_t)lane < csize ? (uint32_t)lane : 0u;
+    const uint32_t dst_rec0 = mapa_u32(smem_u32(&recs0[my_slot]), peer);
+    const uint32_t dst_rec1 = mapa_u32(smem_u32(&recs1[my_slot]), peer);
+    const uint32_t dst_bar0 = mapa_u32(smem_u32(&mbar[0]), peer);
+    const uint32_t dst_bar1 = mapa_u32(smem_u32(&mbar[1]), peer);
+
+    cluster_sync_all();  // peers' mbarriers are initialised past this point
 
     int it = 0;
     for (int j = WEIGHTED ? 0 : 1; j < m; ++j, ++it) {
         const int par = it & 1;
-        if (CLUSTER && tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), csize * kRecBytes);
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), (uint32_t)R * kRecBytes);
 
-        // ---- per-thread scan: first strict maximum in ascending k, as the reference thread does
-        float best = -1.f;
-        int bp = 0;
+        // ---- per-thread: update the running min-distance of every owned point, then argmax
+        float score[P];
         if (WEIGHTED && j == 0) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const float v = wf[p] + 0.0f;  // canonicalise -0.0
-                const bool valid = md[p] != -2.f;
-                if (valid && v > best) {
-                    best = v;
-                    bp = p;
-                }
+                score[p] = (md[p] != -2.f && v > -1.f) ? v : -2.f;
             }
         } else {
 #pragma unroll
@@ -160,95 +196,62 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
                 const float d = sqdist3(x1, y1, z1, X, Y, Z);
                 const float mm = fminf(d, md[p]);  // invalid slots stay at -2
                 md[p] = mm;
-                float score = mm;
-                if (WEIGHTED) score = (mm == -2.f) ? -2.f : (float)((double)mm * fmax((double)wf[p], 1e-12));
-                if (score > best) {
-                    best = score;
-                    bp = p;
-                }
+                score[p] = mm;
+                if (WEIGHTED) score[p] = (mm == -2.f) ? -2.f : (float)((double)mm * fmax((double)wf[p], 1e-12));
             }
         }
-        float bx = 0.f, by = 0.f, bz = 0.f;
-        if (SMEM) {
-            bx = sx[bp * T + tid];
-            by = sy[bp * T + tid];
-            bz = sz[bp * T + tid];
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; ++p)
-                if (p == bp) {
-                    bx = px[p];
-                    by = py[p];
-                    bz = pz[p];
-                }
-        }
-        const uint32_t u = (best > -1.f) ? f32_ordered(best) : 0u;
+        float best;
+        int bp;
+        slot_argmax<P>(score, best, bp);
+        // candidate coordinates: read back this thread's own best slot (conflict-free planes)
+        const float bx = sx[bp * T + tid], by = sy[bp * T + tid], bz = sz[bp * T + tid];
+        const uint32_t u = (best > -1.f) ? f32_ordered(best) : 0u;  // the reference starts from best = -1
         const uint32_t rk = rbase + (uint32_t)bp;
 
-        // ---- warp argmax, one record per warp
+        // ---- warp argmax; the warp's record goes to every CTA of the cluster
         uint32_t wu, wrk;
-        const int sb = CLUSTER ? 0 : par;
-        if (warp_pick(u, rk, wu, wrk)) {
-            FpsRec& s = slots[sb][warp];
-            *reinterpret_cast<uint4*>(&s) = make_uint4(u, rk, __float_as_uint(bx), __float_as_uint(by));
-            s.z = bz;
+        const int wl = warp_pick(u, rk, wu, wrk);
+        const float wx = __shfl_sync(FULL, bx, wl), wy = __shfl_sync(FULL, by, wl), wz = __shfl_sync(FULL, bz, wl);
+        if ((uint32_t)lane < csize) {
+            const uint32_t dr = par ? dst_rec1 : dst_rec0, db = par ? dst_bar1 : dst_bar0;
+            st_async_v4(dr, db, wu, wrk, __float_as_uint(wx), __float_as_uint(wy));
+            st_async_b32(dr + 16, db, __float_as_uint(wz));
         }
-        __syncthreads();
 
+        // ---- all R records of this iteration
+        wait_records(smem_u32(&mbar[par]), (uint32_t)((it >> 1) & 1), a.status);
+        uint32_t cu = 0u, crk = 0xffffffffu;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        const FpsRec* recs = par ? recs1 : recs0;
+        for (int s = lane; s < R; s += 32) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&recs[s]);
+            if (v.x > cu || (v.x == cu && v.y < crk)) {
+                cu = v.x;
+                crk = v.y;
+                cx = __uint_as_float(v.z);
+                cy = __uint_as_float(v.w);
+                cz = recs[s].z;
+            }
+        }
         uint32_t gu, grk;
-        if (CLUSTER) {
-            if (warp == 0) {
-                const uint32_t su = (lane < NW) ? slots[0][lane].u : 0u;
-                const uint32_t sr = (lane < NW) ? slots[0][lane].rank : 0xffffffffu;
-                uint32_t cu, crk;
-                const bool mine = warp_pick(su, sr, cu, crk) && (lane < NW);
-                const int wl = __ffs(__ballot_sync(FULL, mine)) - 1;
-                if (lane < (int)csize) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(&slots[0][wl]);
-                    const uint32_t zz = __float_as_uint(slots[0][wl].z);
-                    const uint32_t dst = mapa_u32(smem_u32(&recs[par][crank]), (uint32_t)lane);
-                    const uint32_t bar = mapa_u32(smem_u32(&mbar[par]), (uint32_t)lane);
-                    st_async_v4(dst, bar, v.x, v.y, v.z, v.w);
-                    st_async_b32(dst + 16, bar, zz);
-                }
-            }
-            wait_records(smem_u32(&mbar[par]), (uint32_t)((it >> 1) & 1), a.status);
-            gu = 0u;
-            grk = 0xffffffffu;
-            int bc = 0;
-            for (int c = 0; c < (int)csize; ++c) {
-                const uint4 v = *reinterpret_cast<const uint4*>(&recs[par][c]);
-                const bool better = (v.x > gu) || (v.x == gu && v.y < grk);
-                if (better) {
-                    gu = v.x;
-                    grk = v.y;
-                    x1 = __uint_as_float(v.z);
-                    y1 = __uint_as_float(v.w);
-                    bc = c;
-                }
-            }
-            z1 = recs[par][bc].z;
-        } else {
-            const uint32_t su = (lane < NW) ? slots[par][lane].u : 0u;
-            const uint32_t sr = (lane < NW) ? slots[par][lane].rank : 0xffffffffu;
-            const bool mine = warp_pick(su, sr, gu, grk) && (lane < NW);
-            const int wl = __ffs(__ballot_sync(FULL, mine)) - 1;
-            const uint4 v = *reinterpret_cast<const uint4*>(&slots[par][wl]);
-            x1 = __uint_as_float(v.z);
-            y1 = __uint_as_float(v.w);
-            z1 = slots[par][wl].z;
-        }
+        const int gl = warp_pick(cu, crk, gu, grk);
+        x1 = __shfl_sync(FULL, cx, gl);
+        y1 = __shfl_sync(FULL, cy, gl);
+        z1 = __shfl_sync(FULL, cz, gl);
 
-        int k = 0;
         if (gu == 0u) {  // no eligible candidate anywhere: the reference yields index 0
             x1 = __ldg(xyz + 0);
             y1 = __ldg(xyz + 1);
             z1 = __ldg(xyz + 2);
-        } else {
-            const uint32_t rr = (L == 0) ? 0u : __brev(grk & ~lowmask);
-            k = (int)(rr + ((grk & lowmask) << L));
         }
-        if (g == 0) idxs[j] = k;
+        if (g == 0) {
+            int k = 0;
+            if (gu != 0u) {
+                const uint32_t rr = (L == 0) ? 0u : __brev(grk & ~lowmask);
+                k = (int)(rr + ((grk & lowmask) << L));
+            }
+            idxs[j] = k;
+        }
     }
 
     if (a.temp) {
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
             if (k < n) a.temp[(size_t)cloud * n + k] = md[p];
         }
     }
-    if (CLUSTER) cluster_sync_all();  // no CTA leaves while a peer may still address its smem
+    cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,9 +314,9 @@ __global__ void __launch_bounds__(1024, 1)
             }
         }
         uint32_t wu, wrk;
-        if (warp_pick(u, rk, wu, wrk)) {
-            slots[par][warp].u = u;
-            slots[par][warp].rank = rk;
+        if (warp_pick(u, rk, wu, wrk) == lane) {
+            slots[par][warp].u = wu;
+            slots[par][warp].rank = wrk;
         }
         __syncthreads();
         uint32_t gu, grk;
@@ -328,11 +331,12 @@ __global__ void __launch_bounds__(1024, 1)
 }
 
 // ------------------------------------------------------------------------------------------
-template <int T, int P, bool CLUSTER, bool WEIGHTED, bool SMEM>
-static int launch_fps(const FpsArgs& a, int b, int csize, cudaStream_t stream) {
-    auto kern = fps_kernel<T, P, CLUSTER, WEIGHTED, SMEM>;
-    const size_t dyn = SMEM ? (size_t)3 * P * T * sizeof(float) : 0;
-    if (dyn > 0) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+template <int T, int P, bool WEIGHTED, bool SMEM>
+static int launch_fps(const FpsArgs& a, int b, int csize, cudaStream_t stream, int* max_clusters) {
+    auto kern = fps_kernel<T, P, WEIGHTED, SMEM>;
+    const size_t dyn = (size_t)3 * P * T * sizeof(float) + (size_t)2 * csize * (T / 32) * sizeof(FpsRec);
+    if (dyn > 227 * 1024 - 64) return TSM_ERR_INVALID;
+    if (dyn > 40 * 1024) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     if (csize > 8) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * csize));
@@ -340,28 +344,31 @@ static int launch_fps(const FpsArgs& a, int b, int csize, cudaStream_t stream) {
     cfg.dynamicSmemBytes = dyn;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    if (CLUSTER) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)csize;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters) {  // query only: how many clusters of this shape are co-resident
+        cudaError_t e = cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            *max_clusters = 0;
+        }
+        return TSM_OK;
     }
     TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
     return TSM_OK;
 }
 
 template <bool WEIGHTED>
-static int dispatch_fps(const FpsArgs& a, int b, int csize, int T, int P, bool smem, cudaStream_t s) {
-#define FPS_CASE(TT, PP)                                                                             \
-    if (T == TT && P == PP && !smem)                                                                 \
-        return csize > 1 ? launch_fps<TT, PP, true, WEIGHTED, false>(a, b, csize, s)                 \
-                         : launch_fps<TT, PP, false, WEIGHTED, false>(a, b, csize, s);
-#define FPS_CASE_SMEM(TT, PP)                                                                        \
-    if (T == TT && P == PP && smem)                                                                  \
-        return csize > 1 ? launch_fps<TT, PP, true, WEIGHTED, true>(a, b, csize, s)                  \
-                         : launch_fps<TT, PP, false, WEIGHTED, true>(a, b, csize, s);
+static int dispatch_fps(const FpsArgs& a, int b, int csize, int T, int P, bool smem, cudaStream_t s,
+                        int* max_clusters = nullptr) {
+#define FPS_CASE(TT, PP) \
+    if (T == TT && P == PP && !smem) return launch_fps<TT, PP, WEIGHTED, false>(a, b, csize, s, max_clusters);
+#define FPS_CASE_SMEM(TT, PP) \
+    if (T == TT && P == PP && smem) return launch_fps<TT, PP, WEIGHTED, true>(a, b, csize, s, max_clusters);
     FPS_CASE(128, 1) FPS_CASE(128, 2) FPS_CASE(128, 4) FPS_CASE(128, 8) FPS_CASE(128, 16) FPS_CASE(128, 32)
     FPS_CASE(256, 1) FPS_CASE(256, 2) FPS_CASE(256, 4) FPS_CASE(256, 8) FPS_CASE(256, 16) FPS_CASE(256, 32)
     FPS_CASE(512, 1) FPS_CASE(512, 2) FPS_CASE(512, 4) FPS_CASE(512, 8) FPS_CASE(512, 16)
@@ -392,6 +399,10 @@ struct FpsPlan {
 
 // Pick cluster size / block size / points per thread.  Overridable for tuning with
 // TSMDET_FPS_CLUSTER / TSMDET_FPS_THREADS (values outside the valid set are ignored).
+// Measured on B200 (profiles/r01_fps_sweep.txt): per-iteration time is a latency chain, so the
+// fewest warps that still hold the cloud in registers win -- 128-thread CTAs with up to 16 points
+// per thread, and the widest cluster whose B instances are all co-resident (a second wave of
+// clusters would double the time).
 static bool plan_for(int c, int want_t, int bs, int J, FpsPlan* out) {
     static const int Ts[4] = {128, 256, 512, 1024};
     static const int Ps[6] = {1, 2, 4, 8, 16, 32};
@@ -400,7 +411,7 @@ static bool plan_for(int c, int want_t, int bs, int J, FpsPlan* out) {
         const int T = Ts[ti];
         if (want_t && T != want_t) continue;
         const long G = (long)c * T;
-        if (G < bs) continue;
+        if (G < bs || G / 32 > tsm::kMaxRecs) continue;
         const int need = tsm::divup(J, (int)(G / bs));
         for (int pi = 0; pi < 6; ++pi) {
             const int P = Ps[pi];
@@ -411,7 +422,7 @@ static bool plan_for(int c, int want_t, int bs, int J, FpsPlan* out) {
                 if (!smem) break;
             }
             const FpsPlan pl = {c, T, P, smem};
-            if (P <= 8 && !smem) {  // smallest block that keeps <= 8 points per thread
+            if (P <= 16 && !smem) {  // smallest block that keeps <= 16 points per thread
                 *out = pl;
                 return true;
             }
@@ -426,26 +437,55 @@ static bool plan_for(int c, int want_t, int bs, int J, FpsPlan* out) {
     return false;
 }
 
-static bool plan_fps(int b, int n, int log2bs, FpsPlan* out) {
+static int co_resident_clusters(const FpsPlan& pl, bool weighted) {
+    tsm::FpsArgs dummy = {};
+    int n = 0;
+    if (weighted)
+        tsm::dispatch_fps<true>(dummy, 1, pl.csize, pl.T, pl.P, pl.smem, nullptr, &n);
+    else
+        tsm::dispatch_fps<false>(dummy, 1, pl.csize, pl.T, pl.P, pl.smem, nullptr, &n);
+    return n;
+}
+
+// occupancy == nullptr: host-only planning (no CUDA calls; used by tsmdet_fps_plan without a GPU)
+static bool plan_fps(int b, int n, int log2bs, bool weighted, bool query_occupancy, FpsPlan* out) {
     const int bs = 1 << log2bs;
     const int J = tsm::divup(n, bs);
     const int sms = tsm_num_sms();
     int cmax = 1;
     while (cmax * 2 <= 8 && b * cmax * 2 <= sms) cmax *= 2;
-    // a 16-CTA (non-portable) cluster only when a portable one cannot hold the cloud
     int want_c = 0, want_t = 0;
     if (const char* e = getenv("TSMDET_FPS_CLUSTER")) want_c = atoi(e);
     if (const char* e = getenv("TSMDET_FPS_THREADS")) want_t = atoi(e);
     if (want_t != 128 && want_t != 256 && want_t != 512 && want_t != 1024) want_t = 0;
+    const bool forced = (want_c == 1 || want_c == 2 || want_c == 4 || want_c == 8 || want_c == 16);
     int order[8], no = 0;
-    if (want_c == 1 || want_c == 2 || want_c == 4 || want_c == 8 || want_c == 16) order[no++] = want_c;
+    if (forced) order[no++] = want_c;
     for (int c = cmax; c >= 1; c >>= 1) order[no++] = c;
-    for (int c = cmax * 2; c <= 16; c <<= 1) order[no++] = c;  // too big for fewer CTAs
-    for (int oi = 0; oi < no && oi < 8; ++oi)
-        if (plan_for(order[oi], want_t, bs, J, out)) return true;
-    if (want_t) {
-        for (int oi = 0; oi < no && oi < 8; ++oi)
-            if (plan_for(order[oi], 0, bs, J, out)) return true;
+    for (int c = cmax * 2; c <= 16; c <<= 1) order[no++] = c;  // a portable cluster cannot hold the cloud
+    FpsPlan first = {0, 0, 0, false};
+    for (int pass = 0; pass < 2; ++pass) {
+        const int wt = pass == 0 ? want_t : 0;
+        for (int oi = 0; oi < no && oi < 8; ++oi) {
+            FpsPlan pl;
+            if (!plan_for(order[oi], wt, bs, J, &pl)) continue;
+            if (!first.T) first = pl;
+            if (!query_occupancy || (forced && oi == 0)) {
+                *out = pl;
+                return true;
+            }
+            // single wave: all b clusters resident at once (or nothing smaller can do better)
+            const int fit = co_resident_clusters(pl, weighted);
+            if (fit >= b || (fit > 0 && pl.csize == 1)) {
+                *out = pl;
+                return true;
+            }
+        }
+        if (!want_t) break;
+    }
+    if (first.T) {
+        *out = first;
+        return true;
     }
     return false;
 }
@@ -464,7 +504,7 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
     a.log2bs = ref_log2_block(n);
     a.status = tsm_status_word(stream);
     FpsPlan pl;
-    if (!plan_fps(b, n, a.log2bs, &pl)) return TSM_ERR_INVALID;
+    if (!plan_fps(b, n, a.log2bs, weights != nullptr, true, &pl)) return TSM_ERR_INVALID;
     if (weights) return tsm::dispatch_fps<true>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
     return tsm::dispatch_fps<false>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
 }
@@ -473,7 +513,10 @@ extern "C" {
 
 int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread, int* smem_xyz) {
     FpsPlan pl;
-    if (n <= 0 || !plan_fps(b, n, ref_log2_block(n), &pl)) return TSM_ERR_INVALID;
+    int ndev = 0;
+    const bool gpu = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+    if (!gpu) cudaGetLastError();
+    if (n <= 0 || !plan_fps(b, n, ref_log2_block(n), false, gpu, &pl)) return TSM_ERR_INVALID;
     if (csize) *csize = pl.csize;
     if (threads) *threads = pl.T;
     if (pts_per_thread) *pts_per_thread = pl.P;

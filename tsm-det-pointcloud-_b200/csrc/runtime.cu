@@ -64,15 +64,7 @@ int tsm_scratch_get(int tag, size_t bytes, cudaStream_t s, void** out) {
             sc = &g_scratch[0];
             for (auto& e : g_scratch)
                 if (e.tick < sc->tick) sc = &e;
-            if (sc->dev == dev) {
-                TSM_CUDA_TRY(cudaFreeAsync(sc->p, sc->stream));
-            } else {
-                int cur = dev;
-                cudaSetDevice(sc->dev);
-                cudaFreeAsync(sc->p, sc->stream);
-                cudaSetDevice(cur);
-            }
-            sc->p = nullptr;
+            sc->p = nullptr;  // retired (see below), never freed
             sc->cap = 0;
         }
         sc->dev = dev;
@@ -81,7 +73,7 @@ int tsm_scratch_get(int tag, size_t bytes, cudaStream_t s, void** out) {
     }
     sc->tick = ++g_tick;
     if (sc->cap < bytes) {
-        if (sc->p) TSM_CUDA_TRY(cudaFreeAsync(sc->p, s));
+        // The outgrown buffer is RETIRED, not freed: a captured CUDA graph may still hold its address.
         sc->p = nullptr;
         sc->cap = 0;
         const size_t want = bytes + bytes / 4;

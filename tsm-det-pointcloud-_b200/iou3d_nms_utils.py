@@ -89,20 +89,27 @@ def nms_normal_gpu(boxes, scores, thresh, **kwargs):
 
 
 @torch.no_grad()
-def nms_gpu_batch(boxes, scores, thresh, counts=None, normal: bool = False):
+def nms_gpu_batch(boxes, scores, thresh, counts=None, normal: bool = False, presorted: bool = False):
     """Device-resident NMS over a batch of frames -- no host synchronisation.
 
     boxes (F,N,>=7), scores (F,N) [padded entries should carry -inf], counts (F,) int32 valid boxes per
-    frame or None.  Returns (selected (F,N) int64: original indices of the kept boxes in score order,
-    padded with -1; num_keep (F,) int32)."""
+    frame or None; presorted=True promises each frame is already in descending score order.  Returns
+    (selected (F,N) int64: original indices of the kept boxes in score order, padded with -1;
+    num_keep (F,) int32)."""
     f, n = scores.shape
-    order = scores.sort(1, descending=True)[1]
-    sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, boxes.size(2))).contiguous()
+    if presorted:
+        order = None
+        sorted_boxes = boxes.contiguous()
+    else:
+        order = scores.sort(1, descending=True)[1]
+        sorted_boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, boxes.size(2))).contiguous()
     keep = torch.empty((f, max(n, 1)), dtype=torch.int64, device=boxes.device)
     num = torch.zeros((f,), dtype=torch.int32, device=boxes.device)
     call("tsmdet_nms_normal_batch" if normal else "tsmdet_nms_batch", f, n, ptr(sorted_boxes), sorted_boxes.size(2),
          ptr(counts), float(thresh), ptr(keep), ptr(num), stream_ptr(boxes.device))
     ar = torch.arange(n, device=boxes.device).unsqueeze(0)
     valid = ar < num.unsqueeze(1)
-    sel = torch.gather(order, 1, torch.where(valid, keep[:, :n], torch.zeros_like(keep[:, :n])))
+    sel = torch.where(valid, keep[:, :n], torch.zeros_like(keep[:, :n]))
+    if order is not None:
+        sel = torch.gather(order, 1, sel)
     return torch.where(valid, sel, torch.full_like(sel, -1)), num
