@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "2")),
+                    help="steps kept in flight (each on its own stream / CUDA graph / buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="per-kernel CUDA-event breakdown to stderr")
     args = ap.parse_args()
@@ -190,24 +192,24 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from tsmdet_b200 import _lib
-    from tsmdet_b200.pipeline import SABackboneNMS
+    from tsmdet_b200.pipeline import PipelinedRunner
 
+    depth = max(1, args.depth)
+    xyz_np, feats_np, boxes_np, scores_np = make_inputs(FRAMES_PER_GPU, seed=1000 * rank)
+    h = [torch.from_numpy(a).pin_memory() for a in (xyz_np, feats_np, boxes_np, scores_np)]
+    d0 = [t.to(dev) for t in h]
     try:
-        engine = SABackboneNMS(precision=args.precision).to(dev)
-        xyz_np, feats_np, boxes_np, scores_np = make_inputs(FRAMES_PER_GPU, seed=1000 * rank)
-        h = [torch.from_numpy(a).pin_memory() for a in (xyz_np, feats_np, boxes_np, scores_np)]
-        d = [t.to(dev) for t in h]
-        engine.forward_device(*d, gather=world > 1)  # probes the tensor-core path, captures the CUDA graph
-        d = engine.static_inputs(*d)  # inputs resident in HBM, in the engine's own buffers
+        runner = PipelinedRunner(depth=depth, device=dev, precision=args.precision)
+        lane_inputs = runner.prepare(*d0)  # captures one CUDA graph per lane; inputs stay resident in HBM
     except _lib.TsmdetError as e:
         if args.precision == "bf16" and e.code == 1000001:
             args.precision = "fp32"
-            engine = SABackboneNMS(precision="fp32").to(dev)
-            engine.forward_device(*d, gather=world > 1)
-            d = engine.static_inputs(*d)
+            runner = PipelinedRunner(depth=depth, device=dev, precision="fp32")
+            lane_inputs = runner.prepare(*d0)
         else:
             raise
-
+    engine = runner.engines[0]
+    gather = world > 1
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -215,48 +217,66 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
-        evs = []
-        for _ in range(steps):
-            flush_buf.zero_()  # L2 flush between timed iterations (not timed)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            fn()
-            e.record()
-            evs.append((s, e))
-        torch.cuda.synchronize(dev)
-        return [s.elapsed_time(e) for s, e in evs]
+    def flush():
+        flush_buf.zero_()  # L2 flush before every step, inside the timed region (on the step's own stream)
 
-    gather = world > 1
-    h_out = engine.forward_host(*h, gather=gather)
-    dev_step = lambda: engine.forward_device(*d, gather=gather)  # noqa: E731
-    host_step = lambda: engine.forward_host(*h, h_out=h_out, gather=gather)  # noqa: E731
+    def timed(submit, steps):
+        """K steps, `depth` in flight; device time between one start and one end event on the main stream."""
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        runner.fork()
+        for _ in range(steps):
+            submit()
+        runner.join()
+        e.record()
+        torch.cuda.synchronize(dev)
+        return s.elapsed_time(e)
+
+    dev_step = lambda: runner.submit_device(lane_inputs, gather=gather, pre=flush)  # noqa: E731
+    host_step = lambda: runner.submit_host(h, gather=gather, pre=flush)  # noqa: E731
 
     for _ in range(args.warmup):
         dev_step()
+    runner.sync()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = _lib.launch_count
     t_wall = time.perf_counter()
-    ms = timed(dev_step, args.steps)
+    ms_total = timed(dev_step, args.steps)
     barrier()
     wall = time.perf_counter() - t_wall
     launches = _lib.launch_count - l0
     clocks = sampler.stop()
     for _ in range(args.warmup):
         host_step()
+    runner.sync()
     barrier()
-    ms_e2e = timed(host_step, args.steps)
+    ms_e2e_total = timed(host_step, args.steps)
     barrier()
+    _, h_out = runner.submit_host(h, gather=gather)
+    runner.sync()
 
-    tot = torch.tensor([sum(ms), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    # single-step latency (one step in flight, no flush inside the events)
+    lat = []
+    for _ in range(5):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        engine.forward_device(*lane_inputs[0])
+        e.record()
+        torch.cuda.synchronize(dev)
+        lat.append(s.elapsed_time(e))
+    lat.sort()
+
+    tot = torch.tensor([ms_total, ms_e2e_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)  # max over ranks
     t_dev, t_e2e = float(tot[0]) / 1000.0, float(tot[1]) / 1000.0
     frames_total = FRAMES_PER_GPU * world * args.steps
     value = frames_total / t_dev
     e2e = frames_total / t_e2e
+    d = lane_inputs[0]
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (CUDA events on the launching stream)
     roof, kernels = kernel_breakdown(engine, d, dev, args)
@@ -268,8 +288,11 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_PER_GPU, "points_per_frame": N_POINTS,
                    "proposals_per_frame": N_PROPOSALS, "parallelism": f"frames sharded x{world}",
-                   "mlp_precision": args.precision, "l2": "256 MB buffer written between timed steps (untimed)",
-                   "execution": "one CUDA graph per step: FPS chain, query+MLP and NMS on 3 concurrent streams"},
+                   "mlp_precision": args.precision,
+                   "l2": "256 MB buffer written before every step, inside the timed region",
+                   "execution": "one CUDA graph per step (FPS chain, query+MLP, NMS on 3 concurrent streams); "
+                                f"{depth} step(s) in flight on separate streams/buffers",
+                   "pipeline_depth": depth, "ms_per_step_single_in_flight": lat[len(lat) // 2]},
         "e2e": {"value": e2e, "unit": "frames/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h)),
                 "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out.values()))},

@@ -39,6 +39,15 @@ int tsmdet_read_status(void);
  *      (sampling.cpp:43-52, 58-67; kernels sampling_gpu.cu:100-260, 588-748) */
 int tsmdet_farthest_point_sampling(int b, int n, int m, const float* xyz, float* temp, int* idxs, void* stream);
 
+/* The same sampler with bookkeeping for CHAINED set-abstraction layers (layer l+1 samples the centres layer l
+ * picked, pointnet2_backbone-style stacks).  tie_iter (B) i32 and vals (B,M) f32 record, per cloud, the first
+ * iteration whose maximum was shared by points with different coordinates and every iteration's winning
+ * min-distance.  Passing them as parent_tie / parent_vals (B,parent_m) to the NEXT level's call lets that call
+ * return its (provably identical) result without iterating; it falls back to the full algorithm per cloud
+ * whenever the record cannot prove it.  idxs are always bit-identical to tsmdet_farthest_point_sampling. */
+int tsmdet_fps_chain(int b, int n, int m, const float* xyz, float* temp, int* idxs, int* tie_iter, float* vals,
+                     const int* parent_tie, const float* parent_vals, int parent_m, void* stream);
+
 /* weights (B,N) f32.  ref: pointnet2_api.cpp:28 furthest_point_sampling_weights_wrapper
  *      (sampling.cpp:112-122; sampling_gpu.cu:901-1067) */
 int tsmdet_furthest_point_sampling_weights(int b, int n, int m, const float* xyz, const float* weights, float* temp,

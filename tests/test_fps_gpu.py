@@ -152,3 +152,30 @@ def test_fps_golden():
     for name in ("uniform", "dup", "lattice", "small", "kitti"):
         xyz, idx = g[f"{name}_xyz"], g[f"{name}_idx"]
         assert np.array_equal(_fps(xyz, idx.shape[1]), idx), name
+
+
+@pytest.mark.parametrize("name,gen,shortcut", [
+    ("objects", lambda: synth.cloud_ground_objects(4, 16384, 70), True),     # no ties: every level takes the shortcut
+    ("dup", lambda: synth.cloud_dup_padded(4, 16384, 71), True),             # duplicate points tie, same coordinates
+    ("lattice", lambda: synth.cloud_lattice(3, 6000, 72), False),            # equal distances between distinct points
+    ("few_unique", lambda: synth.cloud_dup_padded(2, 5000, 73, unique_frac=0.3), False),  # zero-distance picks
+], ids=["objects", "dup", "lattice", "few_unique"])
+def test_fps_chained_levels_match_plain_fps(orc, name, gen, shortcut):
+    """Stacked samplers (4096 -> 1024 -> 512 of the previous level's centres): the chained entry point must
+    return exactly what the plain sampler returns at every level, shortcut or not."""
+    from tsmdet_b200 import pointnet2_utils as pu
+    from tsmdet_b200.pointnet2_modules import gather_xyz
+
+    xyz = torch.from_numpy(gen()).to(_dev())
+    cur, state = xyz, None
+    for m in (4096, 1024, 512):
+        idx, state = pu.farthest_point_sample_chained(cur, m, state)
+        want = pu.farthest_point_sample(cur, m)
+        assert torch.equal(idx, want), (name, m)
+        assert np.array_equal(idx[:1].cpu().numpy(), orc.fps(cur[:1].cpu().numpy(), m)), (name, m)
+        cur = gather_xyz(cur, idx)
+    ar = torch.arange(512, device=_dev(), dtype=torch.int32)
+    # wherever the recorded run saw no tie between distinct points early enough, the prefix IS the answer
+    for b in range(idx.shape[0]):
+        if int(state.tie_iter[b]) >= 512 and shortcut:
+            assert bool((idx[b] == ar).all())

@@ -43,6 +43,8 @@ _pp = POINTER(c_void_p)
 SIGNATURES = {
     "tsmdet_read_status": [],
     "tsmdet_farthest_point_sampling": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tsmdet_fps_chain": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_int, c_void_p],
     "tsmdet_furthest_point_sampling_weights": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_furthest_point_sampling_matrix": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_furthest_point_sampling_with_weighted_dist": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -102,7 +104,7 @@ def check(status: int, where: str) -> None:
 KERNELS_PER_CALL = {
     "tsmdet_nms_batch": 3, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 3, "tsmdet_nms_normal_gpu": 3,
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
-    "tsmdet_fps_plan": 0, "tsmdet_read_status": 0, "tsmdet_sa_mlp_maxpool": 2,
+    "tsmdet_fps_plan": 0, "tsmdet_read_status": 0, "tsmdet_sa_mlp_maxpool": 3,
 }
 launch_count = 0
 

@@ -8,49 +8,43 @@
 // d2 < r^2 (dilated: rin^2 <= d2 < rout^2), idx_cnt = min(hits, nsample), the row is
 // padded cyclically with its own prefix, and a row without hits is all zeros.
 //
-// Design: one WARP per centre group (CW centres held in registers), lanes sweep 32
-// consecutive points per step, so a hit's position in the row is
-// cnt + popc(ballot & lanes_below): ordered compaction without atomics, early exit per
-// warp as soon as its centres are full, and coalesced point traffic.  Point tiles are
-// staged in shared memory by the TMA engine (cp.async.bulk, double buffered) in their
-// native (N,3) layout -- a 3-float stride is conflict-free across the 32 banks.
+// Design: one THREAD per centre; the cloud streams through shared memory in 1024-point tiles that
+// the TMA engine stages in their native (N,3) layout (cp.async.bulk, double buffered) and the CTA
+// re-packs into an x plane + a (y,z) plane.  Every lane of a warp tests the SAME point (a shared-memory
+// broadcast), so a hit appends to the thread's own row in index order with no atomics or ballots.
+// The inner loop is a conservative 1-D reject: d2 >= RN(dx*dx), so |dx| > r(1+2^-20) can never hit;
+// only points that survive it pay for the full reference distance (same FMA shape as the reference, so
+// the hit set is bit-identical).  For r = 0.2 m in a 70 m scene 99.4 % of the tests end after 4
+// instructions.
 #include "common.cuh"
 
 namespace tsm {
 
-constexpr int BQ_THREADS = 256;
-constexpr int BQ_WARPS = BQ_THREADS / 32;
-constexpr int BQ_CW = 4;          // centres per warp
-constexpr int BQ_TILE = 1024;     // points per shared-memory tile (12 KB)
+constexpr int BQ_THREADS = 128;
+constexpr int BQ_TILE = 1024;  // points per shared-memory tile
 
 template <bool DILATED>
 __global__ void __launch_bounds__(BQ_THREADS)
-    ball_query_kernel(int n, int m, float rin2, float rout2, int nsample, const float* __restrict__ new_xyz,
-                      const float* __restrict__ xyz, int* __restrict__ idx_cnt, int* __restrict__ idx, int* status) {
-    __shared__ __align__(128) float tile[2][BQ_TILE * 3];
+    ball_query_kernel(int n, int m, float rin2, float rout2, float rlim, int nsample,
+                      const float* __restrict__ new_xyz, const float* __restrict__ xyz, int* __restrict__ idx_cnt,
+                      int* __restrict__ idx, int* status) {
+    __shared__ __align__(128) float raw[2][BQ_TILE * 3];
+    __shared__ __align__(16) float sx[BQ_TILE];
+    __shared__ float2 syz[BQ_TILE];
     __shared__ __align__(8) uint64_t full[2];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int b = blockIdx.y;
     xyz += (size_t)b * n * 3;
-    const int c0 = (blockIdx.x * BQ_WARPS + warp) * BQ_CW;  // first centre of this warp
-
-    float cx[BQ_CW], cy[BQ_CW], cz[BQ_CW];
-    int cnt[BQ_CW];
-#pragma unroll
-    for (int c = 0; c < BQ_CW; ++c) {
-        const int ci = c0 + c;
-        const bool ok = ci < m;
-        const float* q = new_xyz + ((size_t)b * m + (ok ? ci : 0)) * 3;
-        cx[c] = q[0];
-        cy[c] = q[1];
-        cz[c] = q[2];
-        cnt[c] = ok ? 0 : nsample;  // out-of-range centres are "full" from the start
-    }
-    int* rows = idx + ((size_t)b * m + c0) * nsample;
+    const int ci = blockIdx.x * BQ_THREADS + tid;  // this thread's centre
+    const bool own = ci < m;
+    const float* q = new_xyz + ((size_t)b * m + (own ? ci : 0)) * 3;
+    const float cx = q[0], cy = q[1], cz = q[2];
+    int* row = idx + ((size_t)b * m + (own ? ci : 0)) * nsample;
+    int cnt = own ? 0 : nsample;  // out-of-range threads are "full" from the start
 
     const int ntiles = divup(n, BQ_TILE);
-    // TMA bulk copies need 16-byte aligned source and size; otherwise plain loads.
+    // TMA bulk copies need a 16-byte aligned source and size; otherwise plain loads.
     const bool use_tma = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((n & 3) == 0);
     if (use_tma && tid == 0) {
         mbar_init(smem_u32(&full[0]), 1);
@@ -64,13 +58,152 @@ __global__ void __launch_bounds__(BQ_THREADS)
         const int np = min(BQ_TILE, n - start);
         const uint32_t bytes = (uint32_t)np * 12u;
         mbar_arrive_expect_tx(smem_u32(&full[t & 1]), bytes);
-        bulk_g2s(smem_u32(&tile[t & 1][0]), xyz + (size_t)start * 3, bytes, smem_u32(&full[t & 1]));
+        bulk_g2s(smem_u32(&raw[t & 1][0]), xyz + (size_t)start * 3, bytes, smem_u32(&full[t & 1]));
     };
     if (use_tma && tid == 0) issue(0);
 
     for (int t = 0; t < ntiles; ++t) {
         const int start = t * BQ_TILE;
         const int np = min(BQ_TILE, n - start);
+        if (use_tma) {
+            if (tid == 0 && t + 1 < ntiles) issue(t + 1);  // raw[(t+1)&1] was consumed by the re-pack of tile t-1
+            const uint32_t bar = smem_u32(&full[t & 1]);
+            const uint32_t ph = (uint32_t)((t >> 1) & 1);
+            if (!mbar_try_wait_cta(bar, ph)) {
+                const long long t0 = clock64();
+                while (!mbar_try_wait_cta(bar, ph))
+                    if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
+            }
+            const float* rp = raw[t & 1];
+            for (int e = tid; e < np; e += BQ_THREADS) {  // stride-3 reads: conflict-free
+                sx[e] = rp[e * 3 + 0];
+                syz[e] = make_float2(rp[e * 3 + 1], rp[e * 3 + 2]);
+            }
+        } else {
+            for (int e = tid; e < np; e += BQ_THREADS) {
+                const float* p = xyz + (size_t)(start + e) * 3;
+                sx[e] = __ldg(p + 0);
+                syz[e] = make_float2(__ldg(p + 1), __ldg(p + 2));
+            }
+        }
+        __syncthreads();
+
+        if (cnt < nsample) {
+            auto full_test = [&](int k, float dx) {
+                const float2 yz = syz[k];
+                const float dy = __fsub_rn(cy, yz.x), dz = __fsub_rn(cz, yz.y);
+                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                const bool hit = DILATED ? (d2 >= rin2 && d2 < rout2) : (d2 < rout2);
+                if (hit && cnt < nsample) {
+                    row[cnt] = start + k;
+                    ++cnt;
+                }
+            };
+            int k = 0;
+            for (; k + 8 <= np; k += 8) {  // 8 points per step: two broadcast LDS.128, one branch
+                const float4 xa = *reinterpret_cast<const float4*>(&sx[k]);
+                const float4 xb = *reinterpret_cast<const float4*>(&sx[k + 4]);
+                const float d0 = __fsub_rn(cx, xa.x), d1 = __fsub_rn(cx, xa.y), d2_ = __fsub_rn(cx, xa.z),
+                            d3 = __fsub_rn(cx, xa.w), d4 = __fsub_rn(cx, xb.x), d5 = __fsub_rn(cx, xb.y),
+                            d6 = __fsub_rn(cx, xb.z), d7 = __fsub_rn(cx, xb.w);
+                const float mn = fminf(fminf(fminf(fabsf(d0), fabsf(d1)), fminf(fabsf(d2_), fabsf(d3))),
+                                       fminf(fminf(fabsf(d4), fabsf(d5)), fminf(fabsf(d6), fabsf(d7))));
+                if (mn < rlim) {
+                    if (fabsf(d0) < rlim) full_test(k + 0, d0);
+                    if (fabsf(d1) < rlim) full_test(k + 1, d1);
+                    if (fabsf(d2_) < rlim) full_test(k + 2, d2_);
+                    if (fabsf(d3) < rlim) full_test(k + 3, d3);
+                    if (fabsf(d4) < rlim) full_test(k + 4, d4);
+                    if (fabsf(d5) < rlim) full_test(k + 5, d5);
+                    if (fabsf(d6) < rlim) full_test(k + 6, d6);
+                    if (fabsf(d7) < rlim) full_test(k + 7, d7);
+                }
+            }
+            for (; k < np; ++k) {
+                const float dx = __fsub_rn(cx, sx[k]);
+                if (fabsf(dx) < rlim) full_test(k, dx);
+            }
+        }
+        // everyone is done with sx/syz (and raw[t&1]) before the next re-pack; stop once every row is full
+        if (__syncthreads_and(cnt >= nsample)) {
+            if (use_tma && t + 1 < ntiles) {  // drain the prefetch in flight before the CTA retires
+                const uint32_t bar = smem_u32(&full[(t + 1) & 1]);
+                const uint32_t ph = (uint32_t)(((t + 1) >> 1) & 1);
+                const long long t0 = clock64();
+                while (!mbar_try_wait_cta(bar, ph))
+                    if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
+            }
+            break;
+        }
+    }
+
+    // ---- count + cyclic padding (row[p] = row[p mod cnt]); an empty row is zeroed
+    if (own) {
+        const int k = min(cnt, nsample);
+        idx_cnt[(size_t)b * m + ci] = k;
+        if (k == 0) {
+            for (int p = 0; p < nsample; ++p) row[p] = 0;
+        } else {
+            for (int p = k; p < nsample; ++p) row[p] = row[p - k];
+        }
+    }
+}
+
+// ---- variant for FEW centres: one warp per group of 4 centres, lanes sweep 32 consecutive points per
+// step and compact hits in order with ballots (more parallelism per centre when B*M is small).
+constexpr int BQW_THREADS = 256;
+constexpr int BQW_WARPS = BQW_THREADS / 32;
+constexpr int BQW_CW = 4;          // centres per warp
+constexpr int BQW_TILE = 1024;     // points per shared-memory tile (12 KB)
+
+template <bool DILATED>
+__global__ void __launch_bounds__(BQW_THREADS)
+    ball_query_warp_kernel(int n, int m, float rin2, float rout2, int nsample, const float* __restrict__ new_xyz,
+                      const float* __restrict__ xyz, int* __restrict__ idx_cnt, int* __restrict__ idx, int* status) {
+    __shared__ __align__(128) float tile[2][BQW_TILE * 3];
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    xyz += (size_t)b * n * 3;
+    const int c0 = (blockIdx.x * BQW_WARPS + warp) * BQW_CW;  // first centre of this warp
+
+    float cx[BQW_CW], cy[BQW_CW], cz[BQW_CW];
+    int cnt[BQW_CW];
+#pragma unroll
+    for (int c = 0; c < BQW_CW; ++c) {
+        const int ci = c0 + c;
+        const bool ok = ci < m;
+        const float* q = new_xyz + ((size_t)b * m + (ok ? ci : 0)) * 3;
+        cx[c] = q[0];
+        cy[c] = q[1];
+        cz[c] = q[2];
+        cnt[c] = ok ? 0 : nsample;  // out-of-range centres are "full" from the start
+    }
+    int* rows = idx + ((size_t)b * m + c0) * nsample;
+
+    const int ntiles = divup(n, BQW_TILE);
+    // TMA bulk copies need 16-byte aligned source and size; otherwise plain loads.
+    const bool use_tma = ((reinterpret_cast<uintptr_t>(xyz) & 15) == 0) && ((n & 3) == 0);
+    if (use_tma && tid == 0) {
+        mbar_init(smem_u32(&full[0]), 1);
+        mbar_init(smem_u32(&full[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int start = t * BQW_TILE;
+        const int np = min(BQW_TILE, n - start);
+        const uint32_t bytes = (uint32_t)np * 12u;
+        mbar_arrive_expect_tx(smem_u32(&full[t & 1]), bytes);
+        bulk_g2s(smem_u32(&tile[t & 1][0]), xyz + (size_t)start * 3, bytes, smem_u32(&full[t & 1]));
+    };
+    if (use_tma && tid == 0) issue(0);
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int start = t * BQW_TILE;
+        const int np = min(BQW_TILE, n - start);
         const float* tp = tile[t & 1];
         if (use_tma) {
             if (tid == 0 && t + 1 < ntiles) issue(t + 1);  // buffer (t+1)&1 was released by the barrier below
@@ -82,13 +215,13 @@ __global__ void __launch_bounds__(BQ_THREADS)
                     if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
             }
         } else {
-            for (int e = tid; e < np * 3; e += BQ_THREADS) tile[t & 1][e] = xyz[(size_t)start * 3 + e];
+            for (int e = tid; e < np * 3; e += BQW_THREADS) tile[t & 1][e] = xyz[(size_t)start * 3 + e];
             __syncthreads();
         }
 
         bool active = false;
 #pragma unroll
-        for (int c = 0; c < BQ_CW; ++c) active |= cnt[c] < nsample;
+        for (int c = 0; c < BQW_CW; ++c) active |= cnt[c] < nsample;
         if (active) {
             for (int base = 0; base < np; base += 32) {
                 const int pl = base + lane;
@@ -97,7 +230,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
                 const float y = valid ? tp[pl * 3 + 1] : 0.f;
                 const float z = valid ? tp[pl * 3 + 2] : 0.f;
 #pragma unroll
-                for (int c = 0; c < BQ_CW; ++c) {
+                for (int c = 0; c < BQW_CW; ++c) {
                     if (cnt[c] < nsample) {  // warp-uniform
                         const float d2 = sqdist3(x, y, z, cx[c], cy[c], cz[c]);
                         const bool hit = valid && (DILATED ? (d2 >= rin2 && d2 < rout2) : (d2 < rout2));
@@ -114,7 +247,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
         // every warp must be done with tile[t&1] before it is refilled (tile t+2)
         bool still = false;
 #pragma unroll
-        for (int c = 0; c < BQ_CW; ++c) still |= cnt[c] < nsample;
+        for (int c = 0; c < BQW_CW; ++c) still |= cnt[c] < nsample;
         const int alldone = __syncthreads_and(!still);
         if (alldone) {
             if (use_tma && t + 1 < ntiles) {  // drain the prefetch in flight before the CTA retires
@@ -131,7 +264,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
     // ---- counts + cyclic padding (row[p] = row[p mod cnt]); empty rows are zeroed
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < BQ_CW; ++c) {
+    for (int c = 0; c < BQW_CW; ++c) {
         const int ci = c0 + c;
         if (ci >= m) continue;
         const int k = min(cnt[c], nsample);
@@ -153,14 +286,27 @@ static int run_ball_query(bool dilated, int b, int n, int m, float rin, float ro
     if (n < 0 || nsample <= 0 || b > 65535) return TSM_ERR_INVALID;
     const float rin2 = rin * rin;    // f32 products, as ball_query_gpu.cu:91, 154-155
     const float rout2 = rout * rout;
-    dim3 grid((unsigned)tsm::divup(m, tsm::BQ_WARPS * tsm::BQ_CW), (unsigned)b);
+    // conservative reject bound: any |dx| above it has RN(dx*dx) >= rout2 (NaN/inf radii disable it)
+    float rlim = fabsf(rout) * 1.000002f + 1e-30f;
+    if (!(rlim < 3.0e38f)) rlim = 3.4e38f;
     int* status = tsm_status_word(stream);
-    if (dilated)
-        tsm::ball_query_kernel<true><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, xyz,
-                                                                            idx_cnt, idx, status);
-    else
-        tsm::ball_query_kernel<false><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, xyz,
-                                                                             idx_cnt, idx, status);
+    if ((long)b * m >= 32768) {  // enough centres to fill the GPU with one thread each
+        dim3 grid((unsigned)tsm::divup(m, tsm::BQ_THREADS), (unsigned)b);
+        if (dilated)
+            tsm::ball_query_kernel<true><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample, new_xyz,
+                                                                                xyz, idx_cnt, idx, status);
+        else
+            tsm::ball_query_kernel<false><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample,
+                                                                                 new_xyz, xyz, idx_cnt, idx, status);
+    } else {
+        dim3 grid((unsigned)tsm::divup(m, tsm::BQW_WARPS * tsm::BQW_CW), (unsigned)b);
+        if (dilated)
+            tsm::ball_query_warp_kernel<true><<<grid, tsm::BQW_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz,
+                                                                                     xyz, idx_cnt, idx, status);
+        else
+            tsm::ball_query_warp_kernel<false><<<grid, tsm::BQW_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample,
+                                                                                      new_xyz, xyz, idx_cnt, idx, status);
+    }
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }

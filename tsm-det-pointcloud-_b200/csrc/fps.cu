@@ -37,6 +37,13 @@ struct FpsArgs {
     int n, m;
     int log2bs;  // log2 of the reference block size (cuda_utils.h:10-14)
     int* status;
+    // ---- chaining (optional; see tsmdet_fps_chain): per-cloud tie/value records of this run ...
+    int* tie_iter;     // (B) out: first iteration whose maximum was shared by points with different coordinates
+    float* vals;       // (B,M) out: the winning min-distance of every iteration (vals[0] = +inf)
+    // ... and of the run that produced this cloud as ITS first parent_m picks, in order
+    const int* parent_tie;
+    const float* parent_vals;
+    int parent_m;
 };
 
 struct __align__(16) FpsRec {
@@ -124,6 +131,26 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     const float* __restrict__ xyz = a.xyz + (size_t)cloud * n * 3;
     const uint32_t lowmask = (L == 0) ? 0xffffffffu : ((1u << (32 - L)) - 1u);
     const uint32_t rbase = ((L == 0) ? 0u : __brev((uint32_t)r)) | (uint32_t)(q * P);
+
+    // ---- chained shortcut: this cloud is the first `n` picks (in order) of an FPS run over a superset.
+    // FPS over such a prefix set re-selects it in the same order (each pick maximises the same min-distance
+    // over a subset that still contains the maximiser) unless a maximum was shared by distinct points, or
+    // zero-distance picks put duplicate coordinates into the set.  Both are recorded by the parent run, so
+    // the common case costs a few microseconds instead of m latency-bound iterations.
+    if (!WEIGHTED && a.parent_tie != nullptr) {
+        const bool prefix_ok = a.parent_tie[cloud] >= m && m <= n && n <= a.parent_m &&
+                               a.parent_vals[(size_t)cloud * a.parent_m + a.parent_m - 1] > 0.f;
+        if (prefix_ok) {  // uniform across the cluster: nobody reaches the cluster barriers below
+            for (int j = g; j < m; j += (int)csize * T) {
+                a.idxs[(size_t)cloud * m + j] = j;
+                if (a.vals) a.vals[(size_t)cloud * m + j] = a.parent_vals[(size_t)cloud * a.parent_m + j];
+            }
+            if (g == 0 && a.tie_iter) a.tie_iter[cloud] = a.parent_tie[cloud];
+            return;
+        }
+    }
+    if (!WEIGHTED && g == 0 && a.tie_iter) a.tie_iter[cloud] = 0x7fffffff;
+    if (!WEIGHTED && g == 0 && a.vals && m > 0) a.vals[(size_t)cloud * m] = __int_as_float(0x7f800000);
 
     if (tid == 0) {
         mbar_init(smem_u32(&mbar[0]), 1);
@@ -223,7 +250,16 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
         uint32_t cu = 0u, crk = 0xffffffffu;
         float cx = 0.f, cy = 0.f, cz = 0.f;
         const FpsRec* recs = par ? recs1 : recs0;
-        for (int s = lane; s < R; s += 32) {
+        if (lane < R) {  // R <= 32 in the common shapes: one record per lane
+            const uint4 v = *reinterpret_cast<const uint4*>(&recs[lane]);
+            cz = recs[lane].z;
+            cu = v.x;
+            crk = v.y;
+            cx = __uint_as_float(v.z);
+            cy = __uint_as_float(v.w);
+        }
+#pragma unroll 1
+        for (int s = lane + 32; s < R; s += 32) {
             const uint4 v = *reinterpret_cast<const uint4*>(&recs[s]);
             if (v.x > cu || (v.x == cu && v.y < crk)) {
                 cu = v.x;
@@ -251,6 +287,26 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
                 k = (int)(rr + ((grk & lowmask) << L));
             }
             idxs[j] = k;
+            if (!WEIGHTED && a.vals) a.vals[(size_t)cloud * m + j] = __uint_as_float(gu & 0x7fffffffu);
+        }
+        if (!WEIGHTED && a.tie_iter) {
+            // did another point with DIFFERENT coordinates share this iteration's maximum?  (off the critical
+            // path: nothing below feeds the next iteration)
+            const float gv = __uint_as_float(gu & 0x7fffffffu);
+            bool any_eq = false;
+#pragma unroll
+            for (int p = 0; p < P; ++p) any_eq |= (md[p] == gv);
+            if (any_eq) {
+                bool tie = false;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const float X = SMEM ? sx[p * T + tid] : px[p];
+                    const float Y = SMEM ? sy[p * T + tid] : py[p];
+                    const float Z = SMEM ? sz[p * T + tid] : pz[p];
+                    tie |= (md[p] == gv) && (X != x1 || Y != y1 || Z != z1);
+                }
+                if (tie) atomicMin(a.tie_iter + cloud, j);
+            }
         }
     }
 
@@ -491,7 +547,8 @@ static bool plan_fps(int b, int n, int log2bs, bool weighted, bool query_occupan
 }
 
 static int run_fps(int b, int n, int m, const float* xyz, const float* weights, float* temp, int* idxs,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int* tie_iter = nullptr, float* vals = nullptr, const int* parent_tie = nullptr,
+                   const float* parent_vals = nullptr, int parent_m = 0) {
     if (b <= 0 || m <= 0) return TSM_OK;
     if (n <= 0) return TSM_ERR_INVALID;
     tsm::FpsArgs a;
@@ -503,6 +560,11 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
     a.m = m;
     a.log2bs = ref_log2_block(n);
     a.status = tsm_status_word(stream);
+    a.tie_iter = tie_iter;
+    a.vals = vals;
+    a.parent_tie = parent_tie;
+    a.parent_vals = parent_vals;
+    a.parent_m = parent_m;
     FpsPlan pl;
     if (!plan_fps(b, n, a.log2bs, weights != nullptr, true, &pl)) return TSM_ERR_INVALID;
     if (weights) return tsm::dispatch_fps<true>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
@@ -526,6 +588,17 @@ int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread,
 
 int tsmdet_farthest_point_sampling(int b, int n, int m, const float* xyz, float* temp, int* idxs, void* stream) {
     return run_fps(b, n, m, xyz, nullptr, temp, idxs, (cudaStream_t)stream);
+}
+
+// FPS that records what a follow-up FPS over its own output needs (tie_iter (B) i32, vals (B,M) f32), and
+// that can itself be the follow-up of a recorded run: parent_tie (B) / parent_vals (B,parent_m) describe the
+// FPS whose first n picks, in order, ARE this xyz.  Results are identical to tsmdet_farthest_point_sampling
+// (the prediction is only used where the parent run proves it exact); temp is not produced on that path.
+int tsmdet_fps_chain(int b, int n, int m, const float* xyz, float* temp, int* idxs, int* tie_iter, float* vals,
+                     const int* parent_tie, const float* parent_vals, int parent_m, void* stream) {
+    if ((parent_tie == nullptr) != (parent_vals == nullptr)) return TSM_ERR_INVALID;
+    return run_fps(b, n, m, xyz, nullptr, temp, idxs, (cudaStream_t)stream, tie_iter, vals, parent_tie, parent_vals,
+                   parent_m);
 }
 
 int tsmdet_furthest_point_sampling_weights(int b, int n, int m, const float* xyz, const float* weights, float* temp,

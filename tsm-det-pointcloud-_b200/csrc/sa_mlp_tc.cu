@@ -40,6 +40,7 @@ struct TcPlan {
     int xyz_chunk;             // 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
     int tmem_cols;             // power of two >= 32
     int d_off;                 // TMEM column of the odd layers' accumulator (even layers use column 0)
+    int packed_bytes;          // weights + biases: the first packed_bytes of dynamic smem, same layout in global
 };
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -103,10 +104,43 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(int c, int cp, int 
     }
 }
 
+// Weights (cout,cin) fp32 + bias -> the kernel's shared-memory image: per layer bf16 [K/8][Npad][8] (UMMA
+// K-major core matrices), then the fp32 biases.  Layer 0's input channels are permuted to the operand order
+// [features 0..C-1 | pad to cp | dx,dy,dz | pad] (the reference order is [dx,dy,dz, features...],
+// pointnet2_utils.py:523).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const SaMlpArgs a, const TcPlan pl, unsigned char* __restrict__ packed) {
+    const int l = blockIdx.y;
+    const int K = pl.K[l], Np = pl.Npad[l];
+    const int cin = a.ch[l], cout = a.ch[l + 1];
+    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(packed + pl.w_off[l]);
+    const float* __restrict__ W = a.w[l];
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * K; e += gridDim.x * 256) {
+        const int k = e / Np, n = e - k * Np;  // consecutive threads -> consecutive n: 16-byte-strided writes
+        float v = 0.f;
+        if (n < cout) {
+            int src = -1;
+            if (l == 0) {
+                if (k < a.c_feat)
+                    src = (a.use_xyz ? 3 : 0) + k;
+                else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
+                    src = k - pl.xyz_chunk * 8;
+            } else if (k < cin) {
+                src = k;
+            }
+            if (src >= 0) v = __ldg(W + (size_t)n * cin + src);
+        }
+        ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    }
+    float* bs = reinterpret_cast<float*>(packed + pl.b_off[l]);
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    sa_mlp_tc_kernel(const SaMlpArgs a, const TcPlan pl, const __nv_bfloat16* __restrict__ featT, int num_tiles) {
+    sa_mlp_tc_kernel(const SaMlpArgs a, const TcPlan pl, const __nv_bfloat16* __restrict__ featT,
+                     const unsigned char* __restrict__ packed, int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,37 +148,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int cpt = TC_ROWS / S;  // whole centres per tile (S divides 128)
     const int nl = pl.nl;
 
-    // ---- one-time setup: weights -> bf16 UMMA layout, biases, barrier, TMEM
-    for (int l = 0; l < nl; ++l) {
-        const int K = pl.K[l], Np = pl.Npad[l];
-        const int cin = a.ch[l], cout = a.ch[l + 1];
-        __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(smem + pl.w_off[l]);
-        const float* __restrict__ W = a.w[l];
-        for (int e = tid; e < Np * K; e += TC_THREADS) {
-            const int n = e / K, k = e - n * K;
-            float v = 0.f;
-            if (n < cout) {
-                int src = -1;
-                if (l == 0) {
-                    // operand channel order: [features 0..C-1 | pad to cp | dx,dy,dz | pad]; the weights'
-                    // input order is the reference's [dx,dy,dz, features...] (pointnet2_utils.py:523)
-                    if (k < a.c_feat)
-                        src = (a.use_xyz ? 3 : 0) + k;
-                    else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
-                        src = k - pl.xyz_chunk * 8;
-                } else if (k < cin) {
-                    src = k;
-                }
-                if (src >= 0) v = __ldg(W + (size_t)n * cin + src);
-            }
-            ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
-        }
-        float* bs = reinterpret_cast<float*>(smem + pl.b_off[l]);
-        for (int e = tid; e < Np; e += TC_THREADS) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
-    }
+    // ---- one-time setup: packed weights + biases (bf16 UMMA layout, built by pack_weights_kernel) arrive
+    // with ONE bulk copy (TMA engine); barrier; TMEM
     if (tid == 0) {
         mbar_init(smem_u32(&mma_bar), 1);
+        mbar_init(smem_u32(&w_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
+        bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -152,10 +163,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const uint32_t bar = smem_u32(&w_bar);
+        const long long t0 = clock64();
+        while (!mbar_try_wait_cta(bar, 0))
+            if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+    }
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t a_smem = smem_u32(smem + pl.a_off);
     unsigned char* a_ptr = smem + pl.a_off;
@@ -256,19 +272,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int c0 = 0; c0 < Np; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(t_row + (uint32_t)c0, v);
+                    if (S >= 32) {
+                        uint32_t mine = 0u;  // lane j ends up holding channel c0 + j's maximum
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float x = fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f);
-                        uint32_t u = __float_as_uint(x);
-                        if (S >= 32) {
-                            u = __reduce_max_sync(FULL, u);
-                            if (lane == j) {
-                                if (S == 32)
-                                    omax[(c0 + j) * cpt + ci] = u;
-                                else
-                                    atomicMax(&omax[(c0 + j) * cpt + ci], u);
-                            }
-                        } else {
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f);
+                            // x >= 0: unsigned order == float order, so one redux.sync is the 32-row max
+                            const uint32_t u = __reduce_max_sync(FULL, __float_as_uint(x));
+                            mine = lane == j ? u : mine;
+                        }
+                        if (lane < 16) {
+                            if (S == 32)
+                                omax[(c0 + lane) * cpt + ci] = mine;
+                            else
+                                atomicMax(&omax[(c0 + lane) * cpt + ci], mine);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f);
+                            uint32_t u = __float_as_uint(x);
                             for (int o = S >> 1; o >= 1; o >>= 1) u = max(u, __shfl_xor_sync(FULL, u, o));
                             if ((lane & (S - 1)) == 0) omax[(c0 + j) * cpt + ci] = u;
                         }
@@ -329,6 +352,7 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
         pl.b_off[l] = off;
         off += pl.Npad[l] * 4;
     }
+    pl.packed_bytes = off;  // multiple of 64
     off = round_up(off, 128);
     pl.a_off = off;
     off += TC_ROWS * kmax * 2;
@@ -367,7 +391,17 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     if (grid > tiles) grid = tiles;
     SaMlpArgs args = a;
     args.status = tsm_status_word(stream);
-    sa_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, (int)tiles);
+    unsigned char* packed = nullptr;
+    {
+        void* p = nullptr;
+        int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes, stream, &p);
+        if (rc != TSM_OK) return rc;
+        packed = (unsigned char*)p;
+        dim3 pgrid(16, (unsigned)pl.nl);
+        pack_weights_kernel<<<pgrid, 256, 0, stream>>>(args, pl, packed);
+        TSM_LAUNCH_CHECK();
+    }
+    sa_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }

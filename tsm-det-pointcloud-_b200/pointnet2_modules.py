@@ -296,8 +296,12 @@ class PointNet2SAStack(nn.Module):
 
     def forward(self, xyz, features=None):
         outs = []
+        state = None
         for layer in self.layers:
-            xyz, features, idx = layer(xyz, features)
+            # every layer here is one d-fps over all of the previous layer's centres: chain the samplers
+            idx, state = pointnet2_utils.farthest_point_sample_chained(xyz.contiguous(), layer.npoint_list[0], state)
+            new_xyz = gather_xyz(xyz.contiguous(), idx)
+            xyz, features, _ = layer(xyz, features, new_xyz=new_xyz)
             outs.append((xyz, features, idx))
         return outs
 

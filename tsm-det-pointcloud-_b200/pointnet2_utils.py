@@ -90,6 +90,35 @@ class FarthestPointSampling(Function):
 farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
 
 
+class FpsChainState:
+    """What an FPS run leaves behind for an FPS over its own output (see ``tsmdet_fps_chain``)."""
+
+    __slots__ = ("tie_iter", "vals", "m")
+
+    def __init__(self, tie_iter, vals, m):
+        self.tie_iter, self.vals, self.m = tie_iter, vals, m
+
+
+@torch.no_grad()
+def farthest_point_sample_chained(xyz: torch.Tensor, npoint: int, parent: "FpsChainState" = None):
+    """``farthest_point_sample`` for stacked SA layers: returns ``(idx, state)``.
+
+    Pass the previous layer's ``state`` when ``xyz`` is exactly that layer's sampled centres in sampling
+    order (``new_xyz``); the result is bit-identical to ``farthest_point_sample(xyz, npoint)`` -- FPS over
+    the first picks of an FPS run re-selects them in order -- and costs microseconds whenever the parent
+    run recorded no tie between distinct points (otherwise the full algorithm runs for that cloud)."""
+    assert xyz.is_contiguous()
+    b, n, _ = xyz.size()
+    out = _i32((b, npoint), xyz.device)
+    tie = _i32((b,), xyz.device)
+    vals = _f32((b, npoint), xyz.device)
+    use_parent = parent is not None and parent.m >= n
+    call("tsmdet_fps_chain", b, n, npoint, ptr(xyz), None, ptr(out), ptr(tie), ptr(vals),
+         ptr(parent.tie_iter) if use_parent else None, ptr(parent.vals) if use_parent else None,
+         parent.m if use_parent else 0, stream_ptr(xyz.device))
+    return out, FpsChainState(tie, vals, npoint)
+
+
 class FurthestPointSamplingWithDist(Function):
     """ref :114-137 -- xyz here is a (B,N,N) distance matrix."""
 
