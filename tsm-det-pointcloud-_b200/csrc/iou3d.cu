@@ -75,6 +75,24 @@ __host__ __device__ __forceinline__ bool surely_disjoint(const BoxPrep& a, const
     return ddx * ddx + ddy * ddy > r * r;  // NaN compares false -> full path
 }
 
+// Second, tighter conservative test for pairs whose bounding circles touch: separating axis theorem on
+// the margin-grown rectangles (+4 cm slack, far above the f32 error of the reference's corner arithmetic).
+// Separated rectangles have no edge intersection and no corner within MARGIN of the other box, so the
+// reference returns exactly 0 for them.
+__host__ __device__ __forceinline__ bool surely_separated(const BoxPrep& a, const BoxPrep& b) {
+    const float dx = b.cx - a.cx, dy = b.cy - a.cy;
+    const float c = fabsf(a.ci * b.ci + a.si * b.si), s = fabsf(a.si * b.ci - a.ci * b.si);
+    const float slack = 0.04f + 4e-6f * (fabsf(a.cx) + fabsf(a.cy) + fabsf(b.cx) + fabsf(b.cy));
+    // axes of a: u = (ci, -si), v = (si, ci)   (ci, si = cos, sin of -heading)
+    const float au = fabsf(dx * a.ci - dy * a.si), av = fabsf(dx * a.si + dy * a.ci);
+    if (au > a.mx + b.mx * c + b.my * s + slack) return true;
+    if (av > a.my + b.mx * s + b.my * c + slack) return true;
+    const float bu = fabsf(dx * b.ci - dy * b.si), bv = fabsf(dx * b.si + dy * b.ci);
+    if (bu > b.mx + a.mx * c + a.my * s + slack) return true;
+    if (bv > b.my + a.mx * s + a.my * c + slack) return true;
+    return false;  // NaNs compare false everywhere -> full path
+}
+
 __host__ __device__ __forceinline__ float cross3(float p1x, float p1y, float p2x, float p2y, float p0x, float p0y) {
     return (p1x - p0x) * (p2y - p0y) - (p2x - p0x) * (p1y - p0y);
 }
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(256)
     for (int p = tid; p < 4096; p += 256) {
         const int r = p >> 6, c = p & 63;
         const bool in = r < nr && c < nc;
-        const bool heavy = in && !surely_disjoint(sa[r], sb[c]);
+        const bool heavy = in && !surely_disjoint(sa[r], sb[c]) && !surely_separated(sa[r], sb[c]);
         if (in && !heavy) out[(size_t)(r0 + r) * nb + c0 + c] = 0.f;
         const unsigned bal = __ballot_sync(FULL, heavy);
         if (bal) {
@@ -234,80 +252,86 @@ __global__ void __launch_bounds__(256)
 
 // Suppression words for the tiles on/above the diagonal.
 //   prep (F, nmax) per-frame prepared boxes in score order, counts (F) or null (= nmax)
-//   mask (F, nmax, cbmax) 64-bit words; only words with column block >= row block are written.
+//   mask (F, nmax, cbmax) 64-bit words, ZEROED by the launcher; bits are OR-ed in.
+// Persistent CTAs (gridDim.x per frame) walk the frame's upper-triangular 64x64 tiles.  Each tile's
+// 4096 pairs go through two conservative rejects (bounding circles, then separating axes); survivors
+// are appended -- as (row, col) box indices -- to a shared-memory queue that is kept ACROSS tiles and
+// drained by all 256 threads whenever it holds >= 2048 pairs, so the ~2000-instruction exact IoU always
+// runs on full warps no matter how sparse the overlaps are.
+constexpr int NMS_Q = 4096 + 2048;
+
 template <bool NORMAL>
 __global__ void __launch_bounds__(256)
     nms_mask_kernel(int nmax, const int* __restrict__ counts, float thresh, const BoxPrep* __restrict__ prep,
                     unsigned long long* __restrict__ mask) {
     __shared__ BoxPrep srow[64], scol[64];
-    __shared__ unsigned short queue[4096];
-    __shared__ unsigned long long words[64];
+    __shared__ unsigned int queue[NMS_Q];
     __shared__ int qn;
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = blockIdx.y;
     const int n = counts ? min(counts[f], nmax) : nmax;
     const int cbmax = divup(nmax, 64);
     const int cb = divup(n, 64);
-    // linear tile id -> (rb, cbk) with rb <= cbk over the cbmax grid; skip tiles outside this frame
-    int t = blockIdx.x;
-    int rb = 0;
-    {
-        // row rb holds (cbmax - rb) tiles
-        int rem = t;
-        while (rem >= cbmax - rb) {
-            rem -= cbmax - rb;
-            ++rb;
-        }
-        t = rb + rem;
-    }
-    const int cbk = t;
-    if (rb >= cb || cbk >= cb) return;
+    const long long ntiles = (long long)cb * (cb + 1) / 2;
     const BoxPrep* P = prep + (size_t)f * nmax;
-    const int r0 = rb * 64, c0 = cbk * 64;
-    const int nr = min(64, n - r0), nc = min(64, n - c0);
-    for (int e = tid; e < 64 * 20; e += 256) {
-        const int bi = e / 20, w = e - bi * 20;
-        if (bi < nr) reinterpret_cast<float*>(&srow[bi])[w] = reinterpret_cast<const float*>(&P[r0 + bi])[w];
-        if (bi < nc) reinterpret_cast<float*>(&scol[bi])[w] = reinterpret_cast<const float*>(&P[c0 + bi])[w];
-    }
-    if (tid < 64) words[tid] = 0ull;
+    unsigned long long* M = mask + (size_t)f * nmax * cbmax;
+    const bool all_heavy = !(thresh >= 0.f);  // negative/NaN threshold: a zero IoU may still suppress
     if (tid == 0) qn = 0;
     __syncthreads();
-    const bool diag = rb == cbk;
-    const bool all_heavy = !(thresh >= 0.f);  // negative/NaN threshold: a zero IoU may still suppress
-    for (int p = tid; p < 4096; p += 256) {
-        const int r = p >> 6, c = p & 63;
-        const bool in = r < nr && c < nc && (!diag || c > r);
-        bool heavy = in;
-        if (in && !all_heavy) {
-            if (NORMAL)
-                heavy = true;  // the axis-aligned IoU is cheap: evaluate directly below
-            else
-                heavy = !surely_disjoint(srow[r], scol[c]);
-        }
-        if (NORMAL) {
-            if (heavy && iou_axis(srow[r], scol[c]) > thresh) atomicOr(&words[r], 1ull << c);
-        } else {
-            const unsigned bal = __ballot_sync(FULL, heavy);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&qn, __popc(bal));
-                base = __shfl_sync(FULL, base, 0);
-                if (heavy) queue[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)p;
-            }
-        }
-    }
-    __syncthreads();
-    if (!NORMAL) {
+
+    auto drain = [&]() {  // evaluate every queued pair exactly; all threads busy
         const int total = qn;
         for (int q = tid; q < total; q += 256) {
-            const int p = queue[q];
-            const int r = p >> 6, c = p & 63;
-            if (iou_rotated(srow[r], scol[c]) > thresh) atomicOr(&words[r], 1ull << c);
+            const unsigned int e = queue[q];
+            const int i = (int)(e >> 16), j = (int)(e & 0xffffu);
+            const BoxPrep a = P[i], b = P[j];
+            if (iou_rotated(a, b) > thresh) atomicOr(&M[(size_t)i * cbmax + (j >> 6)], 1ull << (j & 63));
         }
         __syncthreads();
+        if (tid == 0) qn = 0;
+        __syncthreads();
+    };
+
+    // tile t -> (rb, cbk), rb <= cbk: row rb owns (cb - rb) tiles
+    int rb = 0;
+    long long row_first = 0;  // linear id of tile (rb, rb)
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        while (t >= row_first + (cb - rb)) {
+            row_first += cb - rb;
+            ++rb;
+        }
+        const int cbk = rb + (int)(t - row_first);
+        const int r0 = rb * 64, c0 = cbk * 64;
+        const int nr = min(64, n - r0), nc = min(64, n - c0);
+        for (int e = tid; e < 64 * 20; e += 256) {
+            const int bi = e / 20, w = e - bi * 20;
+            if (bi < nr) reinterpret_cast<float*>(&srow[bi])[w] = reinterpret_cast<const float*>(&P[r0 + bi])[w];
+            if (bi < nc) reinterpret_cast<float*>(&scol[bi])[w] = reinterpret_cast<const float*>(&P[c0 + bi])[w];
+        }
+        __syncthreads();
+        const bool diag = rb == cbk;
+        for (int p = tid; p < 4096; p += 256) {
+            const int r = p >> 6, c = p & 63;
+            const bool in = r < nr && c < nc && (!diag || c > r);
+            if (NORMAL) {
+                if (in && iou_axis(srow[r], scol[c]) > thresh)
+                    atomicOr(&M[(size_t)(r0 + r) * cbmax + cbk], 1ull << c);
+            } else {
+                bool heavy = in;
+                if (in && !all_heavy) heavy = !surely_disjoint(srow[r], scol[c]) && !surely_separated(srow[r], scol[c]);
+                const unsigned bal = __ballot_sync(FULL, heavy);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&qn, __popc(bal));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (heavy) queue[base + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)(r0 + r) << 16) | (unsigned)(c0 + c);
+                }
+            }
+        }
+        __syncthreads();
+        if (!NORMAL && qn >= 2048) drain();  // uniform: qn is stable after the barrier
     }
-    if (tid < nr) mask[((size_t)f * nmax + r0 + tid) * cbmax + cbk] = words[tid];
+    if (!NORMAL) drain();
 }
 
 // Greedy sweep (iou3d_nms.cpp:116-131) on the device, one CTA per frame.
@@ -400,9 +424,13 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     const int total = frames * nmax;
     tsm::prep_boxes_kernel<<<tsm::divup(total, 128), 128, 0, s>>>(total, boxes, box_stride, prep);
     TSM_LAUNCH_CHECK();
+    if (nmax > 65535) return TSM_ERR_INVALID;  // queue entries pack (row, col) into 16 + 16 bits
+    TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     const long tiles = (long)cbmax * (cbmax + 1) / 2;
-    if (tiles > 0x7fffffffL) return TSM_ERR_INVALID;
-    dim3 grid((unsigned)tiles, (unsigned)frames);
+    int per_frame = (2 * tsm_num_sms() + frames - 1) / frames;  // ~2 CTAs per SM in total
+    if (per_frame > tiles) per_frame = (int)tiles;
+    if (per_frame < 1) per_frame = 1;
+    dim3 grid((unsigned)per_frame, (unsigned)frames);
     if (normal)
         tsm::nms_mask_kernel<true><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask);
     else
@@ -501,7 +529,9 @@ int tsmdet_boxes_iou_bev_cpu(int num_a, const float* boxes_a, int num_b, const f
     for (int j = 0; j < num_b; ++j) tsm::prep_box(boxes_b + (size_t)j * 7, B[j]);
     for (int i = 0; i < num_a; ++i)
         for (int j = 0; j < num_b; ++j)
-            ans_iou[(size_t)i * num_b + j] = tsm::surely_disjoint(A[i], B[j]) ? 0.f : tsm::iou_rotated(A[i], B[j]);
+            ans_iou[(size_t)i * num_b + j] = (tsm::surely_disjoint(A[i], B[j]) || tsm::surely_separated(A[i], B[j]))
+                                                 ? 0.f
+                                                 : tsm::iou_rotated(A[i], B[j]);
     return TSM_OK;
 }
 

@@ -44,6 +44,7 @@ class SABackboneNMS(torch.nn.Module):
         self.nms_after_fps = os.environ.get("TSMDET_NMS_AFTER_FPS", "0") != "0"
         self._graphs: Dict[tuple, dict] = {}
         self._streams = None
+        self._trace = None  # list of (name, event) when tracing (see trace_step)
         self.eval()
 
     # ------------------------------------------------------------------ the DAG
@@ -78,6 +79,13 @@ class SABackboneNMS(torch.nn.Module):
         s_sa.wait_stream(main)
         s_nms.wait_stream(main)
 
+        trace = self._trace
+        def mark(name, stream):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                trace.append((name, ev))
+        mark("start", main)
         layers = self.backbone.layers
         b = xyz.shape[0]
         cur_xyz = xyz
@@ -87,6 +95,7 @@ class SABackboneNMS(torch.nn.Module):
         for layer in layers:
             idx, state = pointnet2_utils.farthest_point_sample_chained(cur_xyz, layer.npoint_list[0], state)
             new_xyz = gather_xyz(cur_xyz, idx)
+            mark(f"fps{len(ready) + 1}", main)
             ev = torch.cuda.Event()
             ev.record(main)
             centres.append((cur_xyz, new_xyz))
@@ -99,9 +108,11 @@ class SABackboneNMS(torch.nn.Module):
                 s_sa.wait_event(ev)
                 g = layer.groupers[0]
                 cnt, bidx = pointnet2_utils.ball_query(g.radius, g.nsample, src_xyz, new_xyz)
+                mark(f"query{src_xyz.shape[1]}", s_sa)
                 folded = layer._folded_layers()[0]
                 out = torch.empty((b, folded[-1][0].shape[0], new_xyz.shape[1]), dtype=torch.float32, device=dev)
                 sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision)
+                mark(f"mlp{src_xyz.shape[1]}", s_sa)
                 cur_f = out
         # stream C: NMS is independent of the backbone.  (Measured inside the captured graph: letting it run
         # beside the sampling chain is faster -- 4.98 vs 5.61 ms/step -- than holding it back until the chain
@@ -110,9 +121,24 @@ class SABackboneNMS(torch.nn.Module):
             if self.nms_after_fps:
                 s_nms.wait_event(ready[-1])
             det_idx, det_num = self._nms_two_pass(boxes, scores)
+            mark("nms", s_nms)
         main.wait_stream(s_sa)
         main.wait_stream(s_nms)
+        mark("end", main)
         return {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num}
+
+    def trace_step(self, xyz, feats, boxes, scores):
+        """Runs the DAG eagerly with timing events; returns [(name, ms since start)] (diagnostics)."""
+        self._run(xyz, feats, boxes, scores)
+        torch.cuda.synchronize(xyz.device)
+        self._trace = []
+        try:
+            self._run(xyz, feats, boxes, scores)
+            torch.cuda.synchronize(xyz.device)
+            t0 = self._trace[0][1]
+            return [(n, t0.elapsed_time(e)) for n, e in self._trace]
+        finally:
+            self._trace = None
 
     # ------------------------------------------------------------------ graph capture / replay
     def _graph_for(self, xyz, feats, boxes, scores):
