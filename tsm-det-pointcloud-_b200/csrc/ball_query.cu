@@ -27,7 +27,7 @@ template <bool DILATED>
 __global__ void __launch_bounds__(BQ_THREADS)
     ball_query_kernel(int n, int m, float rin2, float rout2, float rlim, int nsample,
                       const float* __restrict__ new_xyz, const float* __restrict__ xyz, int* __restrict__ idx_cnt,
-                      int* __restrict__ idx, int* status) {
+                      int* __restrict__ idx, const int* __restrict__ perm, int* status) {
     __shared__ __align__(128) float raw[2][BQ_TILE * 3];
     __shared__ __align__(16) float sx[BQ_TILE];
     __shared__ float2 syz[BQ_TILE];
@@ -36,8 +36,12 @@ __global__ void __launch_bounds__(BQ_THREADS)
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     xyz += (size_t)b * n * 3;
-    const int ci = blockIdx.x * BQ_THREADS + tid;  // this thread's centre
-    const bool own = ci < m;
+    // Centres are handed out in x-sorted order (perm, built by sort_centres_kernel): the 32 centres of a
+    // warp then span a narrow x interval, so the per-lane reject below fails for (almost) all lanes at once
+    // and the warp skips the point without diverging.  Each thread still owns one output row.
+    const int slot = blockIdx.x * BQ_THREADS + tid;
+    const bool own = slot < m;
+    const int ci = own ? (perm ? perm[(size_t)b * m + slot] : slot) : 0;
     const float* q = new_xyz + ((size_t)b * m + (own ? ci : 0)) * 3;
     const float cx = q[0], cy = q[1], cz = q[2];
     int* row = idx + ((size_t)b * m + (own ? ci : 0)) * nsample;
@@ -147,6 +151,35 @@ __global__ void __launch_bounds__(BQ_THREADS)
             for (int p = k; p < nsample; ++p) row[p] = row[p - k];
         }
     }
+}
+
+// perm[b, :] = centre indices of cloud b sorted by x (bitonic sort in shared memory, m <= 8192).
+__global__ void __launch_bounds__(1024) sort_centres_kernel(int m, int mp2, const float* __restrict__ new_xyz,
+                                                            int* __restrict__ perm) {
+    extern __shared__ unsigned long long keys[];  // (ordered x bits << 32) | index; padding sorts last
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < mp2; i += 1024) {
+        unsigned long long k = ~0ull;
+        if (i < m) k = ((unsigned long long)f32_ordered(new_xyz[((size_t)b * m + i) * 3]) << 32) | (unsigned)i;
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= mp2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (mp2 >> 1); i += 1024) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = keys[lo], c = keys[hi];
+                if ((a > c) == up) {
+                    keys[lo] = c;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < m; i += 1024) perm[(size_t)b * m + i] = (int)(keys[i] & 0xffffffffu);
 }
 
 // ---- variant for FEW centres: one warp per group of 4 centres, lanes sweep 32 consecutive points per
@@ -291,13 +324,27 @@ static int run_ball_query(bool dilated, int b, int n, int m, float rin, float ro
     if (!(rlim < 3.0e38f)) rlim = 3.4e38f;
     int* status = tsm_status_word(stream);
     if ((long)b * m >= 32768) {  // enough centres to fill the GPU with one thread each
+        int* perm = nullptr;
+        if (m <= 8192 && m >= 64) {
+            void* p = nullptr;
+            int rc = tsm_scratch_get(3, sizeof(int) * (size_t)b * m, stream, &p);
+            if (rc != TSM_OK) return rc;
+            perm = (int*)p;
+            int mp2 = 64;
+            while (mp2 < m) mp2 <<= 1;
+            const size_t dyn = sizeof(unsigned long long) * (size_t)mp2;
+            if (dyn > 48 * 1024)
+                TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::sort_centres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            tsm::sort_centres_kernel<<<b, 1024, dyn, stream>>>(m, mp2, new_xyz, perm);
+            TSM_LAUNCH_CHECK();
+        }
         dim3 grid((unsigned)tsm::divup(m, tsm::BQ_THREADS), (unsigned)b);
         if (dilated)
             tsm::ball_query_kernel<true><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample, new_xyz,
-                                                                                xyz, idx_cnt, idx, status);
+                                                                                xyz, idx_cnt, idx, perm, status);
         else
             tsm::ball_query_kernel<false><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample,
-                                                                                 new_xyz, xyz, idx_cnt, idx, status);
+                                                                                 new_xyz, xyz, idx_cnt, idx, perm, status);
     } else {
         dim3 grid((unsigned)tsm::divup(m, tsm::BQW_WARPS * tsm::BQW_CW), (unsigned)b);
         if (dilated)
