@@ -18,10 +18,12 @@ def timeit(fn, reps=3):
 
 only = sys.argv[1] if len(sys.argv) > 1 else None
 res = []
-for (b, n, m) in [(16, 16384, 4096), (16, 4096, 1024), (16, 1024, 512), (8, 65536, 4096), (32, 16384, 1024)]:
+shapes = [(16, 16384, 4096), (16, 4096, 1024), (16, 1024, 512), (8, 65536, 4096), (32, 16384, 1024)]
+if os.environ.get("QUICK"): shapes = shapes[:2]
+for (b, n, m) in shapes:
     xyz = torch.from_numpy(synth.cloud_ground_objects(b, n, 1)).to(dev)
-    for c in (1, 2, 4, 8, 16):
-        for t in (128, 256, 512, 1024):
+    for c in ((8,) if os.environ.get("QUICK") else (1, 2, 4, 8, 16)):
+        for t in ((128,) if os.environ.get("QUICK") else (128, 256, 512, 1024)):
             os.environ["TSMDET_FPS_CLUSTER"] = str(c); os.environ["TSMDET_FPS_THREADS"] = str(t)
             cc, tt, pp, ss = (ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int())
             _lib.call("tsmdet_fps_plan", b, n, ctypes.byref(cc), ctypes.byref(tt), ctypes.byref(pp), ctypes.byref(ss))
@@ -33,6 +35,8 @@ for (b, n, m) in [(16, 16384, 4096), (16, 4096, 1024), (16, 1024, 512), (8, 6553
             r = dict(b=b, n=n, m=m, cluster=c, threads=t, P=pp.value, smem=ss.value, ms=round(ms, 4), us_per_iter=round(1000 * ms / (m - 1), 4))
             res.append(r); print(json.dumps(r), flush=True)
     os.environ.pop("TSMDET_FPS_CLUSTER"); os.environ.pop("TSMDET_FPS_THREADS")
+    ms = timeit(lambda: pu.farthest_point_sample(xyz, m)); print(json.dumps(dict(b=b, n=n, m=m, impl="default_plan", ms=round(ms, 4), us_per_iter=round(1000 * ms / (m - 1), 4))), flush=True)
+    ms = timeit(lambda: pu.farthest_point_sample_chained(xyz, m)); print(json.dumps(dict(b=b, n=n, m=m, impl="chained_root", ms=round(ms, 4), us_per_iter=round(1000 * ms / (m - 1), 4))), flush=True)
     ref = build_ref.load_ref("pointnet2_batch_cuda")
     if ref is not None and n <= 16384:
         temp = torch.full((b, n), 1e10, device=dev); idx = torch.zeros((b, m), dtype=torch.int32, device=dev)

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 300 python scripts/trace_step.py > gpurun_out/trace.log 2>&1; cat gpurun_out/trace.log | tail -16
+NO_NMS=1 timeout 300 python scripts/trace_step.py > gpurun_out/trace.log 2>&1; cat gpurun_out/trace.log | tail -28

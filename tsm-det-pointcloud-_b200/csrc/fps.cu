@@ -107,7 +107,7 @@ __device__ __forceinline__ void slot_argmax(const float (&v)[P], float& best, in
 // One cluster (1..16 CTAs) per cloud.  No CTA barrier inside the loop: every WARP publishes its
 // own candidate to every CTA of the cluster (st.async into recs[parity][warp id in cluster] +
 // complete_tx on that CTA's mbarrier), and every warp reduces the R = csize * NW records itself.
-template <int T, int P, bool WEIGHTED, bool SMEM>
+template <int T, int P, bool WEIGHTED, bool SMEM, bool CHAIN>
 __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     constexpr int NW = T / 32;
     __shared__ __align__(8) uint64_t mbar[2];
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
     // over a subset that still contains the maximiser) unless a maximum was shared by distinct points, or
     // zero-distance picks put duplicate coordinates into the set.  Both are recorded by the parent run, so
     // the common case costs a few microseconds instead of m latency-bound iterations.
-    if (!WEIGHTED && a.parent_tie != nullptr) {
+    if (CHAIN && a.parent_tie != nullptr) {
         const bool prefix_ok = a.parent_tie[cloud] >= m && m <= n && n <= a.parent_m &&
                                a.parent_vals[(size_t)cloud * a.parent_m + a.parent_m - 1] > 0.f;
         if (prefix_ok) {  // uniform across the cluster: nobody reaches the cluster barriers below
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
             return;
         }
     }
-    if (!WEIGHTED && g == 0 && a.tie_iter) a.tie_iter[cloud] = 0x7fffffff;
-    if (!WEIGHTED && g == 0 && a.vals && m > 0) a.vals[(size_t)cloud * m] = __int_as_float(0x7f800000);
+    if (CHAIN && g == 0 && a.tie_iter) a.tie_iter[cloud] = 0x7fffffff;
+    if (CHAIN && g == 0 && a.vals && m > 0) a.vals[(size_t)cloud * m] = __int_as_float(0x7f800000);
 
     if (tid == 0) {
         mbar_init(smem_u32(&mbar[0]), 1);
@@ -201,6 +201,20 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
 
     cluster_sync_all();  // peers' mbarriers are initialised past this point
 
+    // chain bookkeeping of iteration j is carried out one iteration later, inside that iteration's wait window
+    bool pend = false, pend_dup = false;
+    uint32_t pend_u = 0u, pend_gu = 0u;
+    float pend_bx = 0.f, pend_by = 0.f, pend_bz = 0.f, pend_x1 = 0.f, pend_y1 = 0.f, pend_z1 = 0.f;
+    int pend_j = 0;
+    auto settle = [&]() {
+        if (CHAIN && pend) {
+            if (a.tie_iter && pend_u == pend_gu && pend_gu != 0u &&
+                (pend_dup || pend_bx != pend_x1 || pend_by != pend_y1 || pend_bz != pend_z1))
+                atomicMin(a.tie_iter + cloud, pend_j);
+            if (g == 0 && a.vals) a.vals[(size_t)cloud * m + pend_j] = __uint_as_float(pend_gu & 0x7fffffffu);
+        }
+    };
+
     int it = 0;
     for (int j = WEIGHTED ? 0 : 1; j < m; ++j, ++it) {
         const int par = it & 1;
@@ -245,6 +259,20 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
             st_async_b32(dr + 16, db, __float_as_uint(wz));
         }
 
+        // ---- while the records are in flight (the warp would idle here): does this thread hold a SECOND slot
+        // at its own maximum?  (Chain bookkeeping only; treated as a tie whatever its coordinates -- two of one
+        // thread's strided points sharing the cloud-wide maximum is rare enough to just run the full sampler.)
+        bool mydup = false;
+        if (CHAIN && a.tie_iter) {
+            float bscan = best;
+            asm volatile("" : "+f"(bscan));  // keep the scan below the send
+            int eqc = 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) eqc += (score[p] == bscan) ? 1 : 0;
+            mydup = eqc > 1;
+            settle();  // previous iteration's record keeping
+        }
+
         // ---- all R records of this iteration
         wait_records(smem_u32(&mbar[par]), (uint32_t)((it >> 1) & 1), a.status);
         uint32_t cu = 0u, crk = 0xffffffffu;
@@ -287,28 +315,16 @@ __global__ void __launch_bounds__(T, 1) fps_kernel(const FpsArgs a) {
                 k = (int)(rr + ((grk & lowmask) << L));
             }
             idxs[j] = k;
-            if (!WEIGHTED && a.vals) a.vals[(size_t)cloud * m + j] = __uint_as_float(gu & 0x7fffffffu);
         }
-        if (!WEIGHTED && a.tie_iter) {
-            // did another point with DIFFERENT coordinates share this iteration's maximum?  (off the critical
-            // path: nothing below feeds the next iteration)
-            const float gv = __uint_as_float(gu & 0x7fffffffu);
-            bool any_eq = false;
-#pragma unroll
-            for (int p = 0; p < P; ++p) any_eq |= (md[p] == gv);
-            if (any_eq) {
-                bool tie = false;
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const float X = SMEM ? sx[p * T + tid] : px[p];
-                    const float Y = SMEM ? sy[p * T + tid] : py[p];
-                    const float Z = SMEM ? sz[p * T + tid] : pz[p];
-                    tie |= (md[p] == gv) && (X != x1 || Y != y1 || Z != z1);
-                }
-                if (tie) atomicMin(a.tie_iter + cloud, j);
-            }
+        if (CHAIN) {
+            // did another point with DIFFERENT coordinates share this iteration's maximum?  Every thread compares
+            // its own candidate with the winner (settled in the next wait window; a second maximum inside one
+            // thread was found by the scan above).
+            pend = true; pend_dup = mydup; pend_u = u; pend_gu = gu; pend_j = j;
+            pend_bx = bx; pend_by = by; pend_bz = bz; pend_x1 = x1; pend_y1 = y1; pend_z1 = z1;
         }
     }
+    settle();
 
     if (a.temp) {
 #pragma unroll
@@ -389,7 +405,10 @@ __global__ void __launch_bounds__(1024, 1)
 // ------------------------------------------------------------------------------------------
 template <int T, int P, bool WEIGHTED, bool SMEM>
 static int launch_fps(const FpsArgs& a, int b, int csize, cudaStream_t stream, int* max_clusters) {
-    auto kern = fps_kernel<T, P, WEIGHTED, SMEM>;
+    // the chain bookkeeping is compiled only into the 128-thread d-fps variants the planner picks for stacked layers
+    constexpr bool kChainable = !WEIGHTED && !SMEM && T == 128;
+    const bool chain = kChainable && (a.tie_iter != nullptr || a.parent_tie != nullptr);
+    auto kern = chain ? fps_kernel<T, P, WEIGHTED, SMEM, kChainable> : fps_kernel<T, P, WEIGHTED, SMEM, false>;
     const size_t dyn = (size_t)3 * P * T * sizeof(float) + (size_t)2 * csize * (T / 32) * sizeof(FpsRec);
     if (dyn > 227 * 1024 - 64) return TSM_ERR_INVALID;
     if (dyn > 40 * 1024) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -567,6 +586,14 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
     a.parent_m = parent_m;
     FpsPlan pl;
     if (!plan_fps(b, n, a.log2bs, weights != nullptr, true, &pl)) return TSM_ERR_INVALID;
+    if (weights != nullptr || pl.smem || pl.T != 128) {
+        // launch shapes without the chain bookkeeping: tell any follow-up level "tie at iteration 0"
+        if (tie_iter) TSM_CUDA_TRY(cudaMemsetAsync(tie_iter, 0, sizeof(int) * (size_t)b, stream));
+        a.tie_iter = nullptr;
+        a.vals = nullptr;
+        a.parent_tie = nullptr;
+        a.parent_vals = nullptr;
+    }
     if (weights) return tsm::dispatch_fps<true>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
     return tsm::dispatch_fps<false>(a, b, pl.csize, pl.T, pl.P, pl.smem, stream);
 }

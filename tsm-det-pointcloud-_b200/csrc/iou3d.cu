@@ -20,6 +20,7 @@
 //     host loop, no cudaMalloc/cudaFree per call.
 #include <math.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -250,6 +251,198 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spatial-grid candidate generation (rotated NMS): instead of testing all N(N-1)/2 pairs, boxes are
+// binned by centre into a uniform grid whose cell is at least the largest bounding-circle diameter, so two
+// boxes whose circles touch lie in the same or adjacent cells.  Pairs outside the 3x3 neighbourhood are
+// exactly the pairs the bounding-circle reject would have zeroed, so the mask is unchanged.
+struct NmsGrid {
+    float x0, y0, inv_cell;
+    int gx, gy;
+    int fallback;  // 1: non-finite boxes or a degenerate extent -> the all-pairs tile kernel handles this frame
+};
+constexpr int NMS_GMAX = 64;  // grid is at most 64 x 64 cells
+
+__device__ __forceinline__ int grid_cell(const NmsGrid& g, float cx, float cy, int& ix, int& iy) {
+    ix = min(g.gx - 1, max(0, (int)((cx - g.x0) * g.inv_cell)));
+    iy = min(g.gy - 1, max(0, (int)((cy - g.y0) * g.inv_cell)));
+    return iy * g.gx + ix;
+}
+
+// one CTA (1024 threads) per frame: extents -> cell size -> counting sort of box indices by cell
+__global__ void __launch_bounds__(1024)
+    nms_grid_build_kernel(int nmax, const int* __restrict__ counts, const BoxPrep* __restrict__ prep,
+                          NmsGrid* __restrict__ grids, int* __restrict__ cell_start, int* __restrict__ sorted) {
+    __shared__ int cnt[NMS_GMAX * NMS_GMAX];
+    __shared__ float red[5][32];
+    __shared__ int bad_s;
+    __shared__ NmsGrid g_s;
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const int n = counts ? min(counts[f], nmax) : nmax;
+    const BoxPrep* P = prep + (size_t)f * nmax;
+    int* cs = cell_start + (size_t)f * (NMS_GMAX * NMS_GMAX + 1);
+    int* so = sorted + (size_t)f * nmax;
+    if (tid == 0) bad_s = 0;
+    __syncthreads();
+    float xmin = 3.4e38f, xmax = -3.4e38f, ymin = 3.4e38f, ymax = -3.4e38f, rmax = 0.f;
+    int bad = 0;
+    for (int i = tid; i < n; i += 1024) {
+        const float cx = P[i].cx, cy = P[i].cy, r = P[i].rad;
+        if (!(fabsf(cx) < 1e30f) || !(fabsf(cy) < 1e30f) || !(r < 1e30f) || !(r >= 0.f)) bad = 1;
+        xmin = fminf(xmin, cx); xmax = fmaxf(xmax, cx);
+        ymin = fminf(ymin, cy); ymax = fmaxf(ymax, cy);
+        rmax = fmaxf(rmax, r);
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+        rmax = fmaxf(rmax, __shfl_xor_sync(FULL, rmax, o));
+    }
+    if (bad) atomicOr(&bad_s, 1);
+    if (lane == 0) { red[0][warp] = xmin; red[1][warp] = xmax; red[2][warp] = ymin; red[3][warp] = ymax; red[4][warp] = rmax; }
+    for (int i = tid; i < NMS_GMAX * NMS_GMAX; i += 1024) cnt[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 32; ++w) {
+            red[0][0] = fminf(red[0][0], red[0][w]); red[1][0] = fmaxf(red[1][0], red[1][w]);
+            red[2][0] = fminf(red[2][0], red[2][w]); red[3][0] = fmaxf(red[3][0], red[3][w]);
+            red[4][0] = fmaxf(red[4][0], red[4][w]);
+        }
+        NmsGrid g;
+        const float ex = red[1][0] - red[0][0], ey = red[3][0] - red[2][0];
+        float cell = fmaxf(2.f * red[4][0], fmaxf(ex, ey) / (float)NMS_GMAX) * 1.0001f;
+        g.fallback = (bad_s || n <= 0 || !(cell > 0.f) || !(cell < 1e30f)) ? 1 : 0;
+        if (g.fallback) cell = 1.f;
+        g.x0 = red[0][0];
+        g.y0 = red[2][0];
+        g.inv_cell = 1.f / cell;
+        g.gx = min(NMS_GMAX, max(1, (int)(ex * g.inv_cell) + 1));
+        g.gy = min(NMS_GMAX, max(1, (int)(ey * g.inv_cell) + 1));
+        if (g.fallback) { g.gx = 1; g.gy = 1; g.x0 = 0.f; g.y0 = 0.f; }
+        g_s = g;
+        grids[f] = g;
+    }
+    __syncthreads();
+    const NmsGrid g = g_s;
+    if (g.fallback) return;
+    for (int i = tid; i < n; i += 1024) {
+        int ix, iy;
+        atomicAdd(&cnt[grid_cell(g, P[i].cx, P[i].cy, ix, iy)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the 4096 counters: 4 per thread, warp scan, scan of warp totals
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = cnt[tid * 4 + k]; sum += v[k]; }
+    int inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int t = warp_tot[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, t, o);
+            if (lane >= o) t += u;
+        }
+        warp_tot[lane] = t;  // inclusive
+    }
+    __syncthreads();
+    int base = (warp ? warp_tot[warp - 1] : 0) + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cs[tid * 4 + k] = base;
+        cnt[tid * 4 + k] = base;  // becomes the scatter cursor
+        base += v[k];
+    }
+    if (tid == 1023) cs[NMS_GMAX * NMS_GMAX] = base;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        int ix, iy;
+        const int c = grid_cell(g, P[i].cx, P[i].cy, ix, iy);
+        so[atomicAdd(&cnt[c], 1)] = i;
+    }
+}
+
+// Persistent warps: warp w takes boxes i = w, w + W, ...; its lanes sweep the candidates j > i of the 3x3
+// cell neighbourhood, apply the two conservative rejects, and push survivors into a per-warp queue that is
+// drained 32 pairs at a time, so the exact IoU runs with all lanes busy and no CTA-level barrier at all.
+__global__ void __launch_bounds__(256)
+    nms_grid_pairs_kernel(int nmax, const int* __restrict__ counts, float thresh, const BoxPrep* __restrict__ prep,
+                          const NmsGrid* __restrict__ grids, const int* __restrict__ cell_start,
+                          const int* __restrict__ sorted, unsigned long long* __restrict__ mask) {
+    __shared__ unsigned int wq[8][96];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.y;
+    const NmsGrid g = grids[f];
+    if (g.fallback) return;
+    const int n = counts ? min(counts[f], nmax) : nmax;
+    const int cbmax = divup(nmax, 64);
+    const BoxPrep* P = prep + (size_t)f * nmax;
+    unsigned long long* M = mask + (size_t)f * nmax * cbmax;
+    const int* cs = cell_start + (size_t)f * (NMS_GMAX * NMS_GMAX + 1);
+    const int* so = sorted + (size_t)f * nmax;
+    const bool all_heavy = !(thresh >= 0.f);
+    unsigned int* q = wq[warp];
+    int qn = 0;  // warp-uniform
+
+    auto eval32 = [&](int count) {  // exact IoU for queue entries [qn - count, qn)
+        if (lane < count) {
+            const unsigned int e = q[qn - count + lane];
+            const int i = (int)(e >> 16), j = (int)(e & 0xffffu);
+            const BoxPrep a = P[i], b = P[j];
+            if (iou_rotated(a, b) > thresh) atomicOr(&M[(size_t)i * cbmax + (j >> 6)], 1ull << (j & 63));
+        }
+        __syncwarp();
+        qn -= count;
+    };
+
+    const int wstride = gridDim.x * 8;
+    for (int i = blockIdx.x * 8 + warp; i < n; i += wstride) {
+        const BoxPrep a = P[i];
+        int ix, iy;
+        grid_cell(g, a.cx, a.cy, ix, iy);
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = iy + dy;
+            if (yy < 0 || yy >= g.gy) continue;
+            // the (up to) three cells of a grid row are contiguous in the sorted order
+            const int xa = max(ix - 1, 0), xb = min(ix + 1, g.gx - 1);
+            const int s0 = cs[yy * g.gx + xa], s1 = cs[yy * g.gx + xb + 1];
+            for (int k0 = s0; k0 < s1; k0 += 32) {
+                const int k = k0 + lane;
+                bool heavy = false;
+                int j = 0;
+                if (k < s1) {
+                    j = so[k];
+                    if (j > i) {
+                        const BoxPrep* pb = P + j;
+                        if (all_heavy) {
+                            heavy = true;
+                        } else {
+                            BoxPrep b;  // only the fields the rejects read
+                            b.cx = pb->cx; b.cy = pb->cy; b.rad = pb->rad;
+                            b.ci = pb->ci; b.si = pb->si; b.mx = pb->mx; b.my = pb->my;
+                            heavy = !surely_disjoint(a, b) && !surely_separated(a, b);
+                        }
+                    }
+                }
+                const unsigned bal = __ballot_sync(FULL, heavy);
+                if (bal) {
+                    if (heavy) q[qn + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)i << 16) | (unsigned)j;
+                    qn += __popc(bal);
+                    __syncwarp();
+                    if (qn >= 32) eval32(32);
+                }
+            }
+        }
+    }
+    if (qn > 0) eval32(qn);
+}
+
 // Suppression words for the tiles on/above the diagonal.
 //   prep (F, nmax) per-frame prepared boxes in score order, counts (F) or null (= nmax)
 //   mask (F, nmax, cbmax) 64-bit words, ZEROED by the launcher; bits are OR-ed in.
@@ -263,12 +456,13 @@ constexpr int NMS_Q = 4096 + 2048;
 template <bool NORMAL>
 __global__ void __launch_bounds__(256)
     nms_mask_kernel(int nmax, const int* __restrict__ counts, float thresh, const BoxPrep* __restrict__ prep,
-                    unsigned long long* __restrict__ mask) {
+                    unsigned long long* __restrict__ mask, const NmsGrid* __restrict__ gate) {
     __shared__ BoxPrep srow[64], scol[64];
     __shared__ unsigned int queue[NMS_Q];
     __shared__ int qn;
     const int tid = threadIdx.x, lane = tid & 31;
     const int f = blockIdx.y;
+    if (gate && !gate[f].fallback) return;  // this frame is handled by the spatial-grid kernel
     const int n = counts ? min(counts[f], nmax) : nmax;
     const int cbmax = divup(nmax, 64);
     const int cb = divup(n, 64);
@@ -334,10 +528,13 @@ __global__ void __launch_bounds__(256)
     if (!NORMAL) drain();
 }
 
-// Greedy sweep (iou3d_nms.cpp:116-131) on the device, one CTA per frame.
+// Greedy sweep (iou3d_nms.cpp:116-131) on the device, one CTA (256 threads) per frame.
 //   keep (F, nmax) int64: kept indices (into the score-sorted boxes) in ascending order
 //   num_keep (F) int32
-__global__ void __launch_bounds__(1024)
+// Per 64-box block: one thread resolves the block against its diagonal word with the 64 words preloaded into
+// registers (a pure ALU chain, ~12 cycles per box), then all threads OR the rows of the kept boxes into the
+// removal words of the later blocks.
+__global__ void __launch_bounds__(256)
     nms_sweep_kernel(int nmax, const int* __restrict__ counts, const unsigned long long* __restrict__ mask,
                      long long* __restrict__ keep, int* __restrict__ num_keep) {
     extern __shared__ unsigned long long remv[];  // cbmax words
@@ -350,20 +547,24 @@ __global__ void __launch_bounds__(1024)
     const int cb = divup(n, 64);
     const unsigned long long* M = mask + (size_t)f * nmax * cbmax;
     long long* K = keep + (size_t)f * nmax;
-    for (int j = tid; j < cb; j += 1024) remv[j] = 0ull;
+    for (int j = tid; j < cb; j += 256) remv[j] = 0ull;
     int base = 0;
     __syncthreads();
     for (int b = 0; b < cb; ++b) {
         const int rows = min(64, n - b * 64);
-        if (tid < 64) diagw[tid] = tid < rows ? M[(size_t)(b * 64 + tid) * cbmax + b] : 0ull;
+        if (tid < 64) diagw[tid] = tid < rows ? M[(size_t)(b * 64 + tid) * cbmax + b] : ~0ull;
         __syncthreads();
         if (tid == 0) {
+            unsigned long long dw[64];
+#pragma unroll
+            for (int r = 0; r < 64; ++r) dw[r] = diagw[r];
             unsigned long long cur = remv[b], kept = 0ull;
-            for (int r = 0; r < rows; ++r) {
-                if (!((cur >> r) & 1ull)) {
-                    kept |= 1ull << r;
-                    cur |= diagw[r];
-                }
+            if (rows < 64) cur |= ~0ull << rows;  // rows beyond the frame are never kept
+#pragma unroll
+            for (int r = 0; r < 64; ++r) {
+                const bool take = !((cur >> r) & 1ull);
+                kept |= take ? (1ull << r) : 0ull;
+                cur |= take ? dw[r] : 0ull;
             }
             kept_s = kept;
         }
@@ -374,19 +575,18 @@ __global__ void __launch_bounds__(1024)
             K[pos] = (long long)(b * 64 + tid);
         }
         base += __popcll(kept);
-        // OR the rows of the boxes kept in this block into remv[j], j > b:
-        // thread = (column word j, row group g of 4 rows)
+        // OR the rows of the boxes kept in this block into remv[j], j > b: thread = (column word, 16-row group)
         {
             const int ncol = cb - b - 1;
-            const int g = tid >> 6;        // 0..15
+            const int g = tid >> 6;  // 0..3
             const int jc = tid & 63;
             for (int j0 = 0; j0 < ncol; j0 += 64) {
                 const int j = b + 1 + j0 + jc;
                 if (j < cb) {
                     unsigned long long acc = 0ull;
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int r = g * 4 + rr;
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int r = g * 16 + rr;
                         if ((kept >> r) & 1ull) acc |= M[(size_t)(b * 64 + r) * cbmax + j];
                     }
                     if (acc) atomicOr(&remv[j], acc);
@@ -415,12 +615,19 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     if (frames > 65535 || box_stride < 7) return TSM_ERR_INVALID;
     const int cbmax = tsm::divup(nmax, 64);
     const size_t prep_bytes = align_up((size_t)frames * nmax * sizeof(tsm::BoxPrep), 256);
-    const size_t mask_bytes = (size_t)frames * nmax * cbmax * sizeof(unsigned long long);
+    const size_t mask_bytes = align_up((size_t)frames * nmax * cbmax * sizeof(unsigned long long), 256);
+    const size_t grid_bytes = align_up((size_t)frames * sizeof(tsm::NmsGrid), 256);
+    const size_t cs_bytes = align_up((size_t)frames * (tsm::NMS_GMAX * tsm::NMS_GMAX + 1) * sizeof(int), 256);
+    const size_t so_bytes = align_up((size_t)frames * nmax * sizeof(int), 256);
     void* scratch = nullptr;
-    int rc = tsm_scratch_get(0, prep_bytes + mask_bytes, s, &scratch);
+    int rc = tsm_scratch_get(0, prep_bytes + mask_bytes + grid_bytes + cs_bytes + so_bytes, s, &scratch);
     if (rc != TSM_OK) return rc;
-    tsm::BoxPrep* prep = (tsm::BoxPrep*)scratch;
-    unsigned long long* mask = (unsigned long long*)((char*)scratch + prep_bytes);
+    char* sp = (char*)scratch;
+    tsm::BoxPrep* prep = (tsm::BoxPrep*)sp;
+    unsigned long long* mask = (unsigned long long*)(sp + prep_bytes);
+    tsm::NmsGrid* grids = (tsm::NmsGrid*)(sp + prep_bytes + mask_bytes);
+    int* cell_start = (int*)(sp + prep_bytes + mask_bytes + grid_bytes);
+    int* sorted = (int*)(sp + prep_bytes + mask_bytes + grid_bytes + cs_bytes);
     const int total = frames * nmax;
     tsm::prep_boxes_kernel<<<tsm::divup(total, 128), 128, 0, s>>>(total, boxes, box_stride, prep);
     TSM_LAUNCH_CHECK();
@@ -428,19 +635,29 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     const long tiles = (long)cbmax * (cbmax + 1) / 2;
     int per_frame = (2 * tsm_num_sms() + frames - 1) / frames;  // ~2 CTAs per SM in total
-    if (per_frame > tiles) per_frame = (int)tiles;
     if (per_frame < 1) per_frame = 1;
-    dim3 grid((unsigned)per_frame, (unsigned)frames);
+    // rotated NMS with a sane threshold: spatial-grid candidates; the all-pairs tile kernel then only serves
+    // frames the grid builder flagged (non-finite boxes).  A negative/NaN threshold lets IoU == 0 suppress, so
+    // every pair matters and only the tile kernel is exact.
+    const bool use_grid = !normal && (thresh >= 0.f);
+    if (use_grid) {
+        tsm::nms_grid_build_kernel<<<frames, 1024, 0, s>>>(nmax, counts, prep, grids, cell_start, sorted);
+        TSM_LAUNCH_CHECK();
+        dim3 pgrid((unsigned)std::min(per_frame, tsm::divup(nmax, 8)), (unsigned)frames);
+        tsm::nms_grid_pairs_kernel<<<pgrid, 256, 0, s>>>(nmax, counts, thresh, prep, grids, cell_start, sorted, mask);
+        TSM_LAUNCH_CHECK();
+    }
+    dim3 grid((unsigned)std::min<long>(per_frame, tiles), (unsigned)frames);
     if (normal)
-        tsm::nms_mask_kernel<true><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask);
+        tsm::nms_mask_kernel<true><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask, nullptr);
     else
-        tsm::nms_mask_kernel<false><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask);
+        tsm::nms_mask_kernel<false><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask, use_grid ? grids : nullptr);
     TSM_LAUNCH_CHECK();
     const size_t dyn = (size_t)cbmax * sizeof(unsigned long long);
     if (dyn > 200 * 1024) return TSM_ERR_INVALID;
     if (dyn > 48 * 1024)
         TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    tsm::nms_sweep_kernel<<<frames, 1024, dyn, s>>>(nmax, counts, mask, keep, num_keep);
+    tsm::nms_sweep_kernel<<<frames, 256, dyn, s>>>(nmax, counts, mask, keep, num_keep);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }

@@ -29,7 +29,7 @@ from .sharding import gather_detections
 
 class SABackboneNMS(torch.nn.Module):
     def __init__(self, precision: str = "bf16", nms_pre: float = 0.01, nms_post: float = 0.1, k_post: int = 512,
-                 seed: int = 0, use_graph: bool = True):
+                 seed: int = 0, use_graph: bool = True, chain_fps: bool = False):
         super().__init__()
         torch.manual_seed(seed)
         self.backbone = kitti_sa_stack(fused=True, precision=precision)
@@ -41,6 +41,10 @@ class SABackboneNMS(torch.nn.Module):
         self.precision = precision
         self.nms_pre, self.nms_post, self.k_post = nms_pre, nms_post, k_post
         self.use_graph = use_graph
+        # chained samplers (tsmdet_fps_chain) skip levels 2/3 when the level-1 run proves it exact, but the
+        # bookkeeping costs ~17 % of level 1 and one tied cloud in the batch forfeits the saving: measured a wash
+        # at 16 clouds per step, a win for small batches -- so it is opt-in here.
+        self.chain_fps = chain_fps
         self.nms_after_fps = os.environ.get("TSMDET_NMS_AFTER_FPS", "0") != "0"
         self._graphs: Dict[tuple, dict] = {}
         self._streams = None
@@ -93,7 +97,10 @@ class SABackboneNMS(torch.nn.Module):
         # stream A (current): the FPS chain
         state = None
         for layer in layers:
-            idx, state = pointnet2_utils.farthest_point_sample_chained(cur_xyz, layer.npoint_list[0], state)
+            if self.chain_fps:
+                idx, state = pointnet2_utils.farthest_point_sample_chained(cur_xyz, layer.npoint_list[0], state)
+            else:
+                idx = pointnet2_utils.farthest_point_sample(cur_xyz, layer.npoint_list[0])
             new_xyz = gather_xyz(cur_xyz, idx)
             mark(f"fps{len(ready) + 1}", main)
             ev = torch.cuda.Event()

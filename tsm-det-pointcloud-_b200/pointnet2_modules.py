@@ -281,8 +281,9 @@ class PointNet2SAStack(nn.Module):
 
     def __init__(self, npoints: Sequence[int], radii: Sequence[Sequence[float]], nsamples: Sequence[Sequence[int]],
                  mlps: Sequence[Sequence[Sequence[int]]], in_channels: int = 1, fused: bool = True,
-                 precision: str = "fp32"):
+                 precision: str = "fp32", chain_fps: bool = True):
         super().__init__()
+        self.chain_fps = chain_fps
         self.layers = nn.ModuleList()
         c = in_channels
         for npoint, r, ns, specs in zip(npoints, radii, nsamples, mlps):
@@ -299,7 +300,10 @@ class PointNet2SAStack(nn.Module):
         state = None
         for layer in self.layers:
             # every layer here is one d-fps over all of the previous layer's centres: chain the samplers
-            idx, state = pointnet2_utils.farthest_point_sample_chained(xyz.contiguous(), layer.npoint_list[0], state)
+            if self.chain_fps:
+                idx, state = pointnet2_utils.farthest_point_sample_chained(xyz.contiguous(), layer.npoint_list[0], state)
+            else:
+                idx = pointnet2_utils.farthest_point_sample(xyz.contiguous(), layer.npoint_list[0])
             new_xyz = gather_xyz(xyz.contiguous(), idx)
             xyz, features, _ = layer(xyz, features, new_xyz=new_xyz)
             outs.append((xyz, features, idx))
