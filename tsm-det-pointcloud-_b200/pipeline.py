@@ -129,10 +129,18 @@ class SABackboneNMS(torch.nn.Module):
                 s_nms.wait_event(ready[-1])
             det_idx, det_num = self._nms_two_pass(boxes, scores)
             mark("nms", s_nms)
+            # fixed-size detection records (F, K, 9) = box(7), score, 0 -- what the ranks exchange at N > 1
+            f, k = det_idx.shape
+            live = det_idx >= 0
+            safe_k = torch.where(live, det_idx, torch.zeros_like(det_idx))
+            rec = torch.zeros((f, k, 9), dtype=torch.float32, device=dev)
+            rec[:, :, :7] = torch.gather(boxes[:, :, :7], 1, safe_k.unsqueeze(-1).expand(-1, -1, 7))
+            rec[:, :, 7] = torch.gather(scores, 1, safe_k)
+            rec = rec * live.unsqueeze(-1)
         main.wait_stream(s_sa)
         main.wait_stream(s_nms)
         mark("end", main)
-        return {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num}
+        return {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num, "det": rec}
 
     def trace_step(self, xyz, feats, boxes, scores):
         """Runs the DAG eagerly with timing events; returns [(name, ms since start)] (diagnostics)."""
@@ -189,14 +197,11 @@ class SABackboneNMS(torch.nn.Module):
         else:
             res = self._run(xyz, feats, boxes, scores)
         if gather:
-            det_idx, det_num = res["det_idx"], res["det_num"]
-            f, k = det_idx.shape
-            safe_k = torch.where(det_idx >= 0, det_idx, torch.zeros_like(det_idx))
-            rec = torch.zeros((f, k, 9), dtype=torch.float32, device=boxes.device)
-            rec[:, :, :7] = torch.gather(boxes[:, :, :7], 1, safe_k.unsqueeze(-1).expand(-1, -1, 7))
-            rec[:, :, 7] = torch.gather(scores, 1, safe_k)
-            rec = rec * (det_idx >= 0).unsqueeze(-1)
-            res["all_det"], res["all_num"] = gather_detections(rec, det_num)
+            # the one collective of the path: every rank receives every rank's records (equal shards, so the
+            # sizes are known without a size exchange or a host sync)
+            world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+            res["all_det"], res["all_num"] = gather_detections(res["det"], res["det_num"],
+                                                               frames_total=res["det"].shape[0] * world)
         return res
 
     def static_inputs(self, xyz, feats, boxes, scores):
