@@ -63,6 +63,11 @@ int tsmdet_furthest_point_sampling_matrix(int b, int n, int m, const float* matr
 int tsmdet_furthest_point_sampling_with_weighted_dist(int b, int n, int m, const float* matrix, const float* weights,
                                                       float* temp, int* idxs, void* stream);
 
+/* Process-wide choice between the two d-FPS kernels (identical results): 0 = auto (by batch size), 1 = one
+ * thread-block cluster per cloud (lowest pick latency while clouds <= SMs/8), 2 = one CTA per cloud with exact
+ * spatial pruning (one SM per cloud; N <= 16384).  No reference counterpart (the reference has one kernel). */
+int tsmdet_fps_configure(int algo);
+
 /* Introspection: the cluster size / block size / points per thread the sampler would use. */
 int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread, int* smem_xyz);
 

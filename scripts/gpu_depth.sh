@@ -1,13 +1,14 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_query_group_gpu.py -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/test_query_group_gpu.log 2>&1; echo "exit $?"; tail -4 gpurun_out/test_query_group_gpu.log
-for dpt in 1 2 3; do
+timeout 1200 python -m pytest tests/test_fps_gpu.py -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/test_fps_gpu.log 2>&1; echo "exit $?"; tail -4 gpurun_out/test_fps_gpu.log
+for dpt in ${DEPTHS:-1 2 3}; do
 timeout 600 python bench.py --steps 30 --warmup 6 --precision bf16 --no-cpu-baseline --depth $dpt > gpurun_out/bench_d$dpt.log 2> gpurun_out/bench_d$dpt.err; echo "bench $dpt $?"
 tail -3 gpurun_out/bench_d$dpt.err
 done
 python - <<'PY'
 import json
-for dpt in (1,2,3):
+import os
+for dpt in [int(x) for x in os.environ.get("DEPTHS","1 2 3").split()]:
   try:
     d=json.loads(open(f'gpurun_out/bench_d{dpt}.log').read().strip().splitlines()[-1])
     print(dpt, round(d['value'],1), round(d['ms_per_step'],3), d['e2e']['value'], d['gpu_launches'], d['config']['ms_per_step_single_in_flight'], d['clocks'])

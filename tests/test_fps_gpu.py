@@ -43,12 +43,61 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("algo", ["cluster", "bucket"])
 @pytest.mark.parametrize("name,gen,m", CASES, ids=[c[0] for c in CASES])
-def test_fps_matches_oracle(orc, name, gen, m):
+def test_fps_matches_oracle(orc, name, gen, m, algo, monkeypatch):
+    """Both d-FPS kernels: the cluster kernel (fps.cu) and the spatially pruned single-CTA kernel
+    (fps_bucket.cu; clouds above 16384 points stay on the cluster kernel)."""
+    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
     xyz = gen()
     got = _fps(xyz, m)
     want = orc.fps(xyz, m)
     assert np.array_equal(got, want), f"{name}: first mismatch at {np.argwhere(got != want)[:3]}"
+
+
+@pytest.mark.parametrize("threads,pts", [(32, 4), (64, 32), (128, 8), (256, 16), (512, 8), (512, 32), (1024, 4), (1024, 16)])
+def test_fps_bucket_every_launch_shape(orc, threads, pts, monkeypatch):
+    """Threads x points-per-lane only changes which lane owns which (spatially sorted) point, never a pick."""
+    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
+    monkeypatch.setenv("TSMDET_FPSB_T", str(threads))
+    monkeypatch.setenv("TSMDET_FPSB_P", str(pts))
+    cap = threads * pts
+    for xyz, m in [(synth.cloud_dup_padded(2, min(cap, 4096), 20 + pts), 300),
+                   (synth.cloud_lattice(3, min(cap, 2500) - 3, 30 + pts), 120),
+                   (synth.cloud_ground_objects(2, cap, 40 + pts), 257)]:
+        got = _fps(xyz, min(m, xyz.shape[1]))
+        assert np.array_equal(got, orc.fps(xyz, min(m, xyz.shape[1])))
+
+
+def test_fps_bucket_degenerate_clouds(orc, monkeypatch):
+    """Grid construction edge cases: zero extent on one, two or all axes; clouds spanning huge ranges; exact
+    duplicates only; initial min-distances handed in through temp."""
+    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
+    rng = np.random.default_rng(7)
+    flat = synth.cloud_uniform(2, 3000, 61)
+    flat[:, :, 2] = 1.5
+    line = synth.cloud_uniform(2, 2000, 62)
+    line[:, :, 1:] = 0.25
+    huge = (rng.standard_normal((2, 5000, 3)) * 1e6).astype(np.float32)
+    tiny = (rng.standard_normal((2, 5000, 3)) * 1e-6).astype(np.float32)
+    two = np.repeat(np.array([[[0, 0, 0], [1, 2, 3]]], np.float32), 700, axis=1)
+    for name, xyz, m in [("flat", flat, 500), ("line", line, 500), ("huge", huge, 400), ("tiny", tiny, 400), ("two", two, 64)]:
+        got = _fps(xyz, m)
+        assert np.array_equal(got, orc.fps(xyz, m)), name
+    from tsmdet_b200 import pointnet2_batch_cuda as ext
+
+    xyz = synth.cloud_dup_padded(2, 6000, 63)
+    t0 = rng.uniform(0.0, 30.0, size=(2, 6000)).astype(np.float32)
+    x = torch.from_numpy(xyz).to(_dev())
+    temp = torch.from_numpy(t0.copy()).to(_dev())
+    idx = torch.zeros((2, 200), dtype=torch.int32, device=_dev())
+    ext.farthest_point_sampling_wrapper(2, 6000, 200, x, temp, idx)
+    monkeypatch.setenv("TSMDET_FPS_ALGO", "cluster")
+    temp2 = torch.from_numpy(t0.copy()).to(_dev())
+    idx2 = torch.zeros((2, 200), dtype=torch.int32, device=_dev())
+    ext.farthest_point_sampling_wrapper(2, 6000, 200, x, temp2, idx2)
+    assert torch.equal(idx, idx2)
+    assert torch.equal(temp.view(torch.int32), temp2.view(torch.int32))
 
 
 @pytest.mark.parametrize("csize", [1, 2, 4, 8, 16])
@@ -62,7 +111,13 @@ def test_fps_every_launch_shape(orc, csize, threads, monkeypatch):
         assert np.array_equal(got, orc.fps(xyz, m))
 
 
-def test_fps_kitti_full_size(orc):
+@pytest.mark.parametrize("algo", ["cluster", "bucket"])
+def test_fps_kitti_full_size(orc, algo, monkeypatch):
+    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    _fps_kitti_full_size(orc)
+
+
+def _fps_kitti_full_size(orc):
     """BASELINE config-2 layer 1: 16384 -> 4096 on duplicate-padded and structured clouds, B=16 (oracle
     checks 2 clouds; all 16 are checked through size-independent properties)."""
     xyz = np.concatenate([synth.cloud_dup_padded(8, 16384, 40), synth.cloud_ground_objects(8, 16384, 41)], 0)
@@ -86,7 +141,13 @@ def test_fps_large_clouds(orc):
     assert np.array_equal(_fps(xyz, 128)[[0, 19]], orc.fps(xyz[[0, 19]], 128))
 
 
-def test_fps_temp_scratch_contract(orc):
+@pytest.mark.parametrize("algo", ["cluster", "bucket"])
+def test_fps_temp_scratch_contract(orc, algo, monkeypatch):
+    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    _fps_temp_scratch_contract(orc)
+
+
+def _fps_temp_scratch_contract(orc):
     """temp comes in as the initial min-distance and leaves as the final one (SURVEY.md 8b ownership)."""
     from tsmdet_b200 import pointnet2_batch_cuda as ext
 
@@ -160,7 +221,13 @@ def test_fps_golden():
     ("lattice", lambda: synth.cloud_lattice(3, 6000, 72), False),            # equal distances between distinct points
     ("few_unique", lambda: synth.cloud_dup_padded(2, 5000, 73, unique_frac=0.3), False),  # zero-distance picks
 ], ids=["objects", "dup", "lattice", "few_unique"])
-def test_fps_chained_levels_match_plain_fps(orc, name, gen, shortcut):
+@pytest.mark.parametrize("algo", ["cluster", "bucket"])
+def test_fps_chained_levels_match_plain_fps(orc, name, gen, shortcut, algo, monkeypatch):
+    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    _fps_chained_levels(orc, name, gen, shortcut)
+
+
+def _fps_chained_levels(orc, name, gen, shortcut):
     """Stacked samplers (4096 -> 1024 -> 512 of the previous level's centres): the chained entry point must
     return exactly what the plain sampler returns at every level, shortcut or not."""
     from tsmdet_b200 import pointnet2_utils as pu

@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsmdet_b200.so")
+# TSMDET_LIB: load another build of the same C ABI (instrumented builds made by scripts/; never a fallback)
+LIB_PATH = os.environ.get("TSMDET_LIB") or os.path.join(_HERE, "libtsmdet_b200.so")
 
 
 class TsmdetError(RuntimeError):
@@ -50,6 +51,7 @@ SIGNATURES = {
     "tsmdet_furthest_point_sampling_with_weighted_dist": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                           c_void_p],
     "tsmdet_fps_plan": [c_int, c_int, _i, _i, _i, _i],
+    "tsmdet_fps_configure": [c_int],
     "tsmdet_gather_points": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_gather_points_grad": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_gather_xyz": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -104,7 +106,7 @@ def check(status: int, where: str) -> None:
 KERNELS_PER_CALL = {
     "tsmdet_nms_batch": 5, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 5, "tsmdet_nms_normal_gpu": 3,
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
-    "tsmdet_fps_plan": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 2, "tsmdet_ball_query_dilated": 2, "tsmdet_sa_mlp_maxpool": 3,
+    "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 2, "tsmdet_ball_query_dilated": 2, "tsmdet_sa_mlp_maxpool": 3,
 }
 launch_count = 0
 

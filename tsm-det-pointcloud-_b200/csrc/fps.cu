@@ -24,27 +24,13 @@
 //        rank(k) = (bitrev_L(k mod bs) << (32-L)) | (k / bs),  bs = 2^L = opt_n_threads(N)
 //    and the whole argmax is a max over the 64-bit key (ordered(value), ~rank).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "fps.cuh"
 
 namespace tsm {
-
-struct FpsArgs {
-    const float* xyz;      // (B,N,3)
-    const float* weights;  // (B,N) or nullptr
-    float* temp;           // (B,N) or nullptr; in: initial min-dist, out: final min-dist
-    int* idxs;             // (B,M)
-    int n, m;
-    int log2bs;  // log2 of the reference block size (cuda_utils.h:10-14)
-    int* status;
-    // ---- chaining (optional; see tsmdet_fps_chain): per-cloud tie/value records of this run ...
-    int* tie_iter;     // (B) out: first iteration whose maximum was shared by points with different coordinates
-    float* vals;       // (B,M) out: the winning min-distance of every iteration (vals[0] = +inf)
-    // ... and of the run that produced this cloud as ITS first parent_m picks, in order
-    const int* parent_tie;
-    const float* parent_vals;
-    int parent_m;
-};
 
 struct __align__(16) FpsRec {
     uint32_t u, rank;
@@ -63,20 +49,6 @@ __device__ __forceinline__ void wait_records(uint32_t bar, uint32_t phase, int* 
     while (!mbar_try_wait_cta(bar, phase)) {
         if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
     }
-}
-
-// (u desc, rank asc) argmax across the warp.  Returns the winning lane; wu / wrk are warp-uniform.
-// The common case (a unique maximum) costs one redux + one ballot.
-__device__ __forceinline__ int warp_pick(uint32_t u, uint32_t rk, uint32_t& wu, uint32_t& wrk) {
-    wu = __reduce_max_sync(FULL, u);
-    const unsigned tie = __ballot_sync(FULL, u == wu);
-    if (__popc(tie) == 1) {
-        const int wl = __ffs(tie) - 1;
-        wrk = __shfl_sync(FULL, rk, wl);
-        return wl;
-    }
-    wrk = __reduce_min_sync(FULL, (u == wu) ? rk : 0xffffffffu);
-    return __ffs(__ballot_sync(FULL, u == wu && rk == wrk)) - 1;
 }
 
 // Per-thread argmax over P register slots as a balanced tree (short dependency chains; one warp per
@@ -467,6 +439,8 @@ static int ref_log2_block(int n) {
     return l;
 }
 
+static int g_fps_algo = 0;  // 0 auto, 1 cluster kernel, 2 bucketed single-CTA kernel
+
 struct FpsPlan {
     int csize, T, P;
     bool smem;
@@ -584,6 +558,19 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
     a.parent_tie = parent_tie;
     a.parent_vals = parent_vals;
     a.parent_m = parent_m;
+    // Two kernels.  The cluster kernel (this file) has the shorter pick latency when every cloud can have a
+    // full 8-CTA cluster to itself; the spatially pruned single-CTA kernel (fps_bucket.cu) needs one SM per
+    // cloud and wins whenever clouds outnumber clusters -- large batches, or several batches in flight.
+    // auto: by batch size; tsmdet_fps_configure() / TSMDET_FPS_ALGO = cluster | bucket override, and an explicit
+    // cluster launch shape (tuning / tests) implies "cluster".
+    {
+        int algo = g_fps_algo;
+        if (const char* e = getenv("TSMDET_FPS_ALGO")) algo = !strcmp(e, "cluster") ? 1 : (!strcmp(e, "bucket") ? 2 : algo);
+        if (getenv("TSMDET_FPS_CLUSTER") || getenv("TSMDET_FPS_THREADS")) algo = 1;
+        const bool fits = tsm_fps_bucket_supports(n, weights != nullptr);
+        const bool crowded = (long)b * 8 > tsm_num_sms();
+        if (fits && (algo == 2 || (algo == 0 && crowded && n >= 1024))) return tsm_fps_bucket_launch(a, b, stream);
+    }
     FpsPlan pl;
     if (!plan_fps(b, n, a.log2bs, weights != nullptr, true, &pl)) return TSM_ERR_INVALID;
     if (weights != nullptr || pl.smem || pl.T != 128) {
@@ -610,6 +597,14 @@ int tsmdet_fps_plan(int b, int n, int* csize, int* threads, int* pts_per_thread,
     if (threads) *threads = pl.T;
     if (pts_per_thread) *pts_per_thread = pl.P;
     if (smem_xyz) *smem_xyz = pl.smem ? 1 : 0;
+    return TSM_OK;
+}
+
+// Process-wide choice of the d-FPS kernel: 0 = auto (by batch size), 1 = cluster kernel, 2 = bucketed
+// single-CTA kernel (clouds of <= 16384 points; others keep the cluster kernel).  Results are identical.
+int tsmdet_fps_configure(int algo) {
+    if (algo < 0 || algo > 2) return TSM_ERR_INVALID;
+    g_fps_algo = algo;
     return TSM_OK;
 }
 

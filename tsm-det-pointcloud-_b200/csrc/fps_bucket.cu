@@ -1,0 +1,502 @@
+// fps_bucket.cu -- furthest point sampling with exact spatial pruning, one CTA per cloud (N <= 16384).
+//
+// Replaces (same indices, bit for bit) farthest_point_sampling_kernel / furthest_point_sampling_kernel,
+//   /root/reference/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:100-216, 588-704
+// for clouds that fit one SM.  The reference (and fps.cu) touch all N points for every pick: M*N updates.
+// A pick only lowers the running min-distance of points closer to it than their current min-distance,
+// and after i picks that is ~N/i points.  So:
+//
+//  * a prologue sorts the cloud into Morton order of an adaptive grid (counting sort in shared memory:
+//    histogram -> scan -> scatter), so that every LANE owns P spatially compact points and keeps their
+//    bounding box and running min-distances in registers; the coordinates live in shared memory as
+//    float4-readable planes (192 KB at N = 16384), the original indices as u16 next to them (32 KB), and
+//    one bounding box per 16 lanes in what is left of the 227 KB;
+//  * per pick, a lane computes a lower bound of the squared distance from the pick to its group's box with
+//    the SAME rounded operations as the point distance (fsub, fmul, 2 fma; each is monotone, so the bound
+//    never exceeds any member's computed distance).  If bound >= the lane's largest min-distance no
+//    member can change and the lane is skipped; a warp whose 32 lanes all skip does nothing but re-post
+//    its cached candidate.  Skipped updates are no-ops by construction, so every min-distance -- and
+//    therefore every pick -- is bit-identical to the brute force;
+//  * one __syncthreads per pick: warps post (key, position) records, every warp reduces the <= 32
+//    records itself (redux.sync), and the reference's tie rule -- among equal maxima the smallest
+//    rank(k) = bitrev(k mod bs) : k / bs -- is evaluated lazily, only when a maximum is shared.
+//
+// One SM per cloud instead of a cluster of eight, and ~2x fewer cycles per pick: see DESIGN.md 4.1.
+#include "fps.cuh"
+
+namespace tsm {
+
+constexpr int kBucketMaxN = 16384;
+constexpr int kMiscBytes = 512 + 768 + 128 + 16;  // candidate records, box partials, scan offsets, point 0
+
+// planes (12 B per slot) | original indices (2 B per slot) | one box per 16 lanes (24 B); the prologue's cell
+// histogram aliases the front
+__host__ __device__ __forceinline__ size_t bucket_main_bytes(int cap, int threads, int cell_bits) {
+    size_t a = (size_t)14 * cap + (size_t)24 * (threads / 16), h = (size_t)4 << cell_bits;
+    size_t mx = a > h ? a : h;
+    return (mx + 15) & ~(size_t)15;
+}
+
+template <int P>
+__device__ __forceinline__ int slot_index(int s) {  // sorted position -> shared-memory element index
+    const int p = s & (P - 1), l = (s / P) & 31, w = s / (32 * P);
+    return w * (32 * P) + (p >> 2) * 128 + l * 4 + (p & 3);
+}
+
+__device__ __forceinline__ uint32_t ref_rank(uint32_t k, int L) {
+    return (L == 0) ? k : (__brev(k & ((1u << L) - 1u)) | (k >> L));
+}
+
+template <int T, int P>
+__global__ void __launch_bounds__(T, 1)
+    fps_bucket_kernel(const FpsArgs a, const int cell_bits) {
+    constexpr int NW = T / 32;
+    constexpr int CAP = T * P;
+    constexpr int C4 = P / 4;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float* const sx = reinterpret_cast<float*>(dyn);
+    float* const sy = sx + CAP;
+    float* const sz = sy + CAP;
+    uint16_t* const sk = reinterpret_cast<uint16_t*>(sz + CAP);         // original index of every slot
+    float4* const sbox4 = reinterpret_cast<float4*>(sk + CAP);          // [T/16] {x lo, x hi, y lo, y hi}
+    float2* const sbox2 = reinterpret_cast<float2*>(sbox4 + T / 16);    // [T/16] {z lo, z hi}
+    uint32_t* const hist = reinterpret_cast<uint32_t*>(dyn);  // prologue only; aliases the planes
+    unsigned char* const misc = dyn + bucket_main_bytes(CAP, T, cell_bits);
+    uint2* const recs = reinterpret_cast<uint2*>(misc);                      // [2][32] warp candidates
+    float* const red = reinterpret_cast<float*>(misc + 512);                 // [6][32] box partials
+    uint32_t* const woff = reinterpret_cast<uint32_t*>(misc + 512 + 768);    // [32] scan offsets
+    float* const first_xyz = reinterpret_cast<float*>(misc + 512 + 768 + 128);  // point 0
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const int n = a.n, m = a.m, L = a.log2bs;
+    const float* __restrict__ xyz = a.xyz + (size_t)cloud * n * 3;
+    int* __restrict__ idxs = a.idxs + (size_t)cloud * m;
+    const bool chain = a.tie_iter != nullptr;
+
+    // ---- chained shortcut (see fps.cu / tsmdet_fps_chain): this cloud is the first n picks of a recorded run
+    if (a.parent_tie != nullptr) {
+        const bool prefix_ok = a.parent_tie[cloud] >= m && m <= n && n <= a.parent_m &&
+                               a.parent_vals[(size_t)cloud * a.parent_m + a.parent_m - 1] > 0.f;
+        if (prefix_ok) {
+            for (int j = tid; j < m; j += T) {
+                idxs[j] = j;
+                if (a.vals) a.vals[(size_t)cloud * m + j] = a.parent_vals[(size_t)cloud * a.parent_m + j];
+            }
+            if (tid == 0 && a.tie_iter) a.tie_iter[cloud] = a.parent_tie[cloud];
+            return;
+        }
+    }
+    if (tid == 0 && a.tie_iter) a.tie_iter[cloud] = 0x7fffffff;
+    if (tid == 0 && a.vals && m > 0) a.vals[(size_t)cloud * m] = __int_as_float(0x7f800000);
+
+    // ================= prologue: spatial sort =================
+    // (1) bounding box of the cloud
+    float lo0 = __int_as_float(0x7f800000), lo1 = lo0, lo2 = lo0, hi0 = -lo0, hi1 = -lo0, hi2 = -lo0;
+    for (int k = tid; k < n; k += T) {
+        const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+        lo0 = fminf(lo0, x); hi0 = fmaxf(hi0, x);
+        lo1 = fminf(lo1, y); hi1 = fmaxf(hi1, y);
+        lo2 = fminf(lo2, z); hi2 = fmaxf(hi2, z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fminf(lo0, __shfl_xor_sync(FULL, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(FULL, hi0, o));
+        lo1 = fminf(lo1, __shfl_xor_sync(FULL, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(FULL, hi1, o));
+        lo2 = fminf(lo2, __shfl_xor_sync(FULL, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(FULL, hi2, o));
+    }
+    if (lane == 0) {
+        red[0 * 32 + warp] = lo0; red[1 * 32 + warp] = lo1; red[2 * 32 + warp] = lo2;
+        red[3 * 32 + warp] = hi0; red[4 * 32 + warp] = hi1; red[5 * 32 + warp] = hi2;
+    }
+    const int ncells = 1 << cell_bits;
+    for (int c = tid; c < ncells; c += T) hist[c] = 0u;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+        lo0 = fminf(lo0, red[0 * 32 + w]); lo1 = fminf(lo1, red[1 * 32 + w]); lo2 = fminf(lo2, red[2 * 32 + w]);
+        hi0 = fmaxf(hi0, red[3 * 32 + w]); hi1 = fmaxf(hi1, red[4 * 32 + w]); hi2 = fmaxf(hi2, red[5 * 32 + w]);
+    }
+    // (2) grid: cell_bits bits of Morton key, handed out greedily to the axis with the largest cell extent
+    float e0 = hi0 - lo0, e1 = hi1 - lo1, e2 = hi2 - lo2;
+    if (!(e0 > 0.f) || !(e0 < 3.0e38f)) e0 = 0.f;
+    if (!(e1 > 0.f) || !(e1 < 3.0e38f)) e1 = 0.f;
+    if (!(e2 > 0.f) || !(e2 < 3.0e38f)) e2 = 0.f;
+    int nb0 = 0, nb1 = 0, nb2 = 0;
+    uint32_t order = 0u;  // 2 bits per key bit, most significant key bit first
+    {
+        float c0 = e0, c1 = e1, c2 = e2;
+        for (int i = 0; i < cell_bits; ++i) {
+            int ax = 0;
+            if (c1 > c0 && c1 >= c2) ax = 1;
+            if (c2 > c0 && c2 > c1) ax = 2;
+            order |= (uint32_t)ax << (2 * i);
+            if (ax == 0) { ++nb0; c0 *= 0.5f; }
+            else if (ax == 1) { ++nb1; c1 *= 0.5f; }
+            else { ++nb2; c2 *= 0.5f; }
+        }
+    }
+    const float inv0 = e0 > 0.f ? (float)(1 << nb0) / e0 : 0.f;
+    const float inv1 = e1 > 0.f ? (float)(1 << nb1) / e1 : 0.f;
+    const float inv2 = e2 > 0.f ? (float)(1 << nb2) / e2 : 0.f;
+    auto cell_key = [&](float x, float y, float z) -> uint32_t {
+        const int q0 = min(max(__float2int_rd((x - lo0) * inv0), 0), (1 << nb0) - 1);
+        const int q1 = min(max(__float2int_rd((y - lo1) * inv1), 0), (1 << nb1) - 1);
+        const int q2 = min(max(__float2int_rd((z - lo2) * inv2), 0), (1 << nb2) - 1);
+        int r0 = nb0, r1 = nb1, r2 = nb2;
+        uint32_t key = 0u;
+        for (int i = 0; i < cell_bits; ++i) {
+            const uint32_t ax = (order >> (2 * i)) & 3u;
+            uint32_t bit;
+            if (ax == 0u) bit = (q0 >> --r0) & 1;
+            else if (ax == 1u) bit = (q1 >> --r1) & 1;
+            else bit = (q2 >> --r2) & 1;
+            key = (key << 1) | bit;
+        }
+        return key;
+    };
+    // (3) histogram over cells; this thread's points are k = tid + i*T (coalesced reads)
+    uint32_t packed[P / 2];  // two u16 per register: first the cell keys, later the sorted positions
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = tid + i * T;
+        uint32_t key = 0xffffu;
+        if (k < n) {
+            key = cell_key(__ldg(xyz + 3 * k), __ldg(xyz + 3 * k + 1), __ldg(xyz + 3 * k + 2));
+            atomicAdd(&hist[key], 1u);
+        }
+        if (i & 1) packed[i >> 1] |= key << 16;
+        else packed[i >> 1] = key;
+    }
+    __syncthreads();
+    // (4) exclusive scan of the histogram: warp w owns ncells/NW consecutive cells
+    {
+        const int cpw = ncells / NW;
+        uint32_t carry = 0u;
+        for (int c = warp * cpw + lane; c < (warp + 1) * cpw; c += 32) {
+            const uint32_t v = hist[c];
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            hist[c] = carry + inc - v;
+            carry += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) woff[warp] = carry;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = lane < NW ? woff[lane] : 0u;
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane < NW) woff[lane] = inc - v;
+        }
+        __syncthreads();
+        // (5) sorted position of every point (order inside a cell is arbitrary -- it only decides which lane
+        //     owns a point, never a result)
+        const int cshift = cell_bits - (31 - __clz(NW));  // log2(cpw)
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const uint32_t key = (i & 1) ? (packed[i >> 1] >> 16) : (packed[i >> 1] & 0xffffu);
+            uint32_t s = 0xffffu;
+            if (key != 0xffffu) s = atomicAdd(&hist[key], 1u) + woff[key >> cshift];
+            if (i & 1) packed[i >> 1] = (packed[i >> 1] & 0xffffu) | (s << 16);
+            else packed[i >> 1] = (packed[i >> 1] & 0xffff0000u) | s;
+        }
+    }
+    __syncthreads();  // the histogram is dead; its bytes become the coordinate planes
+    // (6) scatter coordinates + original index to the sorted position; zero the padding slots
+    for (int s = n + tid; s < CAP; s += T) {
+        const int e = slot_index<P>(s);
+        sx[e] = 0.f; sy[e] = 0.f; sz[e] = 0.f; sk[e] = 0;
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int k = tid + i * T;
+        if (k < n) {
+            const uint32_t s = (i & 1) ? (packed[i >> 1] >> 16) : (packed[i >> 1] & 0xffffu);
+            const int e = slot_index<P>((int)s);
+            sx[e] = __ldg(xyz + 3 * k);
+            sy[e] = __ldg(xyz + 3 * k + 1);
+            sz[e] = __ldg(xyz + 3 * k + 2);
+            sk[e] = (uint16_t)k;
+        }
+    }
+    __syncthreads();
+
+    // ================= per-lane state =================
+    const int base = warp * (32 * P) + lane * 4;    // element index of this lane's slot 0
+    const int first = (warp * 32 + lane) * P;       // sorted position of slot 0
+    float md[P];
+    {
+        // Order each lane's P points by ascending reference rank (any order inside a lane is as good as another
+        // for the pruning), so that "lowest slot among equal maxima" IS the reference's tie rule inside a lane.
+        // Slots past the cloud's end take the largest ranks and stay last.
+        uint32_t rk[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            rk[p] = (first + p < n) ? ref_rank(sk[base + (p >> 2) * 128 + (p & 3)], L) : (0xffffffe0u + (uint32_t)p);
+        int dst[P];  // element index each slot's point moves to
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int before = 0;
+#pragma unroll
+            for (int q = 0; q < P; ++q) before += (rk[q] < rk[p]) ? 1 : 0;
+            dst[p] = base + (before >> 2) * 128 + (before & 3);
+        }
+        {
+            uint16_t v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) v[p] = sk[base + (p >> 2) * 128 + (p & 3)];
+#pragma unroll
+            for (int p = 0; p < P; ++p) sk[dst[p]] = v[p];
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            float* const plane = sx + pl * CAP;
+            float v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) v[p] = plane[base + (p >> 2) * 128 + (p & 3)];
+#pragma unroll
+            for (int p = 0; p < P; ++p) plane[dst[p]] = v[p];
+        }
+        // (only this thread touches these elements: no barrier needed before it reads them back)
+    }
+    {
+        float bx0 = __int_as_float(0x7f800000), by0 = bx0, bz0 = bx0, bx1 = -bx0, by1 = -bx0, bz1 = -bx0;
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int p = c * 4 + e;
+                float d0 = -2.f;
+                if (first + p < n) {
+                    bx0 = fminf(bx0, xs[e]); bx1 = fmaxf(bx1, xs[e]);
+                    by0 = fminf(by0, ys[e]); by1 = fmaxf(by1, ys[e]);
+                    bz0 = fminf(bz0, zs[e]); bz1 = fmaxf(bz1, zs[e]);
+                    d0 = a.temp ? a.temp[(size_t)cloud * n + sk[base + c * 128 + e]] : 1e10f;
+                }
+                md[p] = d0;
+            }
+        }
+        // one box per 16 lanes (what fits next to the planes): union over the half-warp
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(FULL, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(FULL, bx1, o));
+            by0 = fminf(by0, __shfl_xor_sync(FULL, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(FULL, by1, o));
+            bz0 = fminf(bz0, __shfl_xor_sync(FULL, bz0, o)); bz1 = fmaxf(bz1, __shfl_xor_sync(FULL, bz1, o));
+        }
+        if ((lane & 15) == 0) {
+            sbox4[tid >> 4] = make_float4(bx0, bx1, by0, by1);
+            sbox2[tid >> 4] = make_float2(bz0, bz1);
+        }
+    }
+    if (tid == 0) {
+        idxs[0] = 0;
+        first_xyz[0] = __ldg(xyz + 0);
+        first_xyz[1] = __ldg(xyz + 1);
+        first_xyz[2] = __ldg(xyz + 2);
+    }
+    __syncthreads();
+
+    // lane state: (lmax, u, lpos) = this lane's largest min-distance and where it is; warp state (wu, wpos)
+    float lmax = -2.f;
+    uint32_t u = 0u, wu = 0u, wpos = (uint32_t)base;
+    int lpos = base;
+
+    // One pick's worth of work for a warp whose box the pick may reach: lane-level test, the P updates, the
+    // lane / warp argmax.  Leaves (wu, wpos) = the warp's candidate; bit 31 of wpos = "another point of this
+    // warp with different coordinates shares wu" (chain bookkeeping).
+    auto warp_step = [&](float x1, float y1, float z1, const float4 b4, const float2 b2, bool force) {
+        // lower bound of the computed squared distance over the lane's box, with the point formula's own
+        // rounded operations
+        const float dx = fmaxf(fmaxf(__fsub_rn(b4.x, x1), __fsub_rn(x1, b4.y)), 0.f);
+        const float dy = fmaxf(fmaxf(__fsub_rn(b4.z, y1), __fsub_rn(y1, b4.w)), 0.f);
+        const float dz = fmaxf(fmaxf(__fsub_rn(b2.x, z1), __fsub_rn(z1, b2.y)), 0.f);
+        const float lb = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        const bool hit = !(lb >= lmax) || force;  // NaN bounds count as hits
+        if (!__any_sync(FULL, hit)) return;
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
+            md[c * 4 + 0] = fminf(sqdist3(x1, y1, z1, X.x, Y.x, Z.x), md[c * 4 + 0]);
+            md[c * 4 + 1] = fminf(sqdist3(x1, y1, z1, X.y, Y.y, Z.y), md[c * 4 + 1]);
+            md[c * 4 + 2] = fminf(sqdist3(x1, y1, z1, X.z, Y.z, Z.z), md[c * 4 + 2]);
+            md[c * 4 + 3] = fminf(sqdist3(x1, y1, z1, X.w, Y.w, Z.w), md[c * 4 + 3]);
+        }
+        float t[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) t[p] = md[p];
+#pragma unroll
+        for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+            for (int p = 0; p + w < P; p += 2 * w) t[p] = fmaxf(t[p], t[p + w]);
+        }
+        lmax = t[0];
+        u = (lmax > -1.f) ? f32_ordered(lmax) : 0u;  // the reference starts from best = -1
+        // where this lane's maximum sits: the lowest slot among equals (slots are in reference-rank order)
+        uint32_t eq = 0u;
+#pragma unroll
+        for (int p = 0; p < P; ++p) eq |= (md[p] == lmax) ? (1u << p) : 0u;
+        const int bp = __ffs(eq) - 1;
+        lpos = base + (bp >> 2) * 128 + (bp & 3);
+        const bool several = (eq & (eq - 1u)) != 0u;
+        // the warp's candidate: one redux, one ballot, one shuffle (bit 31: the lane holds several maxima)
+        wu = __reduce_max_sync(FULL, u);
+        const unsigned tie = __ballot_sync(FULL, u == wu);
+        wpos = __shfl_sync(FULL, (uint32_t)lpos | (several ? 0x80000000u : 0u), __ffs(tie) - 1);
+        const bool lane_tie = (wpos >> 31) != 0u;
+        wpos &= 0x7fffffffu;
+        if (wu != 0u && ((tie & (tie - 1u)) != 0u || (chain && lane_tie))) {
+            // shared maximum inside the warp: the reference rank decides between lanes, and (chain bookkeeping)
+            // bit 31 of the candidate says whether a point with DIFFERENT coordinates shares it
+            const uint32_t rk = (u == wu) ? ref_rank(sk[lpos], L) : 0xffffffffu;
+            const uint32_t wrk = __reduce_min_sync(FULL, rk);
+            const int wl = __ffs(__ballot_sync(FULL, rk == wrk)) - 1;
+            wpos = (uint32_t)__shfl_sync(FULL, lpos, wl);
+            if (chain) {
+                bool other = false;
+                if (u == wu) {
+                    const float fx = sx[wpos], fy = sy[wpos], fz = sz[wpos];
+                    uint32_t rest = eq;
+                    while (rest) {
+                        const int p = __ffs(rest) - 1;
+                        rest &= rest - 1u;
+                        const int e = base + (p >> 2) * 128 + (p & 3);
+                        other |= sx[e] != fx || sy[e] != fy || sz[e] != fz;
+                    }
+                }
+                if (__any_sync(FULL, other)) wpos |= 0x80000000u;
+            }
+        }
+    };
+
+    // ================= one barrier per pick =================
+    // Every warp posts its (cached or refreshed) candidate, then reduces the NW records itself.
+    float x1 = first_xyz[0], y1 = first_xyz[1], z1 = first_xyz[2];
+    float4 b4 = sbox4[tid >> 4];
+    float2 b2 = sbox2[tid >> 4];
+    for (int j = 1; j < m; ++j) {
+        uint2* const rec = recs + (j & 1) * 32;  // double-buffered: a fast warp may already post pick j+1
+        warp_step(x1, y1, z1, b4, b2, j == 1);
+        if (lane == 0) rec[warp] = make_uint2(wu, wpos);
+        __syncthreads();
+        uint2 r = make_uint2(0u, 0u);
+        if (lane < NW) r = rec[lane];
+        // the group's box lives in shared memory (registers are short during the update); fetched here, in the
+        // shadow of the reduction, for the next pick's test
+        b4 = sbox4[tid >> 4];
+        b2 = sbox2[tid >> 4];
+        // ---- the pick: largest key, smallest reference rank among equals
+        const uint32_t gu = __reduce_max_sync(FULL, r.x);
+        const unsigned gt = __ballot_sync(FULL, r.x == gu);
+        uint32_t cpos = __shfl_sync(FULL, r.y, __ffs(gt) - 1);
+        bool other = (cpos >> 31) != 0u;  // chain bookkeeping: a different point shares the maximum
+        if (gu == 0u) {  // no eligible candidate anywhere: the reference yields index 0
+            x1 = first_xyz[0];
+            y1 = first_xyz[1];
+            z1 = first_xyz[2];
+            if (tid == 0) {
+                idxs[j] = -1;
+                if (a.vals) a.vals[(size_t)cloud * m + j] = 0.f;
+            }
+            continue;
+        }
+        if ((gt & (gt - 1u)) != 0u) {  // several warps share the maximum
+            const uint32_t rk = (r.x == gu) ? ref_rank(sk[r.y & 0x7fffffffu], L) : 0xffffffffu;
+            const uint32_t grk = __reduce_min_sync(FULL, rk);
+            cpos = __shfl_sync(FULL, r.y, __ffs(__ballot_sync(FULL, rk == grk)) - 1);
+            if (chain) {
+                const int e = (int)(r.y & 0x7fffffffu), w = (int)(cpos & 0x7fffffffu);
+                other = __any_sync(FULL, r.x == gu && ((r.y >> 31) != 0u || sx[e] != sx[w] || sy[e] != sy[w] ||
+                                                      sz[e] != sz[w]));
+            }
+        }
+        const int gpos = (int)(cpos & 0x7fffffffu);
+        x1 = sx[gpos];
+        y1 = sy[gpos];
+        z1 = sz[gpos];
+        if (tid == ((j & (NW - 1)) << 5)) {  // bookkeeping rotates over the warps
+            // the slot for now (fire-and-forget store); translated to the original index after the loop
+            idxs[j] = gpos;
+            if (a.vals) a.vals[(size_t)cloud * m + j] = __uint_as_float(gu & 0x7fffffffu);
+            if (chain && other) atomicMin(a.tie_iter + cloud, j);
+        }
+    }
+
+    __syncthreads();  // every idxs[j] slot store of this CTA is visible to it
+    for (int j = 1 + tid; j < m; j += T) {
+        const int e = idxs[j];
+        idxs[j] = e >= 0 ? (int)sk[e] : 0;
+    }
+    if (a.temp) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if (first + p < n) a.temp[(size_t)cloud * n + sk[base + (p >> 2) * 128 + (p & 3)]] = md[p];
+        }
+    }
+}
+
+template <int T, int P>
+static int launch_bucket(const FpsArgs& a, int b, int cell_bits, cudaStream_t stream) {
+    auto kern = fps_bucket_kernel<T, P>;
+    const size_t dyn = bucket_main_bytes(T * P, T, cell_bits) + kMiscBytes;
+    if (dyn > 227 * 1024) return TSM_ERR_INVALID;
+    if (dyn > 40 * 1024) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    kern<<<b, T, dyn, stream>>>(a, cell_bits);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}
+
+}  // namespace tsm
+
+bool tsm_fps_bucket_supports(int n, bool weighted) { return !weighted && n >= 1 && n <= tsm::kBucketMaxN; }
+
+// Launch shape: T threads x P points per lane >= n.  Measured on B200 (profiles/r01_fps_bucket_sweep.txt): 8
+// points per lane up to 1024 threads, then more points per lane -- 1024 x 16 at N = 16384 (0.67 us per pick,
+// 512 x 32: 0.70).  Overridable with TSMDET_FPSB_T / TSMDET_FPSB_P.
+int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
+    const int n = a.n;
+    if (!tsm_fps_bucket_supports(n, a.weights != nullptr)) return TSM_ERR_INVALID;
+    int T = 0, P = 0;
+    if (const char* e = getenv("TSMDET_FPSB_T")) T = atoi(e);
+    if (const char* e = getenv("TSMDET_FPSB_P")) P = atoi(e);
+    if (P != 4 && P != 8 && P != 16 && P != 32) P = 0;
+    if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512 && T != 1024) T = 0;
+    if (T && P && (long)T * P < n) T = P = 0;
+    if (T && !P) {
+        for (int p = 4; p <= 32 && !P; p <<= 1)
+            if ((long)T * p >= n) P = p;
+        if (!P) T = 0;
+    }
+    if (!T) {
+        if (!P) P = 8;
+        T = 32;
+        while (T < 1024 && (long)T * P < n) T <<= 1;
+        while ((long)T * P < n && P < 32) P <<= 1;
+    }
+    if ((long)T * P > tsm::kBucketMaxN || P > 32) return TSM_ERR_INVALID;
+    int lg = 0;
+    while ((1 << lg) < n) ++lg;
+    int cell_bits = lg + 1;
+    if (cell_bits < 10) cell_bits = 10;
+    if (cell_bits > 15) cell_bits = 15;
+#define FPSB_CASE(TT, PP) \
+    if (T == TT && P == PP) return tsm::launch_bucket<TT, PP>(a, b, cell_bits, stream);
+    FPSB_CASE(32, 4) FPSB_CASE(64, 4) FPSB_CASE(128, 4) FPSB_CASE(256, 4) FPSB_CASE(512, 4) FPSB_CASE(1024, 4)
+    FPSB_CASE(32, 8) FPSB_CASE(64, 8) FPSB_CASE(128, 8) FPSB_CASE(256, 8) FPSB_CASE(512, 8) FPSB_CASE(1024, 8)
+    FPSB_CASE(32, 16) FPSB_CASE(64, 16) FPSB_CASE(128, 16) FPSB_CASE(256, 16) FPSB_CASE(512, 16) FPSB_CASE(1024, 16)
+    FPSB_CASE(32, 32) FPSB_CASE(64, 32) FPSB_CASE(128, 32) FPSB_CASE(256, 32) FPSB_CASE(512, 32)
+#undef FPSB_CASE
+    return TSM_ERR_INVALID;
+}

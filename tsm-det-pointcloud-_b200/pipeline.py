@@ -247,6 +247,11 @@ class PipelinedRunner:
 
     def prepare(self, xyz, feats, boxes, scores):
         """Capture every lane's graph; returns each lane's device-resident input buffers."""
+        # `depth` batches sample concurrently: once their clouds outnumber the 8-CTA clusters the GPU can host,
+        # the one-SM-per-cloud sampler (fps_bucket.cu) is the one that keeps every batch running (identical
+        # results; the choice is baked into the captured graphs).  TSMDET_FPS_ALGO still overrides.
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        _lib.call("tsmdet_fps_configure", 2 if self.depth * xyz.shape[0] * 8 > sms else 0)
         ins = []
         for eng, lane in zip(self.engines, self.lanes):
             lane.wait_stream(torch.cuda.current_stream(self.dev))
