@@ -16,7 +16,13 @@
 // only points that survive it pay for the full reference distance (same FMA shape as the reference, so
 // the hit set is bit-identical).  For r = 0.2 m in a 70 m scene 99.4 % of the tests end after 4
 // instructions.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+
+int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout, int nsample, const float* new_xyz,
+                        const float* xyz, int* idx_cnt, int* idx, cudaStream_t stream, const int** grid_hdr);
 
 namespace tsm {
 
@@ -27,7 +33,8 @@ template <bool DILATED>
 __global__ void __launch_bounds__(BQ_THREADS)
     ball_query_kernel(int n, int m, float rin2, float rout2, float rlim, int nsample,
                       const float* __restrict__ new_xyz, const float* __restrict__ xyz, int* __restrict__ idx_cnt,
-                      int* __restrict__ idx, const int* __restrict__ perm, int* status) {
+                      int* __restrict__ idx, const int* __restrict__ perm, int* status,
+                      const int* __restrict__ grid_hdr) {
     __shared__ __align__(128) float raw[2][BQ_TILE * 3];
     __shared__ __align__(16) float sx[BQ_TILE];
     __shared__ float2 syz[BQ_TILE];
@@ -35,6 +42,7 @@ __global__ void __launch_bounds__(BQ_THREADS)
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
+    if (grid_hdr && grid_hdr[b * 16 + 9]) return;  // answered by the grid query (ball_query_grid.cu)
     xyz += (size_t)b * n * 3;
     // Centres are handed out in x-sorted order (perm, built by sort_centres_kernel): the 32 centres of a
     // warp then span a narrow x interval, so the per-lane reject below fails for (almost) all lanes at once
@@ -155,9 +163,10 @@ __global__ void __launch_bounds__(BQ_THREADS)
 
 // perm[b, :] = centre indices of cloud b sorted by x (bitonic sort in shared memory, m <= 8192).
 __global__ void __launch_bounds__(1024) sort_centres_kernel(int m, int mp2, const float* __restrict__ new_xyz,
-                                                            int* __restrict__ perm) {
+                                                            int* __restrict__ perm, const int* __restrict__ grid_hdr) {
     extern __shared__ unsigned long long keys[];  // (ordered x bits << 32) | index; padding sorts last
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (grid_hdr && grid_hdr[b * 16 + 9]) return;  // answered by the grid query
     for (int i = tid; i < mp2; i += 1024) {
         unsigned long long k = ~0ull;
         if (i < m) k = ((unsigned long long)f32_ordered(new_xyz[((size_t)b * m + i) * 3]) << 32) | (unsigned)i;
@@ -192,12 +201,14 @@ constexpr int BQW_TILE = 1024;     // points per shared-memory tile (12 KB)
 template <bool DILATED>
 __global__ void __launch_bounds__(BQW_THREADS)
     ball_query_warp_kernel(int n, int m, float rin2, float rout2, int nsample, const float* __restrict__ new_xyz,
-                      const float* __restrict__ xyz, int* __restrict__ idx_cnt, int* __restrict__ idx, int* status) {
+                      const float* __restrict__ xyz, int* __restrict__ idx_cnt, int* __restrict__ idx, int* status,
+                      const int* __restrict__ grid_hdr) {
     __shared__ __align__(128) float tile[2][BQW_TILE * 3];
     __shared__ __align__(8) uint64_t full[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
+    if (grid_hdr && grid_hdr[b * 16 + 9]) return;  // answered by the grid query (ball_query_grid.cu)
     xyz += (size_t)b * n * 3;
     const int c0 = (blockIdx.x * BQW_WARPS + warp) * BQW_CW;  // first centre of this warp
 
@@ -323,6 +334,18 @@ static int run_ball_query(bool dilated, int b, int n, int m, float rin, float ro
     float rlim = fabsf(rout) * 1.000002f + 1e-30f;
     if (!(rlim < 3.0e38f)) rlim = 3.4e38f;
     int* status = tsm_status_word(stream);
+    // Clouds of a useful size are answered through a uniform grid (ball_query_grid.cu): ~100x fewer distance
+    // tests than the brute-force kernels below, which then only serve the clouds whose grid was unusable
+    // (flagged on the device; they exit at once for the others).  TSMDET_BQ_ALGO=brute disables the grid.
+    const int* ghdr = nullptr;
+    {
+        const char* algo = getenv("TSMDET_BQ_ALGO");
+        if (n >= 512 && !(algo && !strcmp(algo, "brute"))) {
+            const int rc = tsm_ball_query_grid(dilated, b, n, m, rin, rout, nsample, new_xyz, xyz, idx_cnt, idx, stream,
+                                               &ghdr);
+            if (rc != TSM_OK) return rc;
+        }
+    }
     if ((long)b * m >= 32768) {  // enough centres to fill the GPU with one thread each
         int* perm = nullptr;
         if (m <= 8192 && m >= 64) {
@@ -335,24 +358,24 @@ static int run_ball_query(bool dilated, int b, int n, int m, float rin, float ro
             const size_t dyn = sizeof(unsigned long long) * (size_t)mp2;
             if (dyn > 48 * 1024)
                 TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::sort_centres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            tsm::sort_centres_kernel<<<b, 1024, dyn, stream>>>(m, mp2, new_xyz, perm);
+            tsm::sort_centres_kernel<<<b, 1024, dyn, stream>>>(m, mp2, new_xyz, perm, ghdr);
             TSM_LAUNCH_CHECK();
         }
         dim3 grid((unsigned)tsm::divup(m, tsm::BQ_THREADS), (unsigned)b);
         if (dilated)
             tsm::ball_query_kernel<true><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample, new_xyz,
-                                                                                xyz, idx_cnt, idx, perm, status);
+                                                                                xyz, idx_cnt, idx, perm, status, ghdr);
         else
             tsm::ball_query_kernel<false><<<grid, tsm::BQ_THREADS, 0, stream>>>(n, m, rin2, rout2, rlim, nsample,
-                                                                                 new_xyz, xyz, idx_cnt, idx, perm, status);
+                                                                                 new_xyz, xyz, idx_cnt, idx, perm, status, ghdr);
     } else {
         dim3 grid((unsigned)tsm::divup(m, tsm::BQW_WARPS * tsm::BQW_CW), (unsigned)b);
         if (dilated)
             tsm::ball_query_warp_kernel<true><<<grid, tsm::BQW_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz,
-                                                                                     xyz, idx_cnt, idx, status);
+                                                                                     xyz, idx_cnt, idx, status, ghdr);
         else
             tsm::ball_query_warp_kernel<false><<<grid, tsm::BQW_THREADS, 0, stream>>>(n, m, rin2, rout2, nsample,
-                                                                                      new_xyz, xyz, idx_cnt, idx, status);
+                                                                                      new_xyz, xyz, idx_cnt, idx, status, ghdr);
     }
     TSM_LAUNCH_CHECK();
     return TSM_OK;
