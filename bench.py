@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "2")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "6")),
                     help="steps kept in flight (each on its own stream / CUDA graph / buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="per-kernel CUDA-event breakdown to stderr")
@@ -332,13 +332,23 @@ def kernel_breakdown(engine, d, dev, args):
     b = xyz.shape[0]
 
     def t(fn, reps=5):
+        """Device time of one stage: captured into a CUDA graph (as the timed step runs it -- no per-launch host
+        cost between its kernels), replayed `reps` times between two events on the launching stream."""
         fn()
         torch.cuda.synchronize(dev)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(reps):
-            fn()
-        e.record()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()  # warm on the capture stream: grows that stream's scratch buffers
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                fn()
+            graph.replay()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(side)
+            for _ in range(reps):
+                graph.replay()
+            e.record(side)
         torch.cuda.synchronize(dev)
         return s.elapsed_time(e) / reps
 

@@ -30,9 +30,14 @@ BQ = [
 ]
 
 
+@pytest.mark.parametrize("algo", ["grid", "brute"])
 @pytest.mark.parametrize("case", BQ, ids=[f"bq{i}" for i in range(len(BQ))])
-def test_ball_query(orc, case):
+def test_ball_query(orc, case, algo, monkeypatch):
+    """Both query paths: the uniform-grid kernels (ball_query_grid.cu; clouds of >= 512 points whose grid is
+    usable) and the brute-force kernels (ball_query.cu), against the oracle."""
     from tsmdet_b200 import pointnet2_utils as pu
+
+    monkeypatch.setenv("TSMDET_BQ_ALGO", algo)
 
     b, n, m, rin, r, ns, gen = case
     xyz = gen(b, n, 7)
@@ -49,6 +54,55 @@ def test_ball_query(orc, case):
     assert np.array_equal(cnt.cpu().numpy(), wc)
     assert np.array_equal(idx.cpu().numpy(), wi)
     assert idx.dtype == torch.int32 and cnt.dtype == torch.int32
+
+
+def test_ball_query_grid_edge_cases(orc):
+    """Grid construction corner cases (flat / collinear / single-point clouds, centres far outside the cloud or
+    between samples, radius larger than the cloud, nsample above 32 -> merge kernel) all match the oracle."""
+    from tsmdet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(5)
+    flat = synth.cloud_uniform(2, 4000, 61)
+    flat[:, :, 2] = 1.5
+    line = synth.cloud_uniform(2, 3000, 62)
+    line[:, :, 1:] = 0.25
+    same = np.ones((2, 2000, 3), np.float32)
+    dense = (rng.standard_normal((2, 6000, 3)) * 0.05).astype(np.float32)  # everything in a few cells -> brute force
+    obj = synth.cloud_ground_objects(2, 8192, 63)
+    for name, xyz, r, ns in [("flat", flat, 0.8, 16), ("line", line, 0.5, 16), ("same", same, 0.3, 8), ("dense", dense, 0.4, 32),
+                             ("obj64", obj, 1.0, 64), ("obj48", obj, 0.6, 48), ("huge_r", obj, 500.0, 16), ("tiny_r", obj, 1e-4, 16)]:
+        new_xyz = np.ascontiguousarray(xyz[:, ::9, :]).copy()
+        new_xyz[:, 1] += 1000.0
+        new_xyz[:, 2] += np.float32(0.37 * r)
+        new_xyz[:, 3, 2] -= np.float32(2.5 * r)
+        cnt, idx = pu.ball_query(r, ns, T(xyz), T(new_xyz))
+        wc, wi = orc.ball_query(r, ns, xyz, new_xyz)
+        assert np.array_equal(cnt.cpu().numpy(), wc), name
+        assert np.array_equal(idx.cpu().numpy(), wi), name
+        cnt, idx = pu.ball_query_dilated(0.5 * r, r, ns, T(xyz), T(new_xyz))
+        wc, wi = orc.ball_query_dilated(0.5 * r, r, ns, xyz, new_xyz)
+        assert np.array_equal(cnt.cpu().numpy(), wc), name
+        assert np.array_equal(idx.cpu().numpy(), wi), name
+
+
+def test_ball_query_waymo_scale(orc):
+    """BASELINE config 4 shape (65536 points, 16384 centres, r 0.8, ns 32): grid path vs the oracle on one
+    cloud, vs the brute-force kernels on all."""
+    import os
+
+    from tsmdet_b200 import pointnet2_utils as pu
+
+    xyz = synth.cloud_uniform(2, 65536, 70, synth.WAYMO_RANGE)
+    new_xyz = np.ascontiguousarray(xyz[:, ::4, :])
+    cnt, idx = pu.ball_query(0.8, 32, T(xyz), T(new_xyz))
+    wc, wi = orc.ball_query(0.8, 32, xyz[:1], new_xyz[:1])
+    assert np.array_equal(cnt[:1].cpu().numpy(), wc) and np.array_equal(idx[:1].cpu().numpy(), wi)
+    os.environ["TSMDET_BQ_ALGO"] = "brute"
+    try:
+        c2, i2 = pu.ball_query(0.8, 32, T(xyz), T(new_xyz))
+    finally:
+        os.environ.pop("TSMDET_BQ_ALGO")
+    assert torch.equal(cnt, c2) and torch.equal(idx, i2)
 
 
 def test_ball_query_vs_reference_cuda(ref_pointnet2):

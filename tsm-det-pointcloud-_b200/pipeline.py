@@ -251,7 +251,10 @@ class PipelinedRunner:
         # the one-SM-per-cloud sampler (fps_bucket.cu) is the one that keeps every batch running (identical
         # results; the choice is baked into the captured graphs).  TSMDET_FPS_ALGO still overrides.
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
-        _lib.call("tsmdet_fps_configure", 2 if self.depth * xyz.shape[0] * 8 > sms else 0)
+        crowded = self.depth * xyz.shape[0] * 8 > sms
+        _lib.call("tsmdet_fps_configure", 2 if crowded else 0)
+        for eng in self.engines:  # that sampler records the chaining facts for free: levels 2/3 become look-ups
+            eng.chain_fps = eng.chain_fps or crowded
         ins = []
         for eng, lane in zip(self.engines, self.lanes):
             lane.wait_stream(torch.cuda.current_stream(self.dev))
