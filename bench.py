@@ -209,7 +209,7 @@ def main():
         else:
             raise
     engine = runner.engines[0]
-    gather = world > 1
+    gather = world > 1 and os.environ.get("TSMDET_BENCH_NO_GATHER", "0") == "0"  # (experiments only)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -235,6 +235,9 @@ def main():
     dev_step = lambda: runner.submit_device(lane_inputs, gather=gather, pre=flush)  # noqa: E731
     host_step = lambda: runner.submit_host(h, gather=gather, pre=flush)  # noqa: E731
 
+    for _ in range(depth):  # prime every lane once (graph upload, first collective) whatever --warmup is
+        dev_step()
+    runner.sync()
     for _ in range(args.warmup):
         dev_step()
     runner.sync()
@@ -248,7 +251,7 @@ def main():
     wall = time.perf_counter() - t_wall
     launches = _lib.launch_count - l0
     clocks = sampler.stop()
-    for _ in range(args.warmup):
+    for _ in range(depth + args.warmup):
         host_step()
     runner.sync()
     barrier()

@@ -29,8 +29,12 @@ from .sharding import gather_detections
 
 class SABackboneNMS(torch.nn.Module):
     def __init__(self, precision: str = "bf16", nms_pre: float = 0.01, nms_post: float = 0.1, k_post: int = 512,
-                 seed: int = 0, use_graph: bool = True, chain_fps: bool = False):
+                 seed: int = 0, use_graph: bool = True, chain_fps: bool = False, gather_group=None):
         super().__init__()
+        # torch.distributed group this engine's detection gather runs on, INSIDE the step (and so inside its
+        # CUDA graph: no per-step host-side collective launch).  Engines that run concurrently need a group
+        # each -- collectives of one communicator must execute in one order on every rank.
+        self.gather_group = gather_group
         torch.manual_seed(seed)
         self.backbone = kitti_sa_stack(fused=True, precision=precision)
         g = torch.Generator().manual_seed(seed + 1)
@@ -139,8 +143,15 @@ class SABackboneNMS(torch.nn.Module):
             rec = rec * live.unsqueeze(-1)
         main.wait_stream(s_sa)
         main.wait_stream(s_nms)
+        res = {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num, "det": rec}
+        if self.gather_group is not None:
+            # the one collective of the path: every rank receives every rank's records (equal shards, so the
+            # sizes are known without a size exchange or a host sync)
+            world = torch.distributed.get_world_size(self.gather_group)
+            res["all_det"], res["all_num"] = gather_detections(rec, det_num, frames_total=rec.shape[0] * world,
+                                                               group=self.gather_group)
         mark("end", main)
-        return {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num, "det": rec}
+        return res
 
     def trace_step(self, xyz, feats, boxes, scores):
         """Runs the DAG eagerly with timing events; returns [(name, ms since start)] (diagnostics)."""
@@ -196,9 +207,7 @@ class SABackboneNMS(torch.nn.Module):
             boxes, scores = ent["in"][2], ent["in"][3]
         else:
             res = self._run(xyz, feats, boxes, scores)
-        if gather:
-            # the one collective of the path: every rank receives every rank's records (equal shards, so the
-            # sizes are known without a size exchange or a host sync)
+        if gather and "all_det" not in res:  # engines without their own group: eager collective after the step
             world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
             res["all_det"], res["all_num"] = gather_detections(res["det"], res["det_num"],
                                                                frames_total=res["det"].shape[0] * world)
@@ -240,6 +249,9 @@ class PipelinedRunner:
     def __init__(self, depth: int = 2, device=None, **engine_kwargs):
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth = depth
+        # The lanes share the default communicator: their gathers are issued after each replay, in step order on
+        # every rank.  (Capturing a per-lane communicator's all_gather into the lane graphs deadlocked on 2 GPUs:
+        # concurrently replaying graphs let the ranks start the lanes' collectives in different orders.)
         self.engines = [SABackboneNMS(**engine_kwargs).to(self.dev) for _ in range(depth)]  # same seed: same weights
         self.lanes = [torch.cuda.Stream(self.dev) for _ in range(depth)]
         self._i = 0

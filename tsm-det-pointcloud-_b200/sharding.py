@@ -54,9 +54,9 @@ def gather_detections(padded: torch.Tensor, counts: torch.Tensor, frames_total: 
         return padded, counts
     world = dist.get_world_size(group)
     k = padded.shape[1]
-    f_local = torch.tensor([padded.shape[0]], dtype=torch.int64, device=padded.device)
-    f_all = [torch.zeros_like(f_local) for _ in range(world)]
-    if frames_total is None:
+    if frames_total is None:  # unknown shard sizes: one small exchange (synchronises the host)
+        f_local = torch.tensor([padded.shape[0]], dtype=torch.int64, device=padded.device)
+        f_all = [torch.zeros_like(f_local) for _ in range(world)]
         dist.all_gather(f_all, f_local, group=group)
         sizes = [int(t.item()) for t in f_all]
     else:
@@ -67,8 +67,10 @@ def gather_detections(padded: torch.Tensor, counts: torch.Tensor, frames_total: 
     buf[: padded.numel()] = padded.reshape(-1)
     buf[fmax * k * 9: fmax * k * 9 + counts.numel()] = counts.to(torch.int32).view(torch.float32)
     out = torch.empty((world, buf.numel()), dtype=torch.float32, device=padded.device)
-    dist.all_gather_into_tensor(out, buf, group=group) if hasattr(dist, "all_gather_into_tensor") and padded.is_cuda \
-        else dist.all_gather(list(out.unbind(0)), buf, group=group)
+    if hasattr(dist, "all_gather_into_tensor") and padded.is_cuda:
+        dist.all_gather_into_tensor(out, buf, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), buf, group=group)
     recs, cnts = [], []
     for r in range(world):
         recs.append(out[r, : sizes[r] * k * 9].view(sizes[r], k, 9))
