@@ -356,6 +356,7 @@ def kernel_breakdown(engine, d, dev, args):
         return s.elapsed_time(e) / reps
 
     kernels = []
+    kernels_ctx = {}
     cur_xyz, cur_f = xyz, feats
     with torch.no_grad():
         for li, layer in enumerate(engine.backbone.layers):
@@ -385,15 +386,35 @@ def kernel_breakdown(engine, d, dev, args):
                 {"name": f"sa_mlp_maxpool_L{li + 1}", "ms": ms_mlp, "alg_bytes": sa_bytes, "gbs": sa_bytes / ms_mlp / 1e6,
                  "tflops": flops / ms_mlp / 1e9},
             ]
+            kernels_ctx = {"xyz": cur_xyz, "f": cur_f, "idx": bidx}
             cur_xyz, cur_f = new_xyz, out
+        # the API-level (materialising) grouping op on the last layer's shape: the HBM-bound kernel of the path
+        lay = engine.backbone.layers[-1]
+        g3 = lay.groupers[0]
+        src_xyz, src_f = kernels_ctx["xyz"], kernels_ctx["f"]
+        c3, n3, m3, s3 = src_f.shape[1], src_xyz.shape[1], lay.npoint_list[0], g3.nsample
+        ms_grp = t(lambda: pointnet2_utils.grouping_operation(src_f, kernels_ctx["idx"]))
+        grp_bytes = b * (4 * c3 * n3 + 4 * m3 * s3 + 4 * c3 * m3 * s3)
+        kernels.append({"name": f"grouping_operation_L{len(engine.backbone.layers)} (API op, not on the fused path)",
+                        "ms": ms_grp, "alg_bytes": grp_bytes, "gbs": grp_bytes / ms_grp / 1e6,
+                        "hbm_frac": grp_bytes / ms_grp / 1e6 / float(peaks.get("hbm_gbs", 6650.0))})
         ms_nms = t(lambda: iou3d_nms_utils.nms_gpu_batch(boxes, scores, 0.01))
         p = boxes.shape[1]
         kernels.append({"name": "nms_batch(0.01)", "ms": ms_nms, "alg_bytes": b * 36 * p, "gbs": b * 36 * p / ms_nms / 1e6,
                         "pairs_per_s": b * p * (p - 1) / 2 / ms_nms * 1e3})
     top = max(kernels, key=lambda k: k["ms"])
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.jsonl")) as f:
+            for ln in f:
+                rec = json.loads(ln)
+                if top["name"].startswith("fps") and "fps_bucket_kernel" in rec["kernel"]:
+                    traffic = rec["dram_bytes"]
+    except OSError:
+        pass
     roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": top["gbs"] / peak, "traffic": None, "peak_source": peaks["src"],
+            "frac": top["gbs"] / peak, "traffic": traffic, "peak_source": peaks["src"],
             "note": "FPS is a serial-latency chain (one argmax per selected point); its HBM traffic is the "
                     "compulsory 12N+4M bytes per cloud, so the HBM fraction is tiny by construction -- see us_per_iter"}
     if args.profile_kernels:

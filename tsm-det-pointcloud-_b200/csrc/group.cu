@@ -10,6 +10,8 @@
 // slots, reads its 4 indices once (int4) and loops over channels, so every store is a
 // coalesced 16-byte vector and the index tensor is read exactly once instead of once per
 // channel; the gathers hit L2 (a (C,N) feature slab is <= a few MB).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tsm {
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(GP_THREADS)
     group_concat_kernel(int c, int n, int m, int s, int use_xyz, const float* __restrict__ xyz,
                         const float* __restrict__ new_xyz, const float* __restrict__ features,
                         const int* __restrict__ idx, float* __restrict__ new_features,
-                        float* __restrict__ grouped_xyz) {
+                        float* __restrict__ grouped_xyz, int ctot) {
     const int b = blockIdx.y;
     const int e = m * s;
     const int v = blockIdx.x * GP_THREADS + threadIdx.x;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(GP_THREADS)
     } else {
         id[0] = idx[(size_t)b * e + e0];
     }
-    const int ctot = (use_xyz ? 3 : 0) + (features ? c : 0);
+    // ctot: channels of new_features per cloud (the feature part may be filled by the staged gather instead)
     float* nf = new_features ? new_features + (size_t)b * ctot * e : nullptr;
     float* gx = grouped_xyz ? grouped_xyz + (size_t)b * 3 * e : nullptr;
     // the VEC slots of one thread share a centre when VEC divides s; handle the general case per slot
@@ -160,7 +162,84 @@ __global__ void __launch_bounds__(GP_THREADS)
     out[(size_t)b * m * 3 + t] = __ldg(xyz + ((size_t)b * n + idx[(size_t)b * m + p]) * 3 + a);
 }
 
+
+// Shared-memory staged variant: a CTA copies a slab of CC feature rows, points[b, c0 : c0+CC, :] (one contiguous
+// CC*N*4-byte run of the (B,C,N) tensor), into shared memory with ONE bulk copy of the TMA engine, then serves every
+// gather of its E-range from shared memory: HBM sees the slab once and the output once, the L2 no scattered
+// 4-byte requests at all.  grid = (E chunks, channel chunks, B); out has `out_ctot` channels per cloud and this
+// call fills channels [out_c0, out_c0 + C).
+__global__ void __launch_bounds__(GP_THREADS)
+    group_points_staged_kernel(int c, int n, int e, int cc, int e_per_cta, const float* __restrict__ points,
+                               const int* __restrict__ idx, float* __restrict__ out, int out_ctot, int out_c0,
+                               int* status) {
+    extern __shared__ __align__(128) float slab[];  // [cc][n]
+    __shared__ __align__(8) uint64_t full;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * cc;
+    const int nc = min(cc, c - c0);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(smem_u32(&full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)nc * (uint32_t)n * 4u;
+        mbar_arrive_expect_tx(smem_u32(&full), bytes);
+        bulk_g2s(smem_u32(slab), points + ((size_t)b * c + c0) * n, bytes, smem_u32(&full));
+    }
+    __syncthreads();
+    {
+        const uint32_t bar = smem_u32(&full);
+        if (!mbar_try_wait_cta(bar, 0)) {
+            const long long t0 = clock64();
+            while (!mbar_try_wait_cta(bar, 0))
+                if (clock64() - t0 > 4000000000LL) watchdog_trip(status, TSM_ERR_WATCHDOG);
+        }
+    }
+    const int e_beg = blockIdx.x * e_per_cta;
+    const int e_end = min(e, e_beg + e_per_cta);
+    const int* __restrict__ ib = idx + (size_t)b * e;
+    float* __restrict__ ob = out + ((size_t)b * out_ctot + out_c0 + c0) * e;
+    for (int e0 = e_beg + tid * 4; e0 < e_end; e0 += GP_THREADS * 4) {
+        const int4 t = *reinterpret_cast<const int4*>(ib + e0);
+#pragma unroll 4
+        for (int ci = 0; ci < nc; ++ci) {
+            const float* row = slab + (size_t)ci * n;
+            __stcs(reinterpret_cast<float4*>(ob + (size_t)ci * e + e0), make_float4(row[t.x], row[t.y], row[t.z], row[t.w]));
+        }
+    }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Launches the staged kernel when the shapes allow it (returns false otherwise, nothing launched).
+static bool launch_group_staged(int b, int c, int n, long e, const float* points, const int* idx, float* out,
+                                int out_ctot, int out_c0, cudaStream_t s, int* rc) {
+    *rc = TSM_OK;
+    if ((n & 3) || (e & 3) || !aligned16(points) || !aligned16(idx) || !aligned16(out) || e < 4096 || b > 65535) return false;
+    if ((size_t)n * 4 > 96 * 1024) return false;  // a row must leave room for two CTAs per SM
+    int cc = 1;
+    while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= 72 * 1024) cc *= 2;
+    const int cchunks = divup(c, cc);
+    if (cchunks > 65535) return false;
+    const size_t dyn = (size_t)cc * n * 4;
+    const int resident = (int)((227 * 1024) / (dyn + 1024));
+    long want = (long)tsm_num_sms() * (resident > 8 ? 8 : resident) * 2;  // about two waves
+    long echunks = divup((int)want, b * cchunks);
+    const long emax = e / 2048 > 0 ? e / 2048 : 1;
+    if (echunks > emax) echunks = emax;
+    if (echunks < 1) echunks = 1;
+    long e_per = ((e + echunks - 1) / echunks + 1023) / 1024 * 1024;  // whole passes of the CTA
+    echunks = (e + e_per - 1) / e_per;
+    if (dyn > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(group_points_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (err != cudaSuccess) { *rc = (int)err; return true; }
+    }
+    dim3 grid((unsigned)echunks, (unsigned)cchunks, (unsigned)b);
+    group_points_staged_kernel<<<grid, GP_THREADS, dyn, s>>>(c, n, (int)e, cc, (int)e_per, points, idx, out, out_ctot,
+                                                             out_c0, tsm_status_word(s));
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) *rc = (int)err;
+    return true;
+}
 
 }  // namespace tsm
 
@@ -173,6 +252,8 @@ int tsmdet_group_points(int b, int c, int n, int npoints, int nsample, const flo
     if (b > 65535 || e > 0x7fffffffL) return TSM_ERR_INVALID;
     const bool vec = (e % 4 == 0) && tsm::aligned16(idx) && tsm::aligned16(out);
     cudaStream_t s = (cudaStream_t)stream;
+    int rc = TSM_OK;
+    if (!getenv("TSMDET_GROUP_DIRECT") && tsm::launch_group_staged(b, c, n, e, points, idx, out, c, 0, s, &rc)) return rc;
     if (vec) {
         dim3 grid((unsigned)tsm::divup((int)(e / 4), tsm::GP_THREADS), (unsigned)b);
         tsm::group_points_kernel<4><<<grid, tsm::GP_THREADS, 0, s>>>(c, n, (int)e, points, idx, out);
@@ -204,14 +285,25 @@ int tsmdet_group_concat(int b, int c, int n, int m, int nsample, int use_xyz, co
     const bool vec = (e % 4 == 0) && tsm::aligned16(idx) && (!new_features || tsm::aligned16(new_features)) &&
                      (!grouped_xyz || tsm::aligned16(grouped_xyz));
     cudaStream_t s = (cudaStream_t)stream;
+    const int ctot = (use_xyz ? 3 : 0) + (features ? c : 0);
+    if (features && new_features && c >= 8 && !getenv("TSMDET_GROUP_DIRECT")) {
+        // many feature channels: the staged gather fills channels [3*use_xyz, ...) and the fused kernel below only
+        // writes the coordinate offsets
+        int rc = TSM_OK;
+        if (tsm::launch_group_staged(b, c, n, e, features, idx, new_features, ctot, use_xyz ? 3 : 0, s, &rc)) {
+            if (rc != TSM_OK) return rc;
+            features = nullptr;
+            if (!use_xyz && !grouped_xyz) return TSM_OK;
+        }
+    }
     if (vec) {
         dim3 grid((unsigned)tsm::divup((int)(e / 4), tsm::GP_THREADS), (unsigned)b);
         tsm::group_concat_kernel<4><<<grid, tsm::GP_THREADS, 0, s>>>(c, n, m, nsample, use_xyz, xyz, new_xyz, features,
-                                                                     idx, new_features, grouped_xyz);
+                                                                     idx, new_features, grouped_xyz, ctot);
     } else {
         dim3 grid((unsigned)tsm::divup((int)e, tsm::GP_THREADS), (unsigned)b);
         tsm::group_concat_kernel<1><<<grid, tsm::GP_THREADS, 0, s>>>(c, n, m, nsample, use_xyz, xyz, new_xyz, features,
-                                                                     idx, new_features, grouped_xyz);
+                                                                     idx, new_features, grouped_xyz, ctot);
     }
     TSM_LAUNCH_CHECK();
     return TSM_OK;
