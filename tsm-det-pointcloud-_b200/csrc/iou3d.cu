@@ -24,6 +24,8 @@
 #include <mutex>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tsm {
@@ -401,38 +403,48 @@ __global__ void __launch_bounds__(256)
         qn -= count;
     };
 
+    // Every unordered pair of boxes in the same or adjacent cells is generated exactly once: the warp walks the
+    // boxes in CELL order (position k of the sorted list) and pairs box so[k] with (1) the rest of its own cell
+    // and the cell to its right -- one contiguous run of the sorted list starting at k + 1 -- and (2) the three
+    // cells below it, another contiguous run.  Half the candidates of a full 3x3 sweep, and none is discarded
+    // for being on the wrong side of the diagonal.
     const int wstride = gridDim.x * 8;
-    for (int i = blockIdx.x * 8 + warp; i < n; i += wstride) {
+    for (int k = blockIdx.x * 8 + warp; k < n; k += wstride) {
+        const int i = so[k];
         const BoxPrep a = P[i];
         int ix, iy;
         grid_cell(g, a.cx, a.cy, ix, iy);
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = iy + dy;
-            if (yy < 0 || yy >= g.gy) continue;
-            // the (up to) three cells of a grid row are contiguous in the sorted order
-            const int xa = max(ix - 1, 0), xb = min(ix + 1, g.gx - 1);
-            const int s0 = cs[yy * g.gx + xa], s1 = cs[yy * g.gx + xb + 1];
+#pragma unroll 1
+        for (int run = 0; run < 2; ++run) {
+            int s0, s1;
+            if (run == 0) {
+                s0 = k + 1;
+                s1 = cs[iy * g.gx + min(ix + 1, g.gx - 1) + 1];
+            } else {
+                if (iy + 1 >= g.gy) break;
+                s0 = cs[(iy + 1) * g.gx + max(ix - 1, 0)];
+                s1 = cs[(iy + 1) * g.gx + min(ix + 1, g.gx - 1) + 1];
+            }
             for (int k0 = s0; k0 < s1; k0 += 32) {
-                const int k = k0 + lane;
+                const int kk = k0 + lane;
                 bool heavy = false;
                 int j = 0;
-                if (k < s1) {
-                    j = so[k];
-                    if (j > i) {
-                        const BoxPrep* pb = P + j;
-                        if (all_heavy) {
-                            heavy = true;
-                        } else {
-                            BoxPrep b;  // only the fields the rejects read
-                            b.cx = pb->cx; b.cy = pb->cy; b.rad = pb->rad;
-                            b.ci = pb->ci; b.si = pb->si; b.mx = pb->mx; b.my = pb->my;
-                            heavy = !surely_disjoint(a, b) && !surely_separated(a, b);
-                        }
+                if (kk < s1) {
+                    j = so[kk];
+                    const BoxPrep* pb = P + j;
+                    if (all_heavy) {
+                        heavy = true;
+                    } else {
+                        BoxPrep b;  // only the fields the rejects read
+                        b.cx = pb->cx; b.cy = pb->cy; b.rad = pb->rad;
+                        b.ci = pb->ci; b.si = pb->si; b.mx = pb->mx; b.my = pb->my;
+                        heavy = !surely_disjoint(a, b) && !surely_separated(a, b);
                     }
                 }
                 const unsigned bal = __ballot_sync(FULL, heavy);
                 if (bal) {
-                    if (heavy) q[qn + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)i << 16) | (unsigned)j;
+                    if (heavy)
+                        q[qn + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)min(i, j) << 16) | (unsigned)max(i, j);
                     qn += __popc(bal);
                     __syncwarp();
                     if (qn >= 32) eval32(32);
@@ -634,7 +646,9 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     if (nmax > 65535) return TSM_ERR_INVALID;  // queue entries pack (row, col) into 16 + 16 bits
     TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     const long tiles = (long)cbmax * (cbmax + 1) / 2;
-    int per_frame = (2 * tsm_num_sms() + frames - 1) / frames;  // ~2 CTAs per SM in total
+    int ctas_per_sm = 2;
+    if (const char* e = getenv("TSMDET_NMS_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
+    int per_frame = (ctas_per_sm * tsm_num_sms() + frames - 1) / frames;  // CTAs per SM in total
     if (per_frame < 1) per_frame = 1;
     // rotated NMS with a sane threshold: spatial-grid candidates; the all-pairs tile kernel then only serves
     // frames the grid builder flagged (non-finite boxes).  A negative/NaN threshold lets IoU == 0 suppress, so
