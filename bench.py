@@ -50,18 +50,49 @@ def make_inputs(frames: int, seed: int):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML thread (about 1 kHz;
+    only the samples whose timestamps fall inside [start(), stop()] are kept), nvidia-smi -lms as the fallback."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, device):
+        self.device, self.rows, self.proc, self.nvml, self.handle = device, [], None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(device)
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(device.index or 0)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv, h = self.nvml, self.handle
+        while not self._stop.is_set():
+            try:
+                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        self.t0 = time.perf_counter()
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.device.index or 0)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -72,9 +103,24 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        t1 = time.perf_counter()
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            nv = self.nvml
+            inside = [r for r in self.rows if self.t0 <= r[0] <= t1]
+            sm = sorted(r[1] for r in inside)
+            bits = 0
+            for r in inside:
+                bits |= r[2]
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(n for n, b in self.REASONS if bits & b), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         for r in self.rows:
@@ -83,12 +129,12 @@ class ClockSampler:
                 mx = float(r[1])
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -242,7 +288,7 @@ def main():
         dev_step()
     runner.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev)
     sampler.start()
     l0 = _lib.launch_count
     t_wall = time.perf_counter()

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_fps_gpu.py -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/test_fps_gpu.log 2>&1; echo "exit $?"; tail -4 gpurun_out/test_fps_gpu.log
+echo skip-tests
 for dpt in ${DEPTHS:-1 2 3}; do
 timeout 600 python bench.py --steps 30 --warmup 6 --precision bf16 --no-cpu-baseline --depth $dpt > gpurun_out/bench_d$dpt.log 2> gpurun_out/bench_d$dpt.err; echo "bench $dpt $?"
 tail -3 gpurun_out/bench_d$dpt.err
