@@ -181,3 +181,32 @@ def test_iou_nms_golden():
         assert np.array_equal(k[:nk].numpy(), g[f"keep_{th}"])
         nk = ext.nms_normal_gpu(bs, k, th)
         assert np.array_equal(k[:nk].numpy(), g[f"keepn_{th}"])
+
+
+def test_multi_thresh_batch_matches_per_frame_driver():
+    """The batched, sync-free post-processing equals the reference-shaped per-frame `multi_thresh`
+    (model_nms_utils.py:52-87) frame by frame: same indices in the same (score) order."""
+    from tsmdet_b200 import model_nms_utils as mnu
+
+    dev = torch.device("cuda:0")
+    f, p = 5, 3000
+    boxes = np.stack([synth.boxes_clustered(p, 300 + i, centres=120) for i in range(f)])
+    rng = np.random.default_rng(11)
+    scores = np.stack([rng.permutation(p).astype(np.float32) / p for _ in range(f)])  # distinct scores
+    labels = rng.integers(1, 4, size=(f, p))
+    labels[3, :] = 2            # a frame with a single class
+    scores[4, :] = scores[4, :] * 0.05  # a frame where almost nothing passes the thresholds
+    cfg = mnu.NmsConfig(NMS_TYPE="nms_gpu", NMS_THRESH=0.1, NMS_PRE_MAXSIZE=512, NMS_POST_MAXSIZE=100, MULTI_CLASSES_NMS=False)
+    thr = [0.3, 0.25, 0.2]
+    tb, ts, tl = (torch.from_numpy(a).to(dev) for a in (boxes, scores, labels))
+    idx, num, sc = mnu.multi_thresh_batch(ts, tl, tb, cfg, thr)
+    assert idx.shape[0] == f and idx.shape[1] == 3 * 100
+    for i in range(f):
+        want_idx, want_sc = mnu.multi_thresh(ts[i], tl[i], tb[i], cfg, score_thresh=thr)
+        k = int(num[i])
+        want_idx = want_idx if isinstance(want_idx, torch.Tensor) else torch.zeros((0,), dtype=torch.int64, device=dev)
+        assert k == want_idx.numel(), (i, k, want_idx.numel())
+        assert torch.equal(idx[i, :k], want_idx), i
+        assert bool((idx[i, k:] == -1).all())
+        if k:
+            assert torch.equal(sc[i, :k], ts[i][want_idx])

@@ -95,6 +95,59 @@ def multi_thresh(box_scores, box_labels, box_preds, nms_config, score_thresh=Non
     return selected_end, src_box_scores[selected_end]
 
 
+@torch.no_grad()
+def multi_thresh_batch(box_scores, box_labels, box_preds, nms_config, score_thresh):
+    """`multi_thresh` for a whole batch of frames on the device, with no host synchronisation: what the
+    reference's per-frame / per-class Python loop (``detector3d_template.py:228-303`` calling ref :52-87, up to
+    num_class + 1 ``nms_gpu`` calls per frame, each ending in a blocking copy and ``nonzero()`` syncs) computes,
+    as ``num_class + 1`` batched NMS launches in total.
+
+    box_scores (F,P), box_labels (F,P) int (classes are 1-based, as in the reference), box_preds (F,P,>=7),
+    score_thresh: one threshold per class.  Returns ``(selected (F,K) int64, num (F,) int32, scores (F,K))``:
+    per frame the indices ``multi_thresh`` returns (score order), padded with -1 / -inf; K = num_class *
+    NMS_POST_MAXSIZE.  Rotated NMS only (``NMS_TYPE == 'nms_gpu'``); scores are assumed distinct where order
+    matters (torch.sort / topk leave the order of ties unspecified in the reference too)."""
+    if nms_config.NMS_TYPE not in ("nms_gpu", "nms_normal_gpu"):
+        raise ValueError(f"multi_thresh_batch: unsupported NMS_TYPE {nms_config.NMS_TYPE}")
+    normal = nms_config.NMS_TYPE == "nms_normal_gpu"
+    f, p = box_scores.shape
+    dev = box_scores.device
+    pre = min(int(nms_config.NMS_PRE_MAXSIZE), p)
+    post = int(nms_config.NMS_POST_MAXSIZE)
+    thresh = float(nms_config.NMS_THRESH)
+    boxes7 = box_preds[:, :, :7]
+    neg = torch.full_like(box_scores, float("-inf"))
+    parts_idx, parts_score = [], []
+    for i, cur_thresh in enumerate(score_thresh):
+        live = (box_labels == (i + 1)) & (box_scores >= cur_thresh)
+        vals, order = torch.topk(torch.where(live, box_scores, neg), k=pre, dim=1)  # descending; dead entries last
+        counts = (vals > float("-inf")).sum(dim=1).to(torch.int32)
+        cand = torch.gather(boxes7, 1, order.unsqueeze(-1).expand(-1, -1, 7))
+        sel, num = iou3d_nms_utils.nms_gpu_batch(cand, vals, thresh, counts=counts, normal=normal, presorted=True)
+        k = min(post, pre)
+        sel = sel[:, :k]
+        ok = sel >= 0
+        orig = torch.gather(order, 1, torch.where(ok, sel, torch.zeros_like(sel)))
+        parts_idx.append(torch.where(ok, orig, torch.full_like(orig, -1)))
+        parts_score.append(torch.where(ok, torch.gather(box_scores, 1, torch.where(ok, orig, torch.zeros_like(orig))),
+                                       torch.full((f, k), float("-inf"), device=dev, dtype=box_scores.dtype)))
+    if not parts_idx:
+        return (torch.full((f, 0), -1, dtype=torch.int64, device=dev), torch.zeros((f,), dtype=torch.int32, device=dev),
+                torch.full((f, 0), float("-inf"), device=dev, dtype=box_scores.dtype))
+    cat_idx = torch.cat(parts_idx, dim=1)        # (F, K)
+    cat_score = torch.cat(parts_score, dim=1)
+    ok = cat_idx >= 0
+    cat_boxes = torch.gather(boxes7, 1, torch.where(ok, cat_idx, torch.zeros_like(cat_idx)).unsqueeze(-1).expand(-1, -1, 7))
+    counts = ok.sum(dim=1).to(torch.int32)
+    # the cross-class pass: nms_gpu sorts by score itself (padding carries -inf and sorts last)
+    sel, num = iou3d_nms_utils.nms_gpu_batch(cat_boxes, cat_score, thresh, counts=counts, normal=normal)
+    ok2 = sel >= 0
+    safe = torch.where(ok2, sel, torch.zeros_like(sel))
+    out_idx = torch.where(ok2, torch.gather(cat_idx, 1, safe), torch.full_like(sel, -1))
+    out_score = torch.where(ok2, torch.gather(cat_score, 1, safe), torch.full_like(cat_score, float("-inf")))
+    return out_idx, num, out_score
+
+
 def multi_classes_nms(cls_scores, box_preds, nms_config, score_thresh=None):
     """ref :89-127 -- cls_scores (N,num_class), box_preds (N,7+C) -> (scores, labels, boxes)."""
     pred_scores, pred_labels, pred_boxes = [], [], []
