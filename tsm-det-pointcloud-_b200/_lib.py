@@ -104,7 +104,7 @@ def check(status: int, where: str) -> None:
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "tsmdet_nms_batch": 5, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 5, "tsmdet_nms_normal_gpu": 3,
+    "tsmdet_nms_batch": 6, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 6, "tsmdet_nms_normal_gpu": 3,
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
     "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3,
 }

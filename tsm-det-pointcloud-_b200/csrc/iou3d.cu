@@ -25,6 +25,7 @@
 #include <vector>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -540,6 +541,146 @@ __global__ void __launch_bounds__(256)
     if (!NORMAL) drain();
 }
 
+// Lazy rotated NMS: mask rows are only ever read for boxes the greedy sweep KEEPS, and only their bits for
+// boxes that are still alive.  So instead of building the whole mask and sweeping it afterwards, one CTA per
+// frame walks the score-ordered boxes in blocks of 64 and, per block, (1) computes the suppression rows of
+// the boxes not yet removed -- spatial-grid candidates, the two conservative rejects, exact IoU only against
+// boxes that are themselves still alive -- into shared memory, (2) resolves the block's diagonal serially
+// (iou3d_nms.cpp:116-131), (3) ORs the kept rows into the removal words of the later blocks.  With the
+// clustered proposals of a detector (each kept box removes ~20 others) that is ~12x fewer exact IoUs than the
+// full mask, and the mask never touches HBM.  Keep-lists are identical: a bit that is not computed is a bit the
+// reference's sweep never reads or whose target is already removed.
+// zero the mask of the frames the all-pairs path will serve (the others never touch theirs)
+__global__ void __launch_bounds__(256)
+    nms_clear_flagged_kernel(unsigned long long* __restrict__ mask, size_t words_per_frame, const NmsGrid* __restrict__ grids) {
+    const int f = blockIdx.y;
+    if (!grids[f].fallback) return;
+    unsigned long long* M = mask + (size_t)f * words_per_frame;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < words_per_frame; e += (size_t)gridDim.x * 256) M[e] = 0ull;
+}
+
+constexpr int NMSL_THREADS = 512;
+constexpr int NMSL_WARPS = NMSL_THREADS / 32;
+
+__global__ void __launch_bounds__(NMSL_THREADS)
+    nms_lazy_kernel(int nmax, const int* __restrict__ counts, float thresh, const BoxPrep* __restrict__ prep,
+                    const NmsGrid* __restrict__ grids, const int* __restrict__ cell_start,
+                    const int* __restrict__ sorted, long long* __restrict__ keep, int* __restrict__ num_keep) {
+    extern __shared__ unsigned long long lz[];  // remv[cbmax] | rows[64][cbmax]
+    __shared__ unsigned int wq[NMSL_WARPS][96];
+    __shared__ unsigned long long kept_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const NmsGrid g = grids[f];
+    if (g.fallback) return;  // the all-pairs path serves this frame
+    const int n = counts ? min(counts[f], nmax) : nmax;
+    const int cbmax = divup(nmax, 64);
+    const int cb = divup(n, 64);
+    const BoxPrep* P = prep + (size_t)f * nmax;
+    const int* cs = cell_start + (size_t)f * (NMS_GMAX * NMS_GMAX + 1);
+    const int* so = sorted + (size_t)f * nmax;
+    long long* K = keep + (size_t)f * nmax;
+    unsigned long long* remv = lz;
+    unsigned long long* rows = lz + cbmax;
+    unsigned int* q = wq[warp];
+    for (int j = tid; j < cb; j += NMSL_THREADS) remv[j] = 0ull;
+    int base = 0;
+    __syncthreads();
+    for (int b = 0; b < cb; ++b) {
+        const int nrows = min(64, n - b * 64);
+        unsigned long long alive = ~remv[b];
+        if (nrows < 64) alive &= (1ull << nrows) - 1ull;
+        const int nw = cb - b;  // words b .. cb-1 of a row matter
+        for (int e = tid; e < 64 * nw; e += NMSL_THREADS) {
+            const int r = e / nw;
+            if ((alive >> r) & 1ull) rows[(size_t)r * cbmax + b + (e - r * nw)] = 0ull;
+        }
+        __syncthreads();
+        // ---- (1) rows of the alive boxes of this block: warp w takes the w-th, (w+16)-th, ... alive row
+        {
+            int qn = 0;  // warp-uniform
+            auto eval32 = [&](int count) {
+                if (lane < count) {
+                    const unsigned int e = q[qn - count + lane];
+                    const int r = (int)(e >> 16), j = (int)(e & 0xffffu);
+                    const BoxPrep a = P[b * 64 + r], bb = P[j];
+                    if (iou_rotated(a, bb) > thresh) atomicOr(&rows[(size_t)r * cbmax + (j >> 6)], 1ull << (j & 63));
+                }
+                __syncwarp();
+                qn -= count;
+            };
+            unsigned long long rest = alive;
+            for (int skip = 0; rest; ++skip) {
+                const int r = __ffsll((long long)rest) - 1;
+                rest &= rest - 1ull;
+                if ((skip & (NMSL_WARPS - 1)) != warp) continue;
+                const int i = b * 64 + r;
+                const BoxPrep a = P[i];
+                int ix, iy;
+                grid_cell(g, a.cx, a.cy, ix, iy);
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = iy + dy;
+                    if (yy < 0 || yy >= g.gy) continue;
+                    const int xa = max(ix - 1, 0), xb = min(ix + 1, g.gx - 1);
+                    const int s0 = cs[yy * g.gx + xa], s1 = cs[yy * g.gx + xb + 1];
+                    for (int k0 = s0; k0 < s1; k0 += 32) {
+                        const int k = k0 + lane;
+                        bool heavy = false;
+                        int j = 0;
+                        if (k < s1) {
+                            j = so[k];
+                            // later in score order and not removed yet: the only bits the sweep can still use
+                            if (j > i && !((remv[j >> 6] >> (j & 63)) & 1ull)) {
+                                const BoxPrep* pb = P + j;
+                                BoxPrep c;  // only the fields the rejects read
+                                c.cx = pb->cx; c.cy = pb->cy; c.rad = pb->rad;
+                                c.ci = pb->ci; c.si = pb->si; c.mx = pb->mx; c.my = pb->my;
+                                heavy = !surely_disjoint(a, c) && !surely_separated(a, c);
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(FULL, heavy);
+                        if (bal) {
+                            if (heavy) q[qn + __popc(bal & ((1u << lane) - 1u))] = ((unsigned)r << 16) | (unsigned)j;
+                            qn += __popc(bal);
+                            __syncwarp();
+                            if (qn >= 32) eval32(32);
+                        }
+                    }
+                }
+            }
+            if (qn > 0) eval32(qn);
+        }
+        __syncthreads();
+        // ---- (2) the block's diagonal, serially
+        if (tid == 0) {
+            unsigned long long cur = ~alive, kept = 0ull;
+            for (int r = 0; r < nrows; ++r) {
+                if (!((cur >> r) & 1ull)) {
+                    kept |= 1ull << r;
+                    cur |= rows[(size_t)r * cbmax + b];
+                }
+            }
+            kept_s = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = kept_s;
+        if (tid < 64 && ((kept >> tid) & 1ull)) K[base + __popcll(kept & ((1ull << tid) - 1ull))] = (long long)(b * 64 + tid);
+        base += __popcll(kept);
+        // ---- (3) kept rows -> removal words of the later blocks (one thread per word: no atomics)
+        for (int j = b + 1 + tid; j < cb; j += NMSL_THREADS) {
+            unsigned long long acc = 0ull, kk = kept;
+            while (kk) {
+                const int r = __ffsll((long long)kk) - 1;
+                kk &= kk - 1ull;
+                acc |= rows[(size_t)r * cbmax + j];
+            }
+            remv[j] |= acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) num_keep[f] = base;
+}
+
 // Greedy sweep (iou3d_nms.cpp:116-131) on the device, one CTA (256 threads) per frame.
 //   keep (F, nmax) int64: kept indices (into the score-sorted boxes) in ascending order
 //   num_keep (F) int32
@@ -548,12 +689,13 @@ __global__ void __launch_bounds__(256)
 // removal words of the later blocks.
 __global__ void __launch_bounds__(256)
     nms_sweep_kernel(int nmax, const int* __restrict__ counts, const unsigned long long* __restrict__ mask,
-                     long long* __restrict__ keep, int* __restrict__ num_keep) {
+                     long long* __restrict__ keep, int* __restrict__ num_keep, const NmsGrid* __restrict__ gate) {
     extern __shared__ unsigned long long remv[];  // cbmax words
     __shared__ unsigned long long diagw[64];
     __shared__ unsigned long long kept_s;
     const int tid = threadIdx.x;
     const int f = blockIdx.x;
+    if (gate && !gate[f].fallback) return;  // nms_lazy_kernel answered this frame
     const int n = counts ? min(counts[f], nmax) : nmax;
     const int cbmax = divup(nmax, 64);
     const int cb = divup(n, 64);
@@ -644,7 +786,6 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     tsm::prep_boxes_kernel<<<tsm::divup(total, 128), 128, 0, s>>>(total, boxes, box_stride, prep);
     TSM_LAUNCH_CHECK();
     if (nmax > 65535) return TSM_ERR_INVALID;  // queue entries pack (row, col) into 16 + 16 bits
-    TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     const long tiles = (long)cbmax * (cbmax + 1) / 2;
     int ctas_per_sm = 2;
     if (const char* e = getenv("TSMDET_NMS_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
@@ -654,13 +795,28 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     // frames the grid builder flagged (non-finite boxes).  A negative/NaN threshold lets IoU == 0 suppress, so
     // every pair matters and only the tile kernel is exact.
     const bool use_grid = !normal && (thresh >= 0.f);
+    const size_t lazy_dyn = (size_t)(65) * cbmax * sizeof(unsigned long long);
+    const char* algo = getenv("TSMDET_NMS_ALGO");  // "mask": always build the full mask (tuning / tests)
+    const bool lazy = use_grid && lazy_dyn <= 160 * 1024 && !(algo && !strcmp(algo, "mask"));
+    if (!lazy) TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     if (use_grid) {
         tsm::nms_grid_build_kernel<<<frames, 1024, 0, s>>>(nmax, counts, prep, grids, cell_start, sorted);
         TSM_LAUNCH_CHECK();
-        dim3 pgrid((unsigned)std::min(per_frame, tsm::divup(nmax, 8)), (unsigned)frames);
-        tsm::nms_grid_pairs_kernel<<<pgrid, 256, 0, s>>>(nmax, counts, thresh, prep, grids, cell_start, sorted, mask);
+        if (lazy) {
+            tsm::nms_clear_flagged_kernel<<<dim3(64, (unsigned)frames), 256, 0, s>>>(mask, (size_t)nmax * cbmax, grids);
+            TSM_LAUNCH_CHECK();
+            if (lazy_dyn > 40 * 1024)
+                TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::nms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lazy_dyn));
+            tsm::nms_lazy_kernel<<<frames, tsm::NMSL_THREADS, lazy_dyn, s>>>(nmax, counts, thresh, prep, grids, cell_start,
+                                                                            sorted, keep, num_keep);
+        } else {
+            dim3 pgrid((unsigned)std::min(per_frame, tsm::divup(nmax, 8)), (unsigned)frames);
+            tsm::nms_grid_pairs_kernel<<<pgrid, 256, 0, s>>>(nmax, counts, thresh, prep, grids, cell_start, sorted, mask);
+        }
         TSM_LAUNCH_CHECK();
     }
+    // the all-pairs tile kernel + mask sweep: axis-aligned NMS, odd thresholds, and -- after the lazy kernel -- only
+    // the frames the grid builder flagged (non-finite boxes), for which both exit at once otherwise
     dim3 grid((unsigned)std::min<long>(per_frame, tiles), (unsigned)frames);
     if (normal)
         tsm::nms_mask_kernel<true><<<grid, 256, 0, s>>>(nmax, counts, thresh, prep, mask, nullptr);
@@ -671,7 +827,7 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     if (dyn > 200 * 1024) return TSM_ERR_INVALID;
     if (dyn > 48 * 1024)
         TSM_CUDA_TRY(cudaFuncSetAttribute(tsm::nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    tsm::nms_sweep_kernel<<<frames, 256, dyn, s>>>(nmax, counts, mask, keep, num_keep);
+    tsm::nms_sweep_kernel<<<frames, 256, dyn, s>>>(nmax, counts, mask, keep, num_keep, lazy ? grids : nullptr);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }
