@@ -38,7 +38,9 @@ struct TcPlan {
     int smem_bytes;
     int cp;                    // feature channels padded to 8 (width of the bf16 transpose)
     int xyz_chunk;             // 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
-    int tmem_cols;             // power of two >= 32
+    int a_bytes, o_bytes;      // per tile group
+    int grp_cols;              // TMEM columns of one tile group
+    int tmem_cols;             // power of two >= 32 (all groups)
     int d_off;                 // TMEM column of the odd layers' accumulator (even layers use column 0)
     int packed_bytes;          // weights + biases: the first packed_bytes of dynamic smem, same layout in global
 };
@@ -135,29 +137,39 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const SaMlpArgs a, co
     for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// GROUPS = 1: the CTA is one 128-thread tile pipeline.  GROUPS = 2 (used when the weights leave room for only one
+// CTA per SM): two independent 128-thread pipelines share the resident weights, each with its own operand
+// buffer, TMEM columns, mbarrier and named barrier, so one group's gather / epilogue overlaps the other's MMAs.
+template <int GROUPS>
+__global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
     sa_mlp_tc_kernel(const SaMlpArgs a, const TcPlan pl, const __nv_bfloat16* __restrict__ featT,
                      const unsigned char* __restrict__ packed, int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x >> 7);
+    const int tid = threadIdx.x & 127, lane = tid & 31, warp = tid >> 5;  // within the group
+    uint64_t& mma_bar = mma_bars[grp];
+    auto group_sync = [&]() {
+        if (GROUPS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    };
     const int S = a.s, M = a.m;
     const int cpt = TC_ROWS / S;  // whole centres per tile (S divides 128)
     const int nl = pl.nl;
 
     // ---- one-time setup: packed weights + biases (bf16 UMMA layout, built by pack_weights_kernel) arrive
     // with ONE bulk copy (TMA engine); barrier; TMEM
-    if (tid == 0) {
-        mbar_init(smem_u32(&mma_bar), 1);
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < GROUPS; ++g) mbar_init(smem_u32(&mma_bars[g]), 1);
         mbar_init(smem_u32(&w_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
         bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
     }
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"((uint32_t)pl.tmem_cols)
                      : "memory");
@@ -172,15 +184,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         while (!mbar_try_wait_cta(bar, 0))
             if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
     }
-    const uint32_t tmem_base = tmem_base_s;
-    const uint32_t a_smem = smem_u32(smem + pl.a_off);
-    unsigned char* a_ptr = smem + pl.a_off;
-    uint32_t* omax = reinterpret_cast<uint32_t*>(smem + pl.o_off);
+    const uint32_t tmem_base = tmem_base_s + (uint32_t)(grp * pl.grp_cols);
+    const uint32_t a_smem = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
+    unsigned char* a_ptr = smem + pl.a_off + grp * pl.a_bytes;
+    uint32_t* omax = reinterpret_cast<uint32_t*>(smem + pl.o_off + grp * pl.o_bytes);
     uint32_t phase = 0;
     const int Nlast = pl.Npad[nl - 1];
     const int cout_last = a.ch[nl];
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x * GROUPS + grp; tile < num_tiles; tile += gridDim.x * GROUPS) {
         // ---- gather: row `tid`
         {
             const long long g = (long long)tile * TC_ROWS + tid;
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 for (int e = tid; e < Nlast * cpt; e += TC_THREADS) omax[e] = 0u;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        group_sync();
 
         for (int l = 0; l < nl; ++l) {
             const int K = pl.K[l], Np = pl.Npad[l];
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
+                group_sync();
             } else {
                 // bias + ReLU + max over the S rows of each centre
                 const int ci = tid / S;  // centre within the tile
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();
+                group_sync();
                 // pooled tile -> out[b, out_c0 + c, p]; consecutive threads write consecutive centres
                 const long long cbase = (long long)tile * cpt;
                 const long long ctot = a.total_rows / S;
@@ -310,15 +322,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     const int p2 = (int)(cg - (long long)b2 * M);
                     a.out[((size_t)b2 * a.out_ctot + a.out_c0 + c) * M + p2] = __uint_as_float(omax[c * cpt + cc]);
                 }
-                __syncthreads();  // omax / A buffer are reused by the next tile
+                group_sync();  // omax / A buffer are reused by the next tile
             }
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)pl.tmem_cols)
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"((uint32_t)pl.tmem_cols)
                      : "memory");
     }
 }
@@ -355,17 +367,26 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     pl.packed_bytes = off;  // multiple of 64
     off = round_up(off, 128);
     pl.a_off = off;
-    off += TC_ROWS * kmax * 2;
-    off = round_up(off, 16);
-    pl.o_off = off;
-    off += pl.Npad[pl.nl - 1] * (TC_ROWS / S) * 4;
-    pl.smem_bytes = off;
-    if (pl.smem_bytes > 227 * 1024 - 64) return TSM_ERR_INVALID;
-    // layer l accumulates at TMEM column (l & 1) * d_off, so an epilogue never races the next MMA
-    pl.d_off = pl.nl > 1 ? round_up(nmax, 32) : 0;
-    pl.tmem_cols = 32;
-    while (pl.tmem_cols < pl.d_off + nmax) pl.tmem_cols <<= 1;
-    if (pl.tmem_cols > 512) return TSM_ERR_INVALID;
+    pl.a_bytes = round_up(TC_ROWS * kmax * 2, 128);
+    pl.o_bytes = round_up(pl.Npad[pl.nl - 1] * (TC_ROWS / S) * 4, 16);
+    const int fixed = off;
+    auto smem_for = [&](int groups) { return fixed + groups * (pl.a_bytes + pl.o_bytes); };
+    if (smem_for(1) > 227 * 1024 - 64) return TSM_ERR_INVALID;
+    // One accumulator region serves every layer: an epilogue's tcgen05.ld's are complete (wait::ld) before the
+    // barrier that precedes the next layer's MMA, so nothing races.  (Alternating regions, d_off = nmax, halved
+    // the CTAs per SM the TMEM allows; TSMDET_MLP_TMEM_ALT=1 restores it for experiments.)
+    pl.d_off = (pl.nl > 1 && getenv("TSMDET_MLP_TMEM_ALT")) ? round_up(nmax, 32) : 0;
+    pl.grp_cols = 32;
+    while (pl.grp_cols < pl.d_off + nmax) pl.grp_cols <<= 1;
+    if (pl.grp_cols > 512) return TSM_ERR_INVALID;
+    // two tile groups per CTA when the weights allow only one CTA per SM but a second operand buffer still fits
+    int groups = 1;
+    if ((227 * 1024) / (smem_for(1) + 2048) < 2 && smem_for(2) <= 227 * 1024 - 64 && 2 * pl.grp_cols <= 512 &&
+        !getenv("TSMDET_MLP_ONE_GROUP"))
+        groups = 2;
+    pl.tmem_cols = pl.grp_cols * groups;
+    pl.o_off = pl.a_off + groups * pl.a_bytes;
+    pl.smem_bytes = smem_for(groups);
 
     // bf16 (B,N,Cp) transpose of the features
     __nv_bfloat16* featT = nullptr;
@@ -381,14 +402,28 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     }
     const long long tiles = (a.total_rows + TC_ROWS - 1) / TC_ROWS;
     if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
-    TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    int occ = (227 * 1024) / (pl.smem_bytes + 2048);
+    if (groups == 2)
+        TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    else
+        TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    // resident CTAs per SM: what registers / shared memory allow (asked of the runtime: a grid of more CTAs than
+    // are resident runs a second, partial wave) and what the 512 TMEM columns allow
+    int occ = 1;
+    {
+        cudaError_t e = groups == 2
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_mlp_tc_kernel<2>, TC_THREADS * 2, pl.smem_bytes)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sa_mlp_tc_kernel<1>, TC_THREADS, pl.smem_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            occ = 1;
+        }
+    }
     const int tmem_occ = 512 / pl.tmem_cols;
     if (occ > tmem_occ) occ = tmem_occ;
     if (occ < 1) occ = 1;
-    if (occ > 4) occ = 4;
+    if (const char* e = getenv("TSMDET_MLP_OCC")) occ = atoi(e) > 0 && atoi(e) < occ ? atoi(e) : occ;
     long long grid = (long long)tsm_num_sms() * occ;
-    if (grid > tiles) grid = tiles;
+    if (grid * groups > tiles) grid = (tiles + groups - 1) / groups;
     SaMlpArgs args = a;
     args.status = tsm_status_word(stream);
     unsigned char* packed = nullptr;
@@ -401,7 +436,10 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
         pack_weights_kernel<<<pgrid, 256, 0, stream>>>(args, pl, packed);
         TSM_LAUNCH_CHECK();
     }
-    sa_mlp_tc_kernel<<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    if (groups == 2)
+        sa_mlp_tc_kernel<2><<<(unsigned)grid, TC_THREADS * 2, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    else
+        sa_mlp_tc_kernel<1><<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }

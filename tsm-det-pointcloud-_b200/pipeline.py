@@ -176,7 +176,9 @@ class SABackboneNMS(torch.nn.Module):
         static_in = [torch.empty_like(t) for t in (xyz, feats, boxes, scores)]
         for s, t in zip(static_in, (xyz, feats, boxes, scores)):
             s.copy_(t)
-        cap = torch.cuda.Stream(dev)
+        # the sampling chain is captured on the capture stream itself: TSMDET_FPS_PRIORITY=1 makes it a high-priority
+        # stream (its kernels' graph nodes inherit the priority), so FPS CTAs are placed first when SMs free up
+        cap = torch.cuda.Stream(dev, priority=-1 if os.environ.get("TSMDET_FPS_PRIORITY", "0") == "1" else 0)
         cap.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap):
             for _ in range(2):  # warm-up on the capture stream: grows every scratch buffer, folds BN, plans FPS
