@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "6")),
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "8")),
                     help="steps kept in flight (each on its own stream / CUDA graph / buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="per-kernel CUDA-event breakdown to stderr")
