@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const SaMlpArgs a, co
 // GROUPS = 1: the CTA is one 128-thread tile pipeline.  GROUPS = 2 (used when the weights leave room for only one
 // CTA per SM): two independent 128-thread pipelines share the resident weights, each with its own operand
 // buffer, TMEM columns, mbarrier and named barrier, so one group's gather / epilogue overlaps the other's MMAs.
-template <int GROUPS>
+// SUBWARP: nsample < 32 (several centres per warp: butterfly pooling) -- a separate instantiation so the common
+// nsample >= 32 code does not carry its registers.
+template <int GROUPS, bool SUBWARP>
 __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
     sa_mlp_tc_kernel(const SaMlpArgs a, const TcPlan pl, const __nv_bfloat16* __restrict__ featT,
                      const unsigned char* __restrict__ packed, int num_tiles) {
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
                 for (int c0 = 0; c0 < Np; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(t_row + (uint32_t)c0, v);
-                    if (S >= 32) {
+                    if constexpr (!SUBWARP) {
                         uint32_t mine = 0u;  // lane j ends up holding channel c0 + j's maximum
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -300,13 +302,34 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
                                 atomicMax(&omax[(c0 + lane) * cpt + ci], mine);
                         }
                     } else {
+                        // S < 32: butterfly over the S rows of a centre in which every step also halves the
+                        // channels a lane carries (15 shuffles per 16 channels instead of 16 * log2 S)
+                        uint32_t u[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float x = fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f);
-                            uint32_t u = __float_as_uint(x);
-                            for (int o = S >> 1; o >= 1; o >>= 1) u = max(u, __shfl_xor_sync(FULL, u, o));
-                            if ((lane & (S - 1)) == 0) omax[(c0 + j) * cpt + ci] = u;
+                        for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bs[c0 + j], 0.f));
+                        int base = 0, cnt = 16;
+#pragma unroll
+                        for (int st = 0; st < 4; ++st) {
+                            const int d = S >> (st + 1);  // 8, 4, 2, 1 for S = 16; fewer steps for smaller S
+                            if (d >= 1) {
+                                constexpr int kHalf[4] = {8, 4, 2, 1};
+                                const int half = kHalf[st];
+                                const bool upper = (lane & d) != 0;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if (i < half) {
+                                        const uint32_t mine = upper ? u[half + i] : u[i];
+                                        const uint32_t give = upper ? u[i] : u[half + i];
+                                        u[i] = max(mine, __shfl_xor_sync(FULL, give, d));
+                                    }
+                                }
+                                if (upper) base += half;
+                                cnt = half;
+                            }
                         }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < cnt) omax[(c0 + base + i) * cpt + ci] = u[i];  // 16 / S channels per lane
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -402,16 +425,16 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     }
     const long long tiles = (a.total_rows + TC_ROWS - 1) / TC_ROWS;
     if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
-    if (groups == 2)
-        TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
-    else
-        TSM_CUDA_TRY(cudaFuncSetAttribute(sa_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    const bool subwarp = S < 32;
+    auto kern = groups == 2 ? (subwarp ? sa_mlp_tc_kernel<2, true> : sa_mlp_tc_kernel<2, false>)
+                            : (subwarp ? sa_mlp_tc_kernel<1, true> : sa_mlp_tc_kernel<1, false>);
+    TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     // resident CTAs per SM: what shared memory, registers (a grid of more CTAs than are resident runs a second,
     // partial wave: measured 0.094 -> 0.121 ms on layer 1) and the 512 TMEM columns allow
     int occ = (227 * 1024) / (pl.smem_bytes + 2048);
     {
         cudaFuncAttributes fa;
-        cudaError_t e = groups == 2 ? cudaFuncGetAttributes(&fa, sa_mlp_tc_kernel<2>) : cudaFuncGetAttributes(&fa, sa_mlp_tc_kernel<1>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
         if (e == cudaSuccess && fa.numRegs > 0) {
             const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS * groups;
             const int occ_regs = 65536 / regs_cta;
@@ -439,10 +462,7 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
         pack_weights_kernel<<<pgrid, 256, 0, stream>>>(args, pl, packed);
         TSM_LAUNCH_CHECK();
     }
-    if (groups == 2)
-        sa_mlp_tc_kernel<2><<<(unsigned)grid, TC_THREADS * 2, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
-    else
-        sa_mlp_tc_kernel<1><<<(unsigned)grid, TC_THREADS, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    kern<<<(unsigned)grid, TC_THREADS * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }
