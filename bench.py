@@ -379,6 +379,7 @@ def kernel_breakdown(engine, d, dev, args):
 
     xyz, feats, boxes, scores = d
     b = xyz.shape[0]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def t(fn, reps=5):
         """Device time of one stage: captured into a CUDA graph (as the timed step runs it -- no per-launch host
@@ -393,13 +394,17 @@ def kernel_breakdown(engine, d, dev, args):
             with torch.cuda.graph(graph, stream=side):
                 fn()
             graph.replay()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(side)
+            total = 0.0
             for _ in range(reps):
+                flush_buf.zero_()  # cold L2 for every replay, as in the timed step
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(side)
                 graph.replay()
-            e.record(side)
+                e.record(side)
+                e.synchronize()
+                total += s.elapsed_time(e)
         torch.cuda.synchronize(dev)
-        return s.elapsed_time(e) / reps
+        return total / reps
 
     kernels = []
     kernels_ctx = {}
