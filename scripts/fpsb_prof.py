@@ -6,7 +6,7 @@ import torch, synth
 from tsmdet_b200 import pointnet2_utils as pu
 dev = torch.device("cuda:0")
 os.environ["TSMDET_FPS_ALGO"] = "bucket"
-for (n, m, T, P) in [(16384, 4096, 1024, 16), (16384, 4096, 512, 32), (4096, 1024, 1024, 4), (4096, 1024, 256, 16), (1024, 512, 128, 8), (1024, 512, 32, 32)]:
+for (n, m, T, P) in [(16384, 4096, 1024, 16), (4096, 1024, 512, 8)]:
     os.environ["TSMDET_FPSB_T"] = str(T); os.environ["TSMDET_FPSB_P"] = str(P)
     xyz = torch.from_numpy(synth.cloud_ground_objects(2, n, 1)).to(dev)
     pu.farthest_point_sample(xyz, m); torch.cuda.synchronize()

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
     };
     const int S = a.s, M = a.m;
     const int cpt = TC_ROWS / S;  // whole centres per tile (S divides 128)
+    const int log2s = 31 - __clz(S), log2cpt = 31 - __clz(cpt);
     const int nl = pl.nl;
 
     // ---- one-time setup: packed weights + biases (bf16 UMMA layout, built by pack_weights_kernel) arrive
@@ -199,8 +200,8 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
         {
             const long long g = (long long)tile * TC_ROWS + tid;
             const bool rv = g < a.total_rows;
-            const long long cpi = rv ? g / S : 0;
-            const int b = (int)(cpi / M);
+            const long long cpi = rv ? g >> log2s : 0;   // S is a power of two; B*M < 2^31 (checked by the launcher)
+            const int b = (int)((unsigned)cpi / (unsigned)M);
             bool live = rv;
             int id = 0;
             if (rv) {
@@ -210,22 +211,30 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
             const int nchunk0 = pl.K[0] >> 3;
             const int fchunks = pl.cp >> 3;
             const uint4* frow = reinterpret_cast<const uint4*>(featT + ((size_t)b * a.n + id) * pl.cp);
-            for (int kc = 0; kc < nchunk0; ++kc) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (live) {
-                    if (kc < fchunks) {
-                        v = __ldg(frow + kc);
-                    } else if (kc == pl.xyz_chunk) {
+            // feature chunks four at a time: four independent 16-byte loads in flight per thread, then four stores
+            for (int kc0 = 0; kc0 < nchunk0; kc0 += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kc = kc0 + u;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && kc < fchunks) v[u] = __ldg(frow + kc);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kc = kc0 + u;
+                    if (kc >= nchunk0) break;
+                    if (live && kc == pl.xyz_chunk) {
                         const float* p = a.xyz + ((size_t)b * a.n + id) * 3;
                         const float* q = a.new_xyz + (size_t)cpi * 3;
                         const float dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
                         const float dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
                         const float dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
-                        v.x = pack_bf16(dx, dy);
-                        v.y = pack_bf16(dz, 0.f);
+                        v[u].x = pack_bf16(dx, dy);
+                        v[u].y = pack_bf16(dz, 0.f);
                     }
+                    *reinterpret_cast<uint4*>(a_ptr + (size_t)kc * (TC_ROWS * 16) + tid * 16) = v[u];
                 }
-                *reinterpret_cast<uint4*>(a_ptr + (size_t)kc * (TC_ROWS * 16) + tid * 16) = v;
             }
             if (S > 32)
                 for (int e = tid; e < Nlast * cpt; e += TC_THREADS) omax[e] = 0u;
@@ -335,14 +344,14 @@ __global__ void __launch_bounds__(TC_THREADS * GROUPS, 1)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 group_sync();
                 // pooled tile -> out[b, out_c0 + c, p]; consecutive threads write consecutive centres
-                const long long cbase = (long long)tile * cpt;
-                const long long ctot = a.total_rows / S;
+                const unsigned cbase = (unsigned)tile * (unsigned)cpt;
+                const unsigned ctot = (unsigned)(a.total_rows >> log2s);
                 for (int e = tid; e < cout_last * cpt; e += TC_THREADS) {
-                    const int c = e / cpt, cc = e - c * cpt;
-                    const long long cg = cbase + cc;
+                    const int c = e >> log2cpt, cc = e & (cpt - 1);
+                    const unsigned cg = cbase + (unsigned)cc;
                     if (cg >= ctot) continue;
-                    const int b2 = (int)(cg / M);
-                    const int p2 = (int)(cg - (long long)b2 * M);
+                    const int b2 = (int)(cg / (unsigned)M);
+                    const int p2 = (int)(cg - (unsigned)b2 * (unsigned)M);
                     a.out[((size_t)b2 * a.out_ctot + a.out_c0 + c) * M + p2] = __uint_as_float(omax[c * cpt + cc]);
                 }
                 group_sync();  // omax / A buffer are reused by the next tile
@@ -366,6 +375,7 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     using namespace tsm;
     const int S = a.s;
     if (S > TC_ROWS || (TC_ROWS % S) != 0 || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile
+    if ((long long)b * a.m >= 0x7fffffffLL) return TSM_ERR_INVALID;                         // 32-bit centre arithmetic
     if (a.num_layers < 1 || a.num_layers > TC_MAX_LAYERS) return TSM_ERR_INVALID;
     TcPlan pl;
     pl.nl = a.num_layers;
