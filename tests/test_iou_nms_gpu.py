@@ -210,3 +210,33 @@ def test_multi_thresh_batch_matches_per_frame_driver():
         assert bool((idx[i, k:] == -1).all())
         if k:
             assert torch.equal(sc[i, :k], ts[i][want_idx])
+
+
+@pytest.mark.parametrize("thresh", [0.01, 0.1, 0.5, 0.7])
+def test_lazy_nms_equals_full_mask_nms(thresh, monkeypatch):
+    """The default rotated NMS computes suppression rows lazily (only for boxes still alive, one CTA per frame); the
+    full-mask pipeline (grid pairs -> mask -> sweep) must give the same kept indices in the same order -- batched,
+    with per-frame counts, presorted or not, for clustered, random, duplicate and degenerate (collinear) boxes."""
+    from tsmdet_b200 import iou3d_nms_utils as iu
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    frames = []
+    for i, n in enumerate([4096, 4096, 3000, 1, 65, 2048]):
+        b = synth.boxes_clustered(n, 400 + i, centres=max(1, n // 20)) if i % 2 == 0 else synth.boxes_random(n, 500 + i)
+        pad = np.zeros((4096 - n, 7), np.float32)
+        frames.append(np.concatenate([b, pad], 0))
+    frames[5][:1024] = frames[5][1024:2048]          # exact duplicates
+    frames[2][:500, 1] = 3.0                          # collinear centres
+    boxes = torch.from_numpy(np.stack(frames)).to(dev)
+    counts = torch.tensor([4096, 4096, 3000, 1, 65, 2048], dtype=torch.int32, device=dev)
+    scores = torch.from_numpy(np.stack([rng.permutation(4096).astype(np.float32) for _ in range(6)])).to(dev)
+    scores = torch.where(torch.arange(4096, device=dev).unsqueeze(0) < counts.unsqueeze(1), scores,
+                         torch.full_like(scores, float("-inf")))
+    monkeypatch.setenv("TSMDET_NMS_ALGO", "mask")
+    want_sel, want_num = iu.nms_gpu_batch(boxes, scores, thresh, counts=counts)
+    monkeypatch.delenv("TSMDET_NMS_ALGO")
+    got_sel, got_num = iu.nms_gpu_batch(boxes, scores, thresh, counts=counts)
+    assert torch.equal(got_num, want_num)
+    assert torch.equal(got_sel, want_sel)
+    assert int(got_num[3]) == 1 and int(got_num.min()) >= 1
