@@ -46,5 +46,5 @@ by = b * (4 * c * m + 24 * n + 4 * c * n)
 rows.append(dict(op="three_interpolate", shape="W C=128", ms=round(ms, 4), alg_MB=round(by / 1e6, 2), GBs=round(by / ms / 1e6, 1), frac=round(by / ms / 1e6 / PEAK, 3)))
 unk = torch.from_numpy(synth.cloud_uniform(b, n, 3, synth.WAYMO_RANGE)).to(dev); kn = unk[:, ::4, :].contiguous()
 ms = t(lambda: pu.three_nn(unk, kn), reps=3)
-rows.append(dict(op="three_nn (brute force)", shape="W 65536x16384", ms=round(ms, 4), tests_per_s=round(b * n * m / ms * 1e3 / 1e12, 2)))
+rows.append(dict(op="three_nn (grid)", shape="W 65536x16384", ms=round(ms, 4), tests_per_s=round(b * n * m / ms * 1e3 / 1e12, 2)))
 for r in rows: print(json.dumps(r), flush=True)

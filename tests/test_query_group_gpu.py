@@ -192,6 +192,44 @@ def test_three_nn(orc, b, n, m):
     assert np.array_equal(dist.cpu().numpy().view(np.uint32), np.sqrt(wd2).view(np.uint32))
 
 
+def test_three_nn_grid_equals_brute_force(orc, monkeypatch):
+    """The grid search (three_nn_grid.cu) returns exactly what the brute-force kernel returns -- (d2, k) ties
+    included -- on lattices (many equal distances), duplicated known points, unknown points outside the known
+    cloud, flat and collinear clouds, and at the Waymo FP-layer size (65536 unknown, 16384 known)."""
+    from tsmdet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(9)
+    cases = []
+    lat = synth.cloud_lattice(2, 4000, 41)
+    cases.append(("lattice", synth.cloud_lattice(2, 6000, 40), lat))
+    dup = synth.cloud_dup_padded(2, 4096, 42, unique_frac=0.5)
+    cases.append(("dup", synth.cloud_uniform(2, 5000, 43), dup))
+    out = synth.cloud_uniform(2, 3000, 44) * 3.0 - 40.0
+    cases.append(("outside", out.astype(np.float32), synth.cloud_ground_objects(2, 2048, 45)))
+    flat = synth.cloud_uniform(2, 3000, 46)
+    flat[:, :, 2] = 0.5
+    cases.append(("flat", synth.cloud_uniform(2, 2000, 47), flat))
+    line = synth.cloud_uniform(2, 1500, 48)
+    line[:, :, 1:] = 1.0
+    cases.append(("line", synth.cloud_uniform(2, 2000, 49), line))
+    same = np.ones((1, 600, 3), np.float32)
+    cases.append(("same", synth.cloud_uniform(1, 500, 50), same))
+    w_unknown = synth.cloud_uniform(2, 65536, 51, synth.WAYMO_RANGE)
+    cases.append(("waymo", w_unknown, np.ascontiguousarray(w_unknown[:, ::4, :])))
+    for name, unknown, known in cases:
+        monkeypatch.setenv("TSMDET_NN_ALGO", "brute")
+        d0, i0 = pu.three_nn(T(unknown), T(known))
+        monkeypatch.delenv("TSMDET_NN_ALGO")
+        d1, i1 = pu.three_nn(T(unknown), T(known))
+        assert torch.equal(i0, i1), name
+        assert torch.equal(d0.view(torch.int32), d1.view(torch.int32)), name
+    # and against the oracle on the tie-heavy ones
+    for name, unknown, known in cases[:2]:
+        d1, i1 = pu.three_nn(T(unknown[:1]), T(known[:1]))
+        wd2, wi = orc.three_nn(unknown[:1], known[:1])
+        assert np.array_equal(i1.cpu().numpy(), wi), name
+
+
 def test_three_interpolate_and_grad(orc):
     from tsmdet_b200 import pointnet2_utils as pu
 

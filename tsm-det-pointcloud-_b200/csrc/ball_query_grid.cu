@@ -22,23 +22,9 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "grid.cuh"
 
 namespace tsm {
-
-constexpr int kGridCells = 32768;   // shared-memory histogram: 128 KB
-constexpr int kMaxCell = 256;       // largest cell population the index fix-up accepts
-constexpr int kHdrInts = 16;        // per-cloud header: lo[3], inv[3] (float bits), n[3], ok
-
-struct GridHdr {
-    float lo[3];
-    float inv[3];
-    int n[3];
-    int ok;
-};
-
-__device__ __forceinline__ int grid_q(float v, float lo, float inv, int n) {
-    return min(max(__float2int_rd(__fmul_rn(__fsub_rn(v, lo), inv)), 0), n - 1);
-}
 
 __global__ void __launch_bounds__(1024, 1)
     bq_grid_build_kernel(int n, float rout, const float* __restrict__ xyz_all, int* __restrict__ hdr_all,
@@ -88,11 +74,28 @@ __global__ void __launch_bounds__(1024, 1)
     float ext[3] = {hi0 - lo0, hi1 - lo1, hi2 - lo2};
     const float lo[3] = {lo0, lo1, lo2};
     int nc[3];
-    bool ok = rout > 0.f && rout < 1.0e18f;
-    const float s0 = rout * 1.01f;
+    const bool automatic = rout < 0.f;  // no radius (3-NN): about two points per cell
+    bool ok = automatic || (rout > 0.f && rout < 1.0e18f);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (!(ext[a] >= 0.f) || !(ext[a] < 3.0e38f)) { ok = false; ext[a] = 0.f; }
+    float s0 = rout * 1.01f;
+    if (automatic) {
+        // smallest cell edge whose grid has at most `target` cells (bisection; every thread computes the same)
+        const float target = fminf(fmaxf(0.5f * (float)n, 64.f), (float)kGridCells);
+        float lo_s = 0.f, hi_s = fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
+        if (!(hi_s > 0.f)) hi_s = 1.f;
+        for (int it = 0; it < 40; ++it) {
+            const float mid = 0.5f * (lo_s + hi_s);
+            float cells = 1.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) cells *= fminf(fmaxf(floorf(ext[a] / mid), 1.f), 2048.f);
+            if (mid > 0.f && cells <= target) hi_s = mid; else lo_s = mid;
+        }
+        s0 = hi_s;
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        if (!(ext[a] >= 0.f) || !(ext[a] < 3.0e38f)) { ok = false; ext[a] = 0.f; }
         const float q = ok ? floorf(ext[a] / s0) : 1.f;
         nc[a] = (int)fminf(fmaxf(q, 1.f), 2048.f);
     }
@@ -346,16 +349,14 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace tsm
 
-// Builds the grids of all clouds and answers every cloud whose grid is usable.  *grid_ok receives the
-// per-cloud header array (device; int [b][16], word 15 = usable) for the brute-force kernels to consult.
-int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout, int nsample, const float* new_xyz,
-                        const float* xyz, int* idx_cnt, int* idx, cudaStream_t stream, const int** grid_hdr) {
+int tsm_grid_build(int b, int n, float rout, const float* xyz, cudaStream_t stream, int tag, const int** hdr_out,
+                   const int** cell_start_out, const float4** sorted_out) {
     using namespace tsm;
     const size_t hdr_bytes = ((size_t)b * kHdrInts * sizeof(int) + 255) & ~(size_t)255;
     const size_t cs_bytes = ((size_t)b * (kGridCells + 1) * sizeof(int) + 255) & ~(size_t)255;
     const size_t pts_bytes = ((size_t)b * n * sizeof(float4) + 255) & ~(size_t)255;
     void* base = nullptr;
-    int rc = tsm_scratch_get(4, hdr_bytes + cs_bytes + 2 * pts_bytes, stream, &base);
+    int rc = tsm_scratch_get(tag, hdr_bytes + cs_bytes + 2 * pts_bytes, stream, &base);
     if (rc != TSM_OK) return rc;
     unsigned char* p = static_cast<unsigned char*>(base);
     int* hdr = reinterpret_cast<int*>(p);
@@ -366,6 +367,25 @@ int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout
     TSM_CUDA_TRY(cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     bq_grid_build_kernel<<<b, 1024, dyn, stream>>>(n, rout, xyz, hdr, cell_start, tmp, sorted);
     TSM_LAUNCH_CHECK();
+    *hdr_out = hdr;
+    *cell_start_out = cell_start;
+    *sorted_out = sorted;
+    return TSM_OK;
+}
+
+// Builds the grids of all clouds and answers every cloud whose grid is usable.  *grid_hdr receives the
+// per-cloud header array (device; int [b][16], word 9 = usable) for the brute-force kernels to consult.
+int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout, int nsample, const float* new_xyz,
+                        const float* xyz, int* idx_cnt, int* idx, cudaStream_t stream, const int** grid_hdr) {
+    using namespace tsm;
+    const int *hdr = nullptr, *cell_start = nullptr;
+    const float4* sorted = nullptr;
+    if (!(rout > 0.f)) {  // no ball: nothing can hit; leave every cloud to the brute-force kernels
+        *grid_hdr = nullptr;
+        return TSM_OK;
+    }
+    int rc = tsm_grid_build(b, n, rout, xyz, stream, 4, &hdr, &cell_start, &sorted);
+    if (rc != TSM_OK) return rc;
     const float rin2 = rin * rin, rout2 = rout * rout;  // f32 products, as ball_query_gpu.cu:91, 154-155
     const long long warps = (long long)b * m;
     const unsigned blocks = (unsigned)((warps + 7) / 8);

@@ -12,7 +12,13 @@
 // Known points are streamed through shared memory in their native (M,3) layout; every
 // thread of a warp reads the same point (a broadcast), so the tile costs one
 // shared-memory wavefront per coordinate per warp.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+
+int tsm_three_nn_grid(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx,
+                      cudaStream_t stream, const int** grid_hdr);
 
 namespace tsm {
 
@@ -22,9 +28,10 @@ constexpr int NN_UPT = 2;      // unknown points per thread (amortises the tile 
 
 __global__ void __launch_bounds__(NN_THREADS)
     three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
-                    float* __restrict__ dist2, int* __restrict__ idx) {
+                    float* __restrict__ dist2, int* __restrict__ idx, const int* __restrict__ grid_hdr) {
     __shared__ float tile[NN_TILE * 3];
     const int b = blockIdx.y;
+    if (grid_hdr && grid_hdr[b * 16 + 9]) return;  // answered by the grid search (three_nn_grid.cu)
     const int tid = threadIdx.x;
     known += (size_t)b * m * 3;
     float ux[NN_UPT], uy[NN_UPT], uz[NN_UPT];
@@ -133,8 +140,18 @@ int tsmdet_three_nn(int b, int n, int m, const float* unknown, const float* know
                     void* stream) {
     if (b <= 0 || n <= 0) return TSM_OK;
     if (b > 65535 || m < 0) return TSM_ERR_INVALID;
+    // enough known points for a grid to pay: search the 3x3x3 neighbourhood instead of all m (three_nn_grid.cu);
+    // the brute-force kernel then only serves clouds whose grid was unusable.  TSMDET_NN_ALGO=brute disables it.
+    const int* ghdr = nullptr;
+    {
+        const char* algo = getenv("TSMDET_NN_ALGO");
+        if (m >= 512 && !(algo && !strcmp(algo, "brute"))) {
+            const int rc = tsm_three_nn_grid(b, n, m, unknown, known, dist2, idx, (cudaStream_t)stream, &ghdr);
+            if (rc != TSM_OK) return rc;
+        }
+    }
     dim3 grid((unsigned)tsm::divup(n, tsm::NN_THREADS * tsm::NN_UPT), (unsigned)b);
-    tsm::three_nn_kernel<<<grid, tsm::NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+    tsm::three_nn_kernel<<<grid, tsm::NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx, ghdr);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }
