@@ -45,7 +45,7 @@ struct Scratch {
 // Grow-only device scratch, one buffer per (device, stream, user tag) so that calls on
 // different streams never share a buffer; stream-ordered (cudaMallocAsync), so repeated
 // NMS calls allocate nothing.
-constexpr int kScratchSlots = 16;
+constexpr int kScratchSlots = 256;  // (device, stream, tag) keys: 8 pipeline lanes x 3 streams x 6 tags and room to spare
 static Scratch g_scratch[kScratchSlots];
 static unsigned long long g_tick = 0;
 static std::mutex g_scratch_mu;
