@@ -570,6 +570,16 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
         const bool fits = tsm_fps_bucket_supports(n, weights != nullptr);
         const bool crowded = (long)b * 8 > tsm_num_sms();
         if (fits && (algo == 2 || (algo == 0 && crowded && n >= 1024))) return tsm_fps_bucket_launch(a, b, stream);
+        // clouds of 16385..65536 points: the pruned sampler over a cluster of CTAs (one SM per ~15000 points; a pick
+        // costs the same whatever N is, where the brute-force cluster kernel below slows down with N)
+        if (algo != 1 && tsm_fps_bucket_cluster_supports(n, weights != nullptr)) {
+            if (tie_iter) TSM_CUDA_TRY(cudaMemsetAsync(tie_iter, 0, sizeof(int) * (size_t)b, stream));  // no chaining facts
+            a.tie_iter = nullptr;
+            a.vals = nullptr;
+            a.parent_tie = nullptr;
+            a.parent_vals = nullptr;
+            return tsm_fps_bucket_cluster_launch(a, b, stream);
+        }
     }
     FpsPlan pl;
     if (!plan_fps(b, n, a.log2bs, weights != nullptr, true, &pl)) return TSM_ERR_INVALID;

@@ -41,3 +41,6 @@ __device__ __forceinline__ int warp_pick(uint32_t u, uint32_t rk, uint32_t& wu, 
 // fps_bucket.cu.  Returns TSM_ERR_INVALID when the shape is outside what the bucketed kernel holds in one CTA.
 bool tsm_fps_bucket_supports(int n, bool weighted);
 int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream);
+// fps_bucket_cluster.cu: the same sampler over a cluster of CTAs, 16384 < N <= 65536.
+bool tsm_fps_bucket_cluster_supports(int n, bool weighted);
+int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream);

@@ -1,0 +1,449 @@
+// fps_bucket_cluster.cu -- the spatially pruned sampler of fps_bucket.cu for clouds that need several SMs
+// (16384 < N <= 65536): one thread-block CLUSTER per cloud, every CTA holding a contiguous slice of the
+// Morton-sorted cloud in shared memory.
+//
+// Same indices, bit for bit, as farthest_point_sampling_kernel
+//   /root/reference/pcdet/ops/pointnet2/pointnet2_batch/src/sampling_gpu.cu:100-216.
+//
+//  * fps_sort_kernel (one CTA per cloud, any N): bounding box -> adaptive Morton grid (15 key bits, handed out
+//    greedily to the axis with the largest cell extent) -> counting sort (histogram in shared memory, scan, scatter)
+//    of (x, y, z, original index) float4 records into a global scratch array.
+//  * fps_bucket_cluster_kernel: CTA r of the cluster loads slice r of that array into the shared-memory planes of
+//    fps_bucket.cu (lanes own P spatially compact points, min-distances in registers, one box per 16 lanes) and
+//    runs the same per-pick step -- exact box pruning, one CTA barrier, local 32-record reduction.  The CTAs'
+//    winners (key, original index, coordinates: 20 bytes) are then exchanged with st.async into every peer's
+//    shared memory, completing on the peer's mbarrier (double-buffered by pick parity, no cluster-wide barrier on
+//    the critical path), and every warp picks the cluster winner: largest key, smallest reference rank among
+//    equals.  A pick costs what a single-CTA pick costs plus one DSMEM flight, whatever N is, instead of growing
+//    with N as the brute-force cluster kernel of fps.cu does.
+#include "fps.cuh"
+
+namespace tsm {
+
+constexpr int FBC_T = 1024;
+constexpr int FBC_P = 16;
+constexpr int FBC_CAP = FBC_T * FBC_P;  // points per CTA
+constexpr int FBC_CELL_BITS = 15;
+constexpr uint32_t kXRecBytes = 20;  // key, index, x, y (v4) + z (b32)
+
+struct __align__(16) XRec {
+    uint32_t u, k;
+    float x, y;
+    float z;
+    uint32_t pad[3];
+};
+static_assert(sizeof(XRec) == 32, "XRec must be 32 bytes");
+
+__device__ __forceinline__ uint32_t fbc_rank(uint32_t k, int L) {
+    return (L == 0) ? k : (__brev(k & ((1u << L) - 1u)) | (k >> L));
+}
+
+__device__ __forceinline__ int fbc_slot_index(int s) {  // sorted position within the CTA -> shared-memory element
+    constexpr int P = FBC_P;
+    const int p = s & (P - 1), l = (s / P) & 31, w = s / (32 * P);
+    return w * (32 * P) + (p >> 2) * 128 + l * 4 + (p & 3);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+    fps_sort_kernel(int n, const float* __restrict__ xyz_all, float4* __restrict__ sorted_all) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint32_t* const hist = reinterpret_cast<uint32_t*>(dyn);  // [1 << FBC_CELL_BITS]
+    __shared__ float red[6][32];
+    __shared__ uint32_t woff[32];
+    constexpr int T = 1024, NW = 32, ncells = 1 << FBC_CELL_BITS, cell_bits = FBC_CELL_BITS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ xyz = xyz_all + (size_t)cloud * n * 3;
+    float4* __restrict__ sorted = sorted_all + (size_t)cloud * n;
+
+    const float inf = __int_as_float(0x7f800000);
+    float lo0 = inf, lo1 = inf, lo2 = inf, hi0 = -inf, hi1 = -inf, hi2 = -inf;
+    for (int k = tid; k < n; k += T) {
+        const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+        lo0 = fminf(lo0, x); hi0 = fmaxf(hi0, x);
+        lo1 = fminf(lo1, y); hi1 = fmaxf(hi1, y);
+        lo2 = fminf(lo2, z); hi2 = fmaxf(hi2, z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fminf(lo0, __shfl_xor_sync(FULL, lo0, o)); hi0 = fmaxf(hi0, __shfl_xor_sync(FULL, hi0, o));
+        lo1 = fminf(lo1, __shfl_xor_sync(FULL, lo1, o)); hi1 = fmaxf(hi1, __shfl_xor_sync(FULL, hi1, o));
+        lo2 = fminf(lo2, __shfl_xor_sync(FULL, lo2, o)); hi2 = fmaxf(hi2, __shfl_xor_sync(FULL, hi2, o));
+    }
+    if (lane == 0) {
+        red[0][warp] = lo0; red[1][warp] = lo1; red[2][warp] = lo2;
+        red[3][warp] = hi0; red[4][warp] = hi1; red[5][warp] = hi2;
+    }
+    for (int c = tid; c < ncells; c += T) hist[c] = 0u;
+    __syncthreads();
+    for (int w = 0; w < NW; ++w) {
+        lo0 = fminf(lo0, red[0][w]); lo1 = fminf(lo1, red[1][w]); lo2 = fminf(lo2, red[2][w]);
+        hi0 = fmaxf(hi0, red[3][w]); hi1 = fmaxf(hi1, red[4][w]); hi2 = fmaxf(hi2, red[5][w]);
+    }
+    float e0 = hi0 - lo0, e1 = hi1 - lo1, e2 = hi2 - lo2;
+    if (!(e0 > 0.f) || !(e0 < 3.0e38f)) e0 = 0.f;
+    if (!(e1 > 0.f) || !(e1 < 3.0e38f)) e1 = 0.f;
+    if (!(e2 > 0.f) || !(e2 < 3.0e38f)) e2 = 0.f;
+    int nb0 = 0, nb1 = 0, nb2 = 0;
+    uint32_t order = 0u;  // 2 bits per key bit, most significant key bit first
+    {
+        float c0 = e0, c1 = e1, c2 = e2;
+        for (int i = 0; i < cell_bits; ++i) {
+            int ax = 0;
+            if (c1 > c0 && c1 >= c2) ax = 1;
+            if (c2 > c0 && c2 > c1) ax = 2;
+            order |= (uint32_t)ax << (2 * i);
+            if (ax == 0) { ++nb0; c0 *= 0.5f; }
+            else if (ax == 1) { ++nb1; c1 *= 0.5f; }
+            else { ++nb2; c2 *= 0.5f; }
+        }
+    }
+    const float inv0 = e0 > 0.f ? (float)(1 << nb0) / e0 : 0.f;
+    const float inv1 = e1 > 0.f ? (float)(1 << nb1) / e1 : 0.f;
+    const float inv2 = e2 > 0.f ? (float)(1 << nb2) / e2 : 0.f;
+    auto cell_key = [&](float x, float y, float z) -> uint32_t {
+        const int q0 = min(max(__float2int_rd((x - lo0) * inv0), 0), (1 << nb0) - 1);
+        const int q1 = min(max(__float2int_rd((y - lo1) * inv1), 0), (1 << nb1) - 1);
+        const int q2 = min(max(__float2int_rd((z - lo2) * inv2), 0), (1 << nb2) - 1);
+        int r0 = nb0, r1 = nb1, r2 = nb2;
+        uint32_t key = 0u;
+#pragma unroll 1
+        for (int i = 0; i < cell_bits; ++i) {
+            const uint32_t ax = (order >> (2 * i)) & 3u;
+            uint32_t bit;
+            if (ax == 0u) bit = (q0 >> --r0) & 1;
+            else if (ax == 1u) bit = (q1 >> --r1) & 1;
+            else bit = (q2 >> --r2) & 1;
+            key = (key << 1) | bit;
+        }
+        return key;
+    };
+    for (int k = tid; k < n; k += T)
+        atomicAdd(&hist[cell_key(__ldg(xyz + 3 * k), __ldg(xyz + 3 * k + 1), __ldg(xyz + 3 * k + 2))], 1u);
+    __syncthreads();
+    {
+        constexpr int cpw = ncells / NW;
+        uint32_t carry = 0u;
+        for (int c = warp * cpw + lane; c < (warp + 1) * cpw; c += 32) {
+            const uint32_t v = hist[c];
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            hist[c] = carry + inc - v;
+            carry += __shfl_sync(FULL, inc, 31);
+        }
+        if (lane == 0) woff[warp] = carry;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = woff[lane];
+            uint32_t inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += t;
+            }
+            woff[lane] = inc - v;
+        }
+        __syncthreads();
+        const uint32_t off = woff[warp];
+        for (int c = warp * cpw + lane; c < (warp + 1) * cpw; c += 32) hist[c] += off;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += T) {
+        const float x = __ldg(xyz + 3 * k), y = __ldg(xyz + 3 * k + 1), z = __ldg(xyz + 3 * k + 2);
+        const uint32_t pos = atomicAdd(&hist[cell_key(x, y, z)], 1u);
+        sorted[pos] = make_float4(x, y, z, __int_as_float(k));  // order inside a cell is arbitrary: it never decides a result
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dynamic smem: planes 12*CAP | original index u16 2*CAP | group boxes 24*(T/16) | recs [2][32] uint2 |
+//               exchange records [2][8] XRec | first point (16 B)
+constexpr int FBC_MAXC = 8;
+constexpr int FBC_SMEM = 14 * FBC_CAP + 24 * (FBC_T / 16) + 512 + 2 * FBC_MAXC * 32 + 16;
+
+__global__ void __launch_bounds__(FBC_T, 1)
+    fps_bucket_cluster_kernel(const FpsArgs a, const float4* __restrict__ sorted_all, int per_cta) {
+    constexpr int T = FBC_T, P = FBC_P, CAP = FBC_CAP, C4 = P / 4, NW = T / 32;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    float* const sx = reinterpret_cast<float*>(dyn);
+    float* const sy = sx + CAP;
+    float* const sz = sy + CAP;
+    uint16_t* const sk = reinterpret_cast<uint16_t*>(sz + CAP);
+    float4* const sbox4 = reinterpret_cast<float4*>(sk + CAP);
+    float2* const sbox2 = reinterpret_cast<float2*>(sbox4 + T / 16);
+    uint2* const recs = reinterpret_cast<uint2*>(sbox2 + T / 16);  // [2][32]
+    XRec* const xrec = reinterpret_cast<XRec*>(recs + 64);         // [2][FBC_MAXC]
+    float* const first_xyz = reinterpret_cast<float*>(xrec + 2 * FBC_MAXC);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t csize = cluster_nctarank();
+    const int cloud = blockIdx.x / csize;
+    const int n = a.n, m = a.m, L = a.log2bs;
+    const float* __restrict__ xyz = a.xyz + (size_t)cloud * n * 3;
+    const float4* __restrict__ sorted = sorted_all + (size_t)cloud * n;
+    int* __restrict__ idxs = a.idxs + (size_t)cloud * m;
+    const int lo = min((int)crank * per_cta, n);
+    const int nloc = min(per_cta, n - lo);  // this CTA's slice of the sorted cloud: [lo, lo + nloc)
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
+        mbar_fence_init_cluster();
+        first_xyz[0] = __ldg(xyz + 0);
+        first_xyz[1] = __ldg(xyz + 1);
+        first_xyz[2] = __ldg(xyz + 2);
+        if (crank == 0 && m > 0) idxs[0] = 0;
+    }
+    // ---- load the slice into the lane-major planes
+    for (int s = tid; s < CAP; s += T) {
+        const int e = fbc_slot_index(s);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < nloc) v = sorted[lo + s];
+        sx[e] = v.x; sy[e] = v.y; sz[e] = v.z;
+        sk[e] = s < nloc ? (uint16_t)__float_as_int(v.w) : (uint16_t)0;
+    }
+    __syncthreads();
+
+    const int base = warp * (32 * P) + lane * 4;
+    const int first = (warp * 32 + lane) * P;
+    float md[P];
+    {
+        // each lane's P points in ascending reference rank (see fps_bucket.cu)
+        uint32_t rk[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            rk[p] = (first + p < nloc) ? fbc_rank(sk[base + (p >> 2) * 128 + (p & 3)], L) : (0xffffffe0u + (uint32_t)p);
+        int dst[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int before = 0;
+#pragma unroll
+            for (int q = 0; q < P; ++q) before += (rk[q] < rk[p]) ? 1 : 0;
+            dst[p] = base + (before >> 2) * 128 + (before & 3);
+        }
+        {
+            uint16_t v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) v[p] = sk[base + (p >> 2) * 128 + (p & 3)];
+#pragma unroll
+            for (int p = 0; p < P; ++p) sk[dst[p]] = v[p];
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            float* const plane = sx + pl * CAP;
+            float v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) v[p] = plane[base + (p >> 2) * 128 + (p & 3)];
+#pragma unroll
+            for (int p = 0; p < P; ++p) plane[dst[p]] = v[p];
+        }
+    }
+    {
+        float bx0 = __int_as_float(0x7f800000), by0 = bx0, bz0 = bx0, bx1 = -bx0, by1 = -bx0, bz1 = -bx0;
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int p = c * 4 + e;
+                float d0 = -2.f;
+                if (first + p < nloc) {
+                    bx0 = fminf(bx0, xs[e]); bx1 = fmaxf(bx1, xs[e]);
+                    by0 = fminf(by0, ys[e]); by1 = fmaxf(by1, ys[e]);
+                    bz0 = fminf(bz0, zs[e]); bz1 = fmaxf(bz1, zs[e]);
+                    d0 = a.temp ? a.temp[(size_t)cloud * n + sk[base + c * 128 + e]] : 1e10f;
+                }
+                md[p] = d0;
+            }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(FULL, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(FULL, bx1, o));
+            by0 = fminf(by0, __shfl_xor_sync(FULL, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(FULL, by1, o));
+            bz0 = fminf(bz0, __shfl_xor_sync(FULL, bz0, o)); bz1 = fmaxf(bz1, __shfl_xor_sync(FULL, bz1, o));
+        }
+        if ((lane & 15) == 0) {
+            sbox4[tid >> 4] = make_float4(bx0, bx1, by0, by1);
+            sbox2[tid >> 4] = make_float2(bz0, bz1);
+        }
+    }
+    __syncthreads();
+
+    float lmax = -2.f;
+    uint32_t u = 0u, wu = 0u, wpos = (uint32_t)base;
+    int lpos = base;
+
+    auto warp_step = [&](float x1, float y1, float z1, const float4 b4, const float2 b2, bool force) {
+        const float dx = fmaxf(fmaxf(__fsub_rn(b4.x, x1), __fsub_rn(x1, b4.y)), 0.f);
+        const float dy = fmaxf(fmaxf(__fsub_rn(b4.z, y1), __fsub_rn(y1, b4.w)), 0.f);
+        const float dz = fmaxf(fmaxf(__fsub_rn(b2.x, z1), __fsub_rn(z1, b2.y)), 0.f);
+        const float lb = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        const bool hit = !(lb >= lmax) || force;  // NaN bounds count as hits
+        if (!__any_sync(FULL, hit)) return;
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
+            md[c * 4 + 0] = fminf(sqdist3(x1, y1, z1, X.x, Y.x, Z.x), md[c * 4 + 0]);
+            md[c * 4 + 1] = fminf(sqdist3(x1, y1, z1, X.y, Y.y, Z.y), md[c * 4 + 1]);
+            md[c * 4 + 2] = fminf(sqdist3(x1, y1, z1, X.z, Y.z, Z.z), md[c * 4 + 2]);
+            md[c * 4 + 3] = fminf(sqdist3(x1, y1, z1, X.w, Y.w, Z.w), md[c * 4 + 3]);
+        }
+        float t[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) t[p] = md[p];
+#pragma unroll
+        for (int w = 1; w < P; w <<= 1) {
+#pragma unroll
+            for (int p = 0; p + w < P; p += 2 * w) t[p] = fmaxf(t[p], t[p + w]);
+        }
+        lmax = t[0];
+        u = (lmax > -1.f) ? f32_ordered(lmax) : 0u;  // the reference starts from best = -1
+        uint32_t eq = 0u;
+#pragma unroll
+        for (int p = 0; p < P; ++p) eq |= (md[p] == lmax) ? (1u << p) : 0u;
+        const int bp = __ffs(eq) - 1;  // lowest slot among equals = smallest reference rank inside the lane
+        lpos = base + (bp >> 2) * 128 + (bp & 3);
+        wu = __reduce_max_sync(FULL, u);
+        const unsigned tie = __ballot_sync(FULL, u == wu);
+        wpos = __shfl_sync(FULL, (uint32_t)lpos, __ffs(tie) - 1);
+        if (wu != 0u && (tie & (tie - 1u)) != 0u) {  // shared maximum inside the warp: the reference rank decides
+            const uint32_t rk = (u == wu) ? fbc_rank(sk[lpos], L) : 0xffffffffu;
+            const uint32_t wrk = __reduce_min_sync(FULL, rk);
+            wpos = (uint32_t)__shfl_sync(FULL, lpos, __ffs(__ballot_sync(FULL, rk == wrk)) - 1);
+        }
+    };
+
+    // peers' record slots / barriers (lanes < csize of warp 0 send)
+    const uint32_t peer = (uint32_t)lane < csize ? (uint32_t)lane : 0u;
+    const uint32_t dst_rec0 = mapa_u32(smem_u32(&xrec[crank]), peer);
+    const uint32_t dst_rec1 = mapa_u32(smem_u32(&xrec[FBC_MAXC + crank]), peer);
+    const uint32_t dst_bar0 = mapa_u32(smem_u32(&mbar[0]), peer);
+    const uint32_t dst_bar1 = mapa_u32(smem_u32(&mbar[1]), peer);
+    cluster_sync_all();  // peers' mbarriers are initialised past this point
+
+    float x1 = first_xyz[0], y1 = first_xyz[1], z1 = first_xyz[2];
+    float4 b4 = sbox4[tid >> 4];
+    float2 b2 = sbox2[tid >> 4];
+    int it = 0;
+    for (int j = 1; j < m; ++j, ++it) {
+        const int par = it & 1;
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&mbar[par]), csize * kXRecBytes);
+        uint2* const rec = recs + par * 32;
+        warp_step(x1, y1, z1, b4, b2, j == 1);
+        if (lane == 0) rec[warp] = make_uint2(wu, wpos);
+        __syncthreads();
+        const uint2 r = rec[lane];
+        b4 = sbox4[tid >> 4];
+        b2 = sbox2[tid >> 4];
+        // ---- this CTA's candidate
+        const uint32_t lu = __reduce_max_sync(FULL, r.x);
+        const unsigned gt = __ballot_sync(FULL, r.x == lu);
+        uint32_t cpos = __shfl_sync(FULL, r.y, __ffs(gt) - 1);
+        if (lu != 0u && (gt & (gt - 1u)) != 0u) {
+            const uint32_t rk = (r.x == lu) ? fbc_rank(sk[r.y], L) : 0xffffffffu;
+            const uint32_t grk = __reduce_min_sync(FULL, rk);
+            cpos = __shfl_sync(FULL, r.y, __ffs(__ballot_sync(FULL, rk == grk)) - 1);
+        }
+        // ---- exchange: warp 0 posts (key, original index, coordinates) to every CTA of the cluster
+        if (warp == 0 && (uint32_t)lane < csize) {
+            const uint32_t kk = lu != 0u ? (uint32_t)sk[cpos] : 0u;
+            const uint32_t dr = par ? dst_rec1 : dst_rec0, db = par ? dst_bar1 : dst_bar0;
+            st_async_v4(dr, db, lu, kk, __float_as_uint(sx[cpos]), __float_as_uint(sy[cpos]));
+            st_async_b32(dr + 16, db, __float_as_uint(sz[cpos]));
+        }
+        {
+            const uint32_t bar = smem_u32(&mbar[par]), ph = (uint32_t)((it >> 1) & 1);
+            if (!mbar_try_wait_cluster(bar, ph)) {
+                const long long t0 = clock64();
+                while (!mbar_try_wait_cluster(bar, ph))
+                    if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+            }
+        }
+        uint32_t cu = 0u, ck = 0xffffffffu;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        if ((uint32_t)lane < csize) {
+            const XRec* xr = xrec + par * FBC_MAXC + lane;
+            const uint4 v = *reinterpret_cast<const uint4*>(xr);
+            cu = v.x;
+            ck = v.y;
+            cx = __uint_as_float(v.z);
+            cy = __uint_as_float(v.w);
+            cz = xr->z;
+        }
+        const uint32_t gu = __reduce_max_sync(FULL, cu);
+        const unsigned ct = __ballot_sync(FULL, cu == gu && (uint32_t)lane < csize);
+        int gl = __ffs(ct) - 1;
+        if (gu != 0u && (ct & (ct - 1u)) != 0u) {
+            const uint32_t rk = ((ct >> lane) & 1u) ? fbc_rank(ck, L) : 0xffffffffu;
+            const uint32_t grk = __reduce_min_sync(FULL, rk);
+            gl = __ffs(__ballot_sync(FULL, rk == grk)) - 1;
+        }
+        if (gu != 0u) {
+            x1 = __shfl_sync(FULL, cx, gl);
+            y1 = __shfl_sync(FULL, cy, gl);
+            z1 = __shfl_sync(FULL, cz, gl);
+        } else {  // no eligible candidate anywhere: the reference yields index 0
+            x1 = first_xyz[0];
+            y1 = first_xyz[1];
+            z1 = first_xyz[2];
+        }
+        const uint32_t gk = __shfl_sync(FULL, ck, gl);
+        if (crank == 0 && tid == 0) idxs[j] = gu != 0u ? (int)gk : 0;
+    }
+    if (a.temp) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            if (first + p < nloc) a.temp[(size_t)cloud * n + sk[base + (p >> 2) * 128 + (p & 3)]] = md[p];
+    }
+    cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
+}
+
+}  // namespace tsm
+
+bool tsm_fps_bucket_cluster_supports(int n, bool weighted) { return !weighted && n > 16384 && n <= 65536; }
+
+int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
+    using namespace tsm;
+    const int n = a.n;
+    if (!tsm_fps_bucket_cluster_supports(n, a.weights != nullptr)) return TSM_ERR_INVALID;
+    // slices of at most ~15000 points (whole 512-point warps), so every CTA keeps a little slack
+    int csize = (n + 14999) / 15000;
+    if (csize < 2) csize = 2;
+    int per_cta = ((n + csize - 1) / csize + 511) / 512 * 512;
+    if (per_cta > FBC_CAP || csize > FBC_MAXC) return TSM_ERR_INVALID;
+    void* scratch = nullptr;
+    int rc = tsm_scratch_get(6, (size_t)b * n * sizeof(float4), stream, &scratch);
+    if (rc != TSM_OK) return rc;
+    float4* sorted = static_cast<float4*>(scratch);
+    const size_t sort_dyn = (size_t)(1 << FBC_CELL_BITS) * sizeof(uint32_t);
+    TSM_CUDA_TRY(cudaFuncSetAttribute(fps_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_dyn));
+    fps_sort_kernel<<<b, 1024, sort_dyn, stream>>>(n, a.xyz, sorted);
+    TSM_LAUNCH_CHECK();
+    TSM_CUDA_TRY(cudaFuncSetAttribute(fps_bucket_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FBC_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(b * csize));
+    cfg.blockDim = dim3(FBC_T);
+    cfg.dynamicSmemBytes = FBC_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fps_bucket_cluster_kernel, a, (const float4*)sorted, per_cta));
+    return TSM_OK;
+}
