@@ -161,6 +161,34 @@ def _fps_temp_scratch_contract(orc):
     assert np.array_equal(temp.cpu().numpy().view(np.uint32), want_temp.view(np.uint32))
 
 
+@pytest.mark.parametrize("name,gen,n,m", [
+    ("dup20000", synth.cloud_dup_padded, 20000, 700),          # 2 CTAs, many shared maxima across lanes / warps / CTAs
+    ("lattice40000", synth.cloud_lattice, 40000, 500),         # 3 CTAs, equal distances between distinct points
+    ("objects65536", synth.cloud_ground_objects, 65536, 900),  # 5 CTAs, largest u16-index cloud
+    ("dup70001", synth.cloud_dup_padded, 70001, 600),          # 5 CTAs, indices above 65535 (slice-position mode)
+    ("lattice163840", synth.cloud_lattice, 163840, 400),       # 11 CTAs (non-portable cluster size), Waymo test size
+], ids=["dup20000", "lattice40000", "objects65536", "dup70001", "lattice163840"])
+def test_fps_bucket_cluster_equals_cluster_kernel(name, gen, n, m, monkeypatch):
+    """The pruned sampler over a CTA cluster (fps_bucket_cluster.cu, the default for 16385..240000 points) returns
+    exactly what the brute-force cluster kernel returns, including the final min-distances handed back in temp."""
+    from tsmdet_b200 import pointnet2_batch_cuda as ext
+
+    xyz = torch.from_numpy(gen(2, n, 90)).to(_dev())
+    outs = []
+    for algo in ("cluster", None):
+        if algo:
+            monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+        else:
+            monkeypatch.delenv("TSMDET_FPS_ALGO", raising=False)
+        temp = torch.full((2, n), 1e10, device=_dev())
+        idx = torch.zeros((2, m), dtype=torch.int32, device=_dev())
+        ext.farthest_point_sampling_wrapper(2, n, m, xyz, temp, idx)
+        torch.cuda.synchronize()
+        outs.append((idx, temp))
+    assert torch.equal(outs[0][0], outs[1][0]), name
+    assert torch.equal(outs[0][1].view(torch.int32), outs[1][1].view(torch.int32)), name
+
+
 def test_fps_weights(orc):
     from tsmdet_b200 import pointnet2_utils as pu
 

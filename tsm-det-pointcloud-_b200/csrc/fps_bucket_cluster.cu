@@ -1,5 +1,5 @@
 // fps_bucket_cluster.cu -- the spatially pruned sampler of fps_bucket.cu for clouds that need several SMs
-// (16384 < N <= 65536): one thread-block CLUSTER per cloud, every CTA holding a contiguous slice of the
+// (16384 < N <= 240000): one thread-block CLUSTER per cloud, every CTA holding a contiguous slice of the
 // Morton-sorted cloud in shared memory.
 //
 // Same indices, bit for bit, as farthest_point_sampling_kernel
@@ -26,13 +26,19 @@ constexpr int FBC_CAP = FBC_T * FBC_P;  // points per CTA
 constexpr int FBC_CELL_BITS = 15;
 constexpr uint32_t kXRecBytes = 20;  // key, index, x, y (v4) + z (b32)
 
-struct __align__(16) XRec {
+struct __align__(8) XRec {  // 24-byte slots: 16 peers x 2 parities have to fit next to 224 KB of points
     uint32_t u, k;
     float x, y;
     float z;
-    uint32_t pad[3];
+    uint32_t pad;
 };
-static_assert(sizeof(XRec) == 32, "XRec must be 32 bytes");
+static_assert(sizeof(XRec) == 24, "XRec must be 24 bytes");
+
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+                 "r"(a), "r"(b), "r"(rbar)
+                 : "memory");
+}
 
 __device__ __forceinline__ uint32_t fbc_rank(uint32_t k, int L) {
     return (L == 0) ? k : (__brev(k & ((1u << L) - 1u)) | (k >> L));
@@ -162,10 +168,13 @@ __global__ void __launch_bounds__(1024, 1)
 
 // ------------------------------------------------------------------------------------------------------------
 // dynamic smem: planes 12*CAP | original index u16 2*CAP | group boxes 24*(T/16) | recs [2][32] uint2 |
-//               exchange records [2][8] XRec | first point (16 B)
-constexpr int FBC_MAXC = 8;
-constexpr int FBC_SMEM = 14 * FBC_CAP + 24 * (FBC_T / 16) + 512 + 2 * FBC_MAXC * 32 + 16;
+//               exchange records [2][16] XRec (24 B) | first point (16 B)
+constexpr int FBC_MAXC = 16;
+constexpr int FBC_SMEM = 14 * FBC_CAP + 24 * (FBC_T / 16) + 512 + 2 * FBC_MAXC * 24 + 16;
 
+// BIG (N > 65536): the u16 next to every point is its position in the CTA's slice; the original index is read from
+// the sorted array when it is needed (lane ordering and temp in the prologue, shared maxima, the final translation).
+template <bool BIG>
 __global__ void __launch_bounds__(FBC_T, 1)
     fps_bucket_cluster_kernel(const FpsArgs a, const float4* __restrict__ sorted_all, int per_cta) {
     constexpr int T = FBC_T, P = FBC_P, CAP = FBC_CAP, C4 = P / 4, NW = T / 32;
@@ -191,6 +200,10 @@ __global__ void __launch_bounds__(FBC_T, 1)
     int* __restrict__ idxs = a.idxs + (size_t)cloud * m;
     const int lo = min((int)crank * per_cta, n);
     const int nloc = min(per_cta, n - lo);  // this CTA's slice of the sorted cloud: [lo, lo + nloc)
+    auto orig = [&](int e) -> uint32_t {  // original index of the point at shared-memory element e
+        const uint32_t v = sk[e];
+        return BIG ? (uint32_t)__float_as_int(sorted[lo + (int)v].w) : v;
+    };
 
     if (tid == 0) {
         mbar_init(smem_u32(&mbar[0]), 1);
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(FBC_T, 1)
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < nloc) v = sorted[lo + s];
         sx[e] = v.x; sy[e] = v.y; sz[e] = v.z;
-        sk[e] = s < nloc ? (uint16_t)__float_as_int(v.w) : (uint16_t)0;
+        sk[e] = s < nloc ? (BIG ? (uint16_t)s : (uint16_t)__float_as_int(v.w)) : (uint16_t)0;
     }
     __syncthreads();
 
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(FBC_T, 1)
         uint32_t rk[P];
 #pragma unroll
         for (int p = 0; p < P; ++p)
-            rk[p] = (first + p < nloc) ? fbc_rank(sk[base + (p >> 2) * 128 + (p & 3)], L) : (0xffffffe0u + (uint32_t)p);
+            rk[p] = (first + p < nloc) ? fbc_rank(orig(base + (p >> 2) * 128 + (p & 3)), L) : (0xffffffe0u + (uint32_t)p);
         int dst[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(FBC_T, 1)
                     bx0 = fminf(bx0, xs[e]); bx1 = fmaxf(bx1, xs[e]);
                     by0 = fminf(by0, ys[e]); by1 = fmaxf(by1, ys[e]);
                     bz0 = fminf(bz0, zs[e]); bz1 = fmaxf(bz1, zs[e]);
-                    d0 = a.temp ? a.temp[(size_t)cloud * n + sk[base + c * 128 + e]] : 1e10f;
+                    d0 = a.temp ? a.temp[(size_t)cloud * n + orig(base + c * 128 + e)] : 1e10f;
                 }
                 md[p] = d0;
             }
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(FBC_T, 1)
         const unsigned tie = __ballot_sync(FULL, u == wu);
         wpos = __shfl_sync(FULL, (uint32_t)lpos, __ffs(tie) - 1);
         if (wu != 0u && (tie & (tie - 1u)) != 0u) {  // shared maximum inside the warp: the reference rank decides
-            const uint32_t rk = (u == wu) ? fbc_rank(sk[lpos], L) : 0xffffffffu;
+            const uint32_t rk = (u == wu) ? fbc_rank(orig(lpos), L) : 0xffffffffu;
             const uint32_t wrk = __reduce_min_sync(FULL, rk);
             wpos = (uint32_t)__shfl_sync(FULL, lpos, __ffs(__ballot_sync(FULL, rk == wrk)) - 1);
         }
@@ -329,6 +342,8 @@ __global__ void __launch_bounds__(FBC_T, 1)
     const uint32_t peer = (uint32_t)lane < csize ? (uint32_t)lane : 0u;
     const uint32_t dst_rec0 = mapa_u32(smem_u32(&xrec[crank]), peer);
     const uint32_t dst_rec1 = mapa_u32(smem_u32(&xrec[FBC_MAXC + crank]), peer);
+    if (BIG && crank == 0)  // picks are written as (CTA << 16 | slice position) and translated after the loop
+        for (int j = 1 + tid; j < m; j += T) idxs[j] = -1;
     const uint32_t dst_bar0 = mapa_u32(smem_u32(&mbar[0]), peer);
     const uint32_t dst_bar1 = mapa_u32(smem_u32(&mbar[1]), peer);
     cluster_sync_all();  // peers' mbarriers are initialised past this point
@@ -352,15 +367,16 @@ __global__ void __launch_bounds__(FBC_T, 1)
         const unsigned gt = __ballot_sync(FULL, r.x == lu);
         uint32_t cpos = __shfl_sync(FULL, r.y, __ffs(gt) - 1);
         if (lu != 0u && (gt & (gt - 1u)) != 0u) {
-            const uint32_t rk = (r.x == lu) ? fbc_rank(sk[r.y], L) : 0xffffffffu;
+            const uint32_t rk = (r.x == lu) ? fbc_rank(orig((int)r.y), L) : 0xffffffffu;
             const uint32_t grk = __reduce_min_sync(FULL, rk);
             cpos = __shfl_sync(FULL, r.y, __ffs(__ballot_sync(FULL, rk == grk)) - 1);
         }
         // ---- exchange: warp 0 posts (key, original index, coordinates) to every CTA of the cluster
         if (warp == 0 && (uint32_t)lane < csize) {
-            const uint32_t kk = lu != 0u ? (uint32_t)sk[cpos] : 0u;
+            const uint32_t kk = lu != 0u ? (BIG ? ((crank << 16) | (uint32_t)sk[cpos]) : (uint32_t)sk[cpos]) : 0u;
             const uint32_t dr = par ? dst_rec1 : dst_rec0, db = par ? dst_bar1 : dst_bar0;
-            st_async_v4(dr, db, lu, kk, __float_as_uint(sx[cpos]), __float_as_uint(sy[cpos]));
+            st_async_v2(dr, db, lu, kk);
+            st_async_v2(dr + 8, db, __float_as_uint(sx[cpos]), __float_as_uint(sy[cpos]));
             st_async_b32(dr + 16, db, __float_as_uint(sz[cpos]));
         }
         {
@@ -375,18 +391,23 @@ __global__ void __launch_bounds__(FBC_T, 1)
         float cx = 0.f, cy = 0.f, cz = 0.f;
         if ((uint32_t)lane < csize) {
             const XRec* xr = xrec + par * FBC_MAXC + lane;
-            const uint4 v = *reinterpret_cast<const uint4*>(xr);
-            cu = v.x;
-            ck = v.y;
-            cx = __uint_as_float(v.z);
-            cy = __uint_as_float(v.w);
+            const uint2 v0 = *reinterpret_cast<const uint2*>(xr);
+            const float2 v1 = *reinterpret_cast<const float2*>(&xr->x);
+            cu = v0.x;
+            ck = v0.y;
+            cx = v1.x;
+            cy = v1.y;
             cz = xr->z;
         }
         const uint32_t gu = __reduce_max_sync(FULL, cu);
         const unsigned ct = __ballot_sync(FULL, cu == gu && (uint32_t)lane < csize);
         int gl = __ffs(ct) - 1;
         if (gu != 0u && (ct & (ct - 1u)) != 0u) {
-            const uint32_t rk = ((ct >> lane) & 1u) ? fbc_rank(ck, L) : 0xffffffffu;
+            uint32_t rk = 0xffffffffu;
+            if ((ct >> lane) & 1u) {
+                const uint32_t kt = BIG ? (uint32_t)__float_as_int(sorted[(int)(ck >> 16) * per_cta + (int)(ck & 0xffffu)].w) : ck;
+                rk = fbc_rank(kt, L);
+            }
             const uint32_t grk = __reduce_min_sync(FULL, rk);
             gl = __ffs(__ballot_sync(FULL, rk == grk)) - 1;
         }
@@ -400,19 +421,26 @@ __global__ void __launch_bounds__(FBC_T, 1)
             z1 = first_xyz[2];
         }
         const uint32_t gk = __shfl_sync(FULL, ck, gl);
-        if (crank == 0 && tid == 0) idxs[j] = gu != 0u ? (int)gk : 0;
+        if (crank == 0 && tid == 0) idxs[j] = gu != 0u ? (int)gk : (BIG ? -1 : 0);
+    }
+    if (BIG && crank == 0) {
+        __syncthreads();  // this CTA wrote every idxs[j]
+        for (int j = 1 + tid; j < m; j += T) {
+            const int code = idxs[j];
+            idxs[j] = code >= 0 ? __float_as_int(sorted[(code >> 16) * per_cta + (code & 0xffff)].w) : 0;
+        }
     }
     if (a.temp) {
 #pragma unroll
         for (int p = 0; p < P; ++p)
-            if (first + p < nloc) a.temp[(size_t)cloud * n + sk[base + (p >> 2) * 128 + (p & 3)]] = md[p];
+            if (first + p < nloc) a.temp[(size_t)cloud * n + orig(base + (p >> 2) * 128 + (p & 3))] = md[p];
     }
     cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
 }
 
 }  // namespace tsm
 
-bool tsm_fps_bucket_cluster_supports(int n, bool weighted) { return !weighted && n > 16384 && n <= 65536; }
+bool tsm_fps_bucket_cluster_supports(int n, bool weighted) { return !weighted && n > 16384 && n <= 240000; }
 
 int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
     using namespace tsm;
@@ -431,7 +459,10 @@ int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t str
     TSM_CUDA_TRY(cudaFuncSetAttribute(fps_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_dyn));
     fps_sort_kernel<<<b, 1024, sort_dyn, stream>>>(n, a.xyz, sorted);
     TSM_LAUNCH_CHECK();
-    TSM_CUDA_TRY(cudaFuncSetAttribute(fps_bucket_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FBC_SMEM));
+    const bool big = n > 65536;
+    auto kern = big ? fps_bucket_cluster_kernel<true> : fps_bucket_cluster_kernel<false>;
+    TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FBC_SMEM));
+    if (csize > 8) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * csize));
     cfg.blockDim = dim3(FBC_T);
@@ -444,6 +475,6 @@ int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t str
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, fps_bucket_cluster_kernel, a, (const float4*)sorted, per_cta));
+    TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, (const float4*)sorted, per_cta));
     return TSM_OK;
 }
