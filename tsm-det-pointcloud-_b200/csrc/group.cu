@@ -216,13 +216,17 @@ static bool launch_group_staged(int b, int c, int n, long e, const float* points
     *rc = TSM_OK;
     if ((n & 3) || (e & 3) || !aligned16(points) || !aligned16(idx) || !aligned16(out) || e < 4096 || b > 65535) return false;
     if ((size_t)n * 4 > 96 * 1024) return false;  // a row must leave room for two CTAs per SM
+    size_t slab_cap = 32 * 1024;  // measured: 16..32 KB slabs (5-6 CTAs per SM) beat larger ones
+    if (const char* e = getenv("TSMDET_GROUP_SLAB_KB")) slab_cap = (size_t)atoi(e) * 1024;
     int cc = 1;
-    while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= 72 * 1024) cc *= 2;
+    while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= slab_cap) cc *= 2;
     const int cchunks = divup(c, cc);
     if (cchunks > 65535) return false;
     const size_t dyn = (size_t)cc * n * 4;
     const int resident = (int)((227 * 1024) / (dyn + 1024));
-    long want = (long)tsm_num_sms() * (resident > 8 ? 8 : resident) * 2;  // about two waves
+    int waves = 4;
+    if (const char* e = getenv("TSMDET_GROUP_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 4;
+    long want = (long)tsm_num_sms() * (resident > 8 ? 8 : resident) * waves;  // about two waves
     long echunks = divup((int)want, b * cchunks);
     const long emax = e / 2048 > 0 ? e / 2048 : 1;
     if (echunks > emax) echunks = emax;
