@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(256)
         uint32_t v[K + 1];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
+            v[k] = NONE;
+            if (base + k * 32 >= total) continue;  // (uniform) no candidates left for this slot: skip the search
             const int j = base + k * 32 + lane;
             // owner cell = first lane whose inclusive prefix exceeds j (binary search over the lanes)
             int t = 0;
@@ -315,7 +317,6 @@ __global__ void __launch_bounds__(256)
                 if (val <= j) t += step;
             }
             const int src = __shfl_sync(FULL, excl_beg, t & 31) + j;
-            v[k] = NONE;
             if (j < total) {
                 const float4 p = sorted[src];
                 const float d2 = sqdist3(p.x, p.y, p.z, cx, cy, cz);
