@@ -66,3 +66,42 @@ def test_gather_detections_world2():
         assert int(allc[f]) == k
         assert torch.equal(allp[f, :k, :7], bx[:k])
         assert float(allp[f, k:].abs().sum()) == 0.0
+
+
+def _worker_packed(rank, world, port, frames, k_post, q):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tsmdet_b200.sharding import gather_packed, pack_detections
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        rec = torch.rand((frames, k_post, 9), generator=g) + rank
+        cnt = torch.randint(0, k_post + 1, (frames,), generator=g, dtype=torch.int32)
+        out = None
+        for _ in range(2):  # second call reuses the receive buffer
+            all_det, all_num, out = gather_packed(pack_detections(rec, cnt), frames, k_post, out=out)
+        q.put((rank, rec.numpy().copy(), cnt.numpy().copy(), all_det.numpy().copy(), all_num.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_packed_world2():
+    """The pipeline's collective (equal shards, one all_gather of the packed records + counts)."""
+    frames, k_post, world = 3, 5, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_packed, args=(r, world, port, frames, k_post, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda t: t[0])
+    for r in res:
+        assert r[3].shape == (world, frames, k_post, 9) and r[4].shape == (world, frames)
+        for src in res:
+            assert (r[3][src[0]] == src[1]).all() and (r[4][src[0]] == src[2]).all()

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib, iou3d_nms_utils, pointnet2_utils
 from .pointnet2_modules import gather_xyz, kitti_sa_stack, sa_mlp_maxpool
-from .sharding import gather_detections
+from .sharding import gather_detections, gather_packed, pack_detections
 
 
 class SABackboneNMS(torch.nn.Module):
@@ -143,7 +143,8 @@ class SABackboneNMS(torch.nn.Module):
             rec = rec * live.unsqueeze(-1)
         main.wait_stream(s_sa)
         main.wait_stream(s_nms)
-        res = {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num, "det": rec}
+        res = {"xyz": cur_xyz, "features": cur_f, "det_idx": det_idx, "det_num": det_num, "det": rec,
+               "det_packed": pack_detections(rec, det_num)}  # the collective's send buffer, built inside the graph
         if self.gather_group is not None:
             # the one collective of the path: every rank receives every rank's records (equal shards, so the
             # sizes are known without a size exchange or a host sync)
@@ -209,10 +210,15 @@ class SABackboneNMS(torch.nn.Module):
             boxes, scores = ent["in"][2], ent["in"][3]
         else:
             res = self._run(xyz, feats, boxes, scores)
-        if gather and "all_det" not in res:  # engines without their own group: eager collective after the step
-            world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-            res["all_det"], res["all_num"] = gather_detections(res["det"], res["det_num"],
-                                                               frames_total=res["det"].shape[0] * world)
+        if gather and "all_det" not in res:
+            # the one collective of the path, issued after the replay: equal shards, so a single all_gather of the
+            # packed buffer the graph produced -- no size exchange, no host sync, no other kernels
+            if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+                f, k = res["det"].shape[0], res["det"].shape[1]
+                res["all_det"], res["all_num"], self._gather_out = gather_packed(
+                    res["det_packed"], f, k, out=getattr(self, "_gather_out", None))
+            else:
+                res["all_det"], res["all_num"] = res["det"].unsqueeze(0), res["det_num"].unsqueeze(0)
         return res
 
     def static_inputs(self, xyz, feats, boxes, scores):

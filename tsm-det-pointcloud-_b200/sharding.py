@@ -76,3 +76,24 @@ def gather_detections(padded: torch.Tensor, counts: torch.Tensor, frames_total: 
         recs.append(out[r, : sizes[r] * k * 9].view(sizes[r], k, 9))
         cnts.append(out[r, fmax * k * 9: fmax * k * 9 + sizes[r]].contiguous().view(torch.int32))
     return torch.cat(recs, 0), torch.cat(cnts, 0)
+
+
+def pack_detections(padded: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """(F,K,9) records + (F,) int32 counts -> one flat float32 buffer (records, then the counts' bit patterns): the
+    send buffer of ``gather_packed``.  Pure tensor ops, so it can live inside a captured CUDA graph."""
+    return torch.cat([padded.reshape(-1), counts.to(torch.int32).view(torch.float32)])
+
+
+def gather_packed(packed: torch.Tensor, frames: int, k: int, out: Optional[torch.Tensor] = None, group=None):
+    """Equal shards (every rank owns ``frames`` frames): ONE collective and no other device or host work --
+    returns ``(all_det (world, frames, k, 9), all_num (world, frames) int32, out)`` as views of the receive buffer
+    ``out`` (pass it back in to reuse it)."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world, packed.numel()), dtype=torch.float32, device=packed.device)
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(out, packed, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), packed, group=group)
+    n = frames * k * 9
+    return out[:, :n].view(world, frames, k, 9), out[:, n:].view(torch.int32), out
