@@ -50,7 +50,7 @@ def make_inputs(frames: int, seed: int):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML thread (about 1 kHz;
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML thread (about 250 Hz;
     only the samples whose timestamps fall inside [start(), stop()] are kept), nvidia-smi -lms as the fallback."""
 
     REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
@@ -80,7 +80,7 @@ class ClockSampler:
                                   int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
             except Exception:
                 break
-            time.sleep(0.001)
+            time.sleep(0.004)  # ~250 Hz: NVML calls hold the GIL, the timed loop needs it
 
     def start(self):
         self.t0 = time.perf_counter()
