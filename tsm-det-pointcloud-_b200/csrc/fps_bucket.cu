@@ -25,6 +25,37 @@
 #include "fps.cuh"
 
 namespace tsm {
+#ifndef FPSB_U1
+#define FPSB_U1 4
+#endif
+constexpr int kU1 = FPSB_U1;
+#ifndef FPSB_UPD
+#define FPSB_UPD 2
+#endif
+
+// -DFPSB_PROF: thread 0 of cloud 0 accumulates clock() per phase of a multi-pick round and prints the totals
+#ifdef FPSB_PROF
+#define PROF_T(v) const long long v = clock64()
+#define PROF_TD(v, dep) const long long v = clock_after((uint32_t)(dep))
+__device__ __forceinline__ long long clock_after(uint32_t dep) {  // a clock read that waits for `dep`
+    long long t;
+    asm volatile("{\n\t.reg .b32 z;\n\tand.b32 z, %1, 0;\n\tcvt.u64.u32 %0, z;\n\t.reg .b64 c;\n\tmov.u64 c, %%clock64;\n\tadd.u64 %0, %0, c;\n\t}" : "=l"(t) : "r"(dep) : "memory");
+    return t;
+}
+#define PROF_ACC(t0, t1, t2, t3)                                                 \
+    if (tid == 0) {                                                              \
+        prof_apply += t1 - t0; prof_wait += t2 - t1; prof_lead += t3 - t2; ++prof_rounds; \
+    }
+#define PROF_ACC2(t0, t1, t2, t3, t4, t5)                                        \
+    if (tid == 0) {                                                              \
+        prof_q[0] += t1 - t0; prof_q[1] += t2 - t1; prof_q[2] += t3 - t2; prof_q[3] += t4 - t3; prof_q[4] += t5 - t4; \
+    }
+#else
+#define PROF_T(v)
+#define PROF_TD(v, dep)
+#define PROF_ACC(t0, t1, t2, t3)
+#define PROF_ACC2(t0, t1, t2, t3, t4, t5)
+#endif
 
 constexpr int kBucketMaxN = 16384;
 constexpr int kMiscBytes = 512 + 768 + 128 + 16;  // candidate records, box partials, scan offsets, point 0
@@ -47,7 +78,7 @@ __device__ __forceinline__ uint32_t ref_rank(uint32_t k, int L) {
     return (L == 0) ? k : (__brev(k & ((1u << L) - 1u)) | (k >> L));
 }
 
-template <int T, int P>
+template <int T, int P, int K>
 __global__ void __launch_bounds__(T, 1)
     fps_bucket_kernel(const FpsArgs a, const int cell_bits) {
     constexpr int NW = T / 32;
@@ -307,40 +338,47 @@ __global__ void __launch_bounds__(T, 1)
     }
     __syncthreads();
 
-    // lane state: (lmax, u, lpos) = this lane's largest min-distance and where it is; warp state (wu, wpos)
+    // lane state: (lmax, u, lpos) = this lane's largest min-distance and where it is; warp state (wu, wpos) = the
+    // warp's candidate, wu2 = an upper bound (as a key) of every OTHER point of the warp
     float lmax = -2.f;
-    uint32_t u = 0u, wu = 0u, wpos = (uint32_t)base;
+    uint32_t u = 0u, wu = 0u, wpos = (uint32_t)base, wu2 = 0u;
     int lpos = base;
 
-    // One pick's worth of work for a warp whose box the pick may reach: lane-level test, the P updates, the
-    // lane / warp argmax.  Leaves (wu, wpos) = the warp's candidate; bit 31 of wpos = "another point of this
-    // warp with different coordinates shares wu" (chain bookkeeping).
-    auto warp_step = [&](float x1, float y1, float z1, const float4 b4, const float2 b2, bool force) {
-        // lower bound of the computed squared distance over the lane's box, with the point formula's own
-        // rounded operations
+    // lower bound of the computed squared distance from a pick to the lane's box, with the point formula's own
+    // rounded operations
+    auto box_bound = [&](float x1, float y1, float z1, const float4 b4, const float2 b2) -> float {
         const float dx = fmaxf(fmaxf(__fsub_rn(b4.x, x1), __fsub_rn(x1, b4.y)), 0.f);
         const float dy = fmaxf(fmaxf(__fsub_rn(b4.z, y1), __fsub_rn(y1, b4.w)), 0.f);
         const float dz = fmaxf(fmaxf(__fsub_rn(b2.x, z1), __fsub_rn(z1, b2.y)), 0.f);
-        const float lb = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-        const bool hit = !(lb >= lmax) || force;  // NaN bounds count as hits
-        if (!__any_sync(FULL, hit)) return;
+        return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    };
+    auto update = [&](float x1, float y1, float z1) {
 #pragma unroll
-        for (int c = 0; c < C4; ++c) {
-            const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
-            const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
-            const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
-            md[c * 4 + 0] = fminf(sqdist3(x1, y1, z1, X.x, Y.x, Z.x), md[c * 4 + 0]);
-            md[c * 4 + 1] = fminf(sqdist3(x1, y1, z1, X.y, Y.y, Z.y), md[c * 4 + 1]);
-            md[c * 4 + 2] = fminf(sqdist3(x1, y1, z1, X.z, Y.z, Z.z), md[c * 4 + 2]);
-            md[c * 4 + 3] = fminf(sqdist3(x1, y1, z1, X.w, Y.w, Z.w), md[c * 4 + 3]);
+        for (int q = 0; q < C4; ++q) {
+            const float4 X = *reinterpret_cast<const float4*>(sx + base + q * 128);
+            const float4 Y = *reinterpret_cast<const float4*>(sy + base + q * 128);
+            const float4 Z = *reinterpret_cast<const float4*>(sz + base + q * 128);
+            md[q * 4 + 0] = fminf(sqdist3(x1, y1, z1, X.x, Y.x, Z.x), md[q * 4 + 0]);
+            md[q * 4 + 1] = fminf(sqdist3(x1, y1, z1, X.y, Y.y, Z.y), md[q * 4 + 1]);
+            md[q * 4 + 2] = fminf(sqdist3(x1, y1, z1, X.z, Y.z, Z.z), md[q * 4 + 2]);
+            md[q * 4 + 3] = fminf(sqdist3(x1, y1, z1, X.w, Y.w, Z.w), md[q * 4 + 3]);
         }
-        float t[P];
+    };
+    // The lane / warp argmax after an update.  Leaves (wu, wpos, wu2); bit 31 of wpos = "another point of this warp
+    // with different coordinates shares wu" (chain bookkeeping).
+    auto warp_argmax = [&]() {
+        // balanced max tree over the P slots; for K > 1 it also carries the runner-up (which equals the maximum when
+        // the maximum is held twice: min(a, b) of two equal maxima)
+        float t[P], t2[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) t[p] = md[p];
+        for (int p = 0; p < P; ++p) { t[p] = md[p]; t2[p] = -2.f; }
 #pragma unroll
         for (int w = 1; w < P; w <<= 1) {
 #pragma unroll
-            for (int p = 0; p + w < P; p += 2 * w) t[p] = fmaxf(t[p], t[p + w]);
+            for (int p = 0; p + w < P; p += 2 * w) {
+                if (K > 1) t2[p] = fmaxf(fminf(t[p], t[p + w]), fmaxf(t2[p], t2[p + w]));
+                t[p] = fmaxf(t[p], t[p + w]);
+            }
         }
         lmax = t[0];
         u = (lmax > -1.f) ? f32_ordered(lmax) : 0u;  // the reference starts from best = -1
@@ -357,6 +395,12 @@ __global__ void __launch_bounds__(T, 1)
         wpos = __shfl_sync(FULL, (uint32_t)lpos | (several ? 0x80000000u : 0u), __ffs(tie) - 1);
         const bool lane_tie = (wpos >> 31) != 0u;
         wpos &= 0x7fffffffu;
+        if (K > 1) {
+            // the runner-up key: the largest in the warp once the candidate itself is set aside (a second lane or slot
+            // holding the maximum makes it equal to wu)
+            const uint32_t u2 = (t2[0] > -1.f) ? f32_ordered(t2[0]) : 0u;
+            wu2 = __reduce_max_sync(FULL, (lane == __ffs(tie) - 1) ? u2 : u);
+        }
         if (wu != 0u && ((tie & (tie - 1u)) != 0u || (chain && lane_tie))) {
             // shared maximum inside the warp: the reference rank decides between lanes, and (chain bookkeeping)
             // bit 31 of the candidate says whether a point with DIFFERENT coordinates shares it
@@ -380,58 +424,281 @@ __global__ void __launch_bounds__(T, 1)
             }
         }
     };
-
-    // ================= one barrier per pick =================
-    // Every warp posts its (cached or refreshed) candidate, then reduces the NW records itself.
-    float x1 = first_xyz[0], y1 = first_xyz[1], z1 = first_xyz[2];
-    float4 b4 = sbox4[tid >> 4];
-    float2 b2 = sbox2[tid >> 4];
-    for (int j = 1; j < m; ++j) {
-        uint2* const rec = recs + (j & 1) * 32;  // double-buffered: a fast warp may already post pick j+1
-        warp_step(x1, y1, z1, b4, b2, j == 1);
-        if (lane == 0) rec[warp] = make_uint2(wu, wpos);
-        __syncthreads();
-        uint2 r = make_uint2(0u, 0u);
-        if (lane < NW) r = rec[lane];
-        // the group's box lives in shared memory (registers are short during the update); fetched here, in the
-        // shadow of the reduction, for the next pick's test
-        b4 = sbox4[tid >> 4];
-        b2 = sbox2[tid >> 4];
-        // ---- the pick: largest key, smallest reference rank among equals
-        const uint32_t gu = __reduce_max_sync(FULL, r.x);
-        const unsigned gt = __ballot_sync(FULL, r.x == gu);
-        uint32_t cpos = __shfl_sync(FULL, r.y, __ffs(gt) - 1);
-        bool other = (cpos >> 31) != 0u;  // chain bookkeeping: a different point shares the maximum
-        if (gu == 0u) {  // no eligible candidate anywhere: the reference yields index 0
-            x1 = first_xyz[0];
-            y1 = first_xyz[1];
-            z1 = first_xyz[2];
-            if (tid == 0) {
-                idxs[j] = -1;
-                if (a.vals) a.vals[(size_t)cloud * m + j] = 0.f;
-            }
-            continue;
-        }
+    // The pick among the posted records (held one per lane): largest key, smallest reference rank among equals.
+    // Returns the record lane; `other` = chain bookkeeping (a different point shares the maximum).
+    auto first_pick = [&](const uint2 r, const uint32_t gu, const unsigned gt, uint32_t& cpos, bool& other) -> int {
+        int gl = __ffs(gt) - 1;
+        cpos = __shfl_sync(FULL, r.y, gl);
+        other = (cpos >> 31) != 0u;
         if ((gt & (gt - 1u)) != 0u) {  // several warps share the maximum
             const uint32_t rk = (r.x == gu) ? ref_rank(sk[r.y & 0x7fffffffu], L) : 0xffffffffu;
             const uint32_t grk = __reduce_min_sync(FULL, rk);
-            cpos = __shfl_sync(FULL, r.y, __ffs(__ballot_sync(FULL, rk == grk)) - 1);
+            gl = __ffs(__ballot_sync(FULL, rk == grk)) - 1;
+            cpos = __shfl_sync(FULL, r.y, gl);
             if (chain) {
                 const int e = (int)(r.y & 0x7fffffffu), w = (int)(cpos & 0x7fffffffu);
                 other = __any_sync(FULL, r.x == gu && ((r.y >> 31) != 0u || sx[e] != sx[w] || sy[e] != sy[w] ||
                                                       sz[e] != sz[w]));
             }
         }
-        const int gpos = (int)(cpos & 0x7fffffffu);
-        x1 = sx[gpos];
-        y1 = sy[gpos];
-        z1 = sz[gpos];
-        if (tid == ((j & (NW - 1)) << 5)) {  // bookkeeping rotates over the warps
-            // the slot for now (fire-and-forget store); translated to the original index after the loop
-            idxs[j] = gpos;
-            if (a.vals) a.vals[(size_t)cloud * m + j] = __uint_as_float(gu & 0x7fffffffu);
-            if (chain && other) atomicMin(a.tie_iter + cloud, j);
+        return gl;
+    };
+
+    float4 b4 = sbox4[tid >> 4];
+    float2 b2 = sbox2[tid >> 4];
+    if constexpr (K == 1) {
+        // ================= one barrier per pick =================
+        // Every warp posts its (cached or refreshed) candidate, then reduces the NW records itself.
+        float x1 = first_xyz[0], y1 = first_xyz[1], z1 = first_xyz[2];
+        for (int j = 1; j < m; ++j) {
+            uint2* const rec = recs + (j & 1) * 32;  // double-buffered: a fast warp may already post pick j+1
+            const bool hit = !(box_bound(x1, y1, z1, b4, b2) >= lmax) || j == 1;  // NaN bounds count as hits
+            if (__any_sync(FULL, hit)) {
+                update(x1, y1, z1);
+                warp_argmax();
+            }
+            if (lane == 0) rec[warp] = make_uint2(wu, wpos);
+            __syncthreads();
+            uint2 r = make_uint2(0u, 0u);
+            if (lane < NW) r = rec[lane];
+            // the group's box lives in shared memory (registers are short during the update); fetched here, in the
+            // shadow of the reduction, for the next pick's test
+            b4 = sbox4[tid >> 4];
+            b2 = sbox2[tid >> 4];
+            const uint32_t gu = __reduce_max_sync(FULL, r.x);
+            const unsigned gt = __ballot_sync(FULL, r.x == gu);
+            if (gu == 0u) {  // no eligible candidate anywhere: the reference yields index 0
+                x1 = first_xyz[0];
+                y1 = first_xyz[1];
+                z1 = first_xyz[2];
+                if (tid == 0) {
+                    idxs[j] = -1;
+                    if (a.vals) a.vals[(size_t)cloud * m + j] = 0.f;
+                }
+                continue;
+            }
+            uint32_t cpos;
+            bool other;
+            first_pick(r, gu, gt, cpos, other);
+            const int gpos = (int)(cpos & 0x7fffffffu);
+            x1 = sx[gpos];
+            y1 = sy[gpos];
+            z1 = sz[gpos];
+            if (tid == ((j & (NW - 1)) << 5)) {  // bookkeeping rotates over the warps
+                // the slot for now (fire-and-forget store); translated to the original index after the loop
+                idxs[j] = gpos;
+                if (a.vals) a.vals[(size_t)cloud * m + j] = __uint_as_float(gu & 0x7fffffffu);
+                if (chain && other) atomicMin(a.tie_iter + cloud, j);
+            }
         }
+    } else {
+        // ================= rounds of up to K picks =================
+        // Warp-collectives (SHFL / VOTE / REDUX) cost ~50 cycles each and do not overlap inside one warp (measured with
+        // clock(): 32 back-to-back shuffles = 1600 cycles), and every instruction an idle warp issues is taken from the
+        // few warps with real work.  So the round is organised around shared memory instead:
+        //  * APPLY: a warp reads ONE word, its hit mask over the round's picks (computed by the leader against the warp's
+        //    box and current maximum).  Zero -> it does nothing at all.  Otherwise its lanes test their 16-lane group box
+        //    against those picks, the P updates run for the picks that may reach a lane, and the warp posts its new
+        //    candidate (key, position) and runner-up key.
+        //  * DECIDE (leader = warp 0, lane w = warp w's record): every lane finds its record's sorted position by
+        //    comparing against all 32 keys read as 8 LDS.128 (key ties: ordered by reference rank in a lane-local slow
+        //    path), position k < K is adopted by lane k through two small tables, candidates are exchanged through
+        //    shared memory, and one ballot yields the number of picks.  Position 0 is the plain argmax (largest key,
+        //    smallest reference rank among equals).  The candidate q at position k is ALSO the pick that would follow
+        //    -- with no update in between -- when
+        //      (i)   no other warp's candidate shares its key,
+        //      (ii)  its key is strictly larger than the runner-up key of every warp an earlier pick of this round came
+        //            from, and
+        //      (iii) no earlier pick of this round changes it: !(sqdist(pick, q) < md[q]), the update's own expression;
+        //    every other point is below q now and updates only lower min-distances, so q is the exact next argmax.  The
+        //    round stops at the first position that fails a test.
+        uint32_t* const rkey = reinterpret_cast<uint32_t*>(misc);          // [32] warp candidates: key
+        uint32_t* const rpos = rkey + 32;                                  // [32] position (bit 31: chain bookkeeping)
+        uint32_t* const rkey2 = rkey + 64;                                 // [32] runner-up key
+        uint32_t* const posarr = rkey + 96;                                // [32] leader: sorted position | tie << 7
+        uint32_t* const order = rkey + 128;                                // [32] leader: record lane at a position
+        uint32_t* const whit = rkey + 160;                                 // [32] per warp: picks that may reach it
+        float4* const cand = reinterpret_cast<float4*>(rkey + 192);        // [K] the round's candidates / picks
+        int* const npick = reinterpret_cast<int*>(rkey + 192 + 4 * K);     // how many of them are picks
+        const uint32_t bar_picks = smem_u32(rkey + 192 + 4 * K + 2);       // mbarrier: "the round is decided"
+        static_assert(K <= 16 && (192 + 4 * 16 + 4) * 4 <= 512 + 768 + 128, "round state must fit the prologue scratch");
+        constexpr int kBarPost = 1;
+        __syncthreads();  // the prologue scratch is dead
+        if (tid < 32) {
+            rkey[tid] = 0u;
+            rpos[tid] = 0u;
+            rkey2[tid] = 0u;
+            posarr[tid] = 0x7fu;
+            order[tid] = 0u;
+            whit[tid] = 1u;  // round 0: every warp applies pick 0
+        }
+        if (tid < K) cand[tid] = make_float4(first_xyz[0], first_xyz[1], first_xyz[2], 0.f);
+        if (tid == 0) {
+            *npick = 1;
+            mbar_init(bar_picks, 1);
+        }
+        __syncthreads();
+#ifdef FPSB_PROF
+        long long prof_apply = 0, prof_wait = 0, prof_lead = 0, prof_rounds = 0, prof_t00 = clock64();
+        long long prof_q[5] = {0, 0, 0, 0, 0};
+#endif
+        int round = 0;
+        for (int j = 1; j < m; ++round) {
+            PROF_T(tp0);
+            // ---- APPLY the round's picks (cand[0..c)); j = the first pick the leader decides next
+            const unsigned wm = whit[warp];
+            if (wm != 0u) {
+                const float4 b4 = sbox4[tid >> 4];
+                const float2 b2 = sbox2[tid >> 4];
+                unsigned hm = 0u;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                    if (((wm >> k) & 1u) == 0u) continue;
+                    const float4 pk = cand[k];
+                    // lmax only shrinks inside a round, so testing every pick against the round's initial lmax never
+                    // skips an update that could change a value; NaN bounds count as hits
+                    const bool hit = !(box_bound(pk.x, pk.y, pk.z, b4, b2) >= lmax) || round == 0;
+                    hm |= hit ? (1u << k) : 0u;
+                }
+                hm = __reduce_or_sync(FULL, hm);
+                if (hm != 0u) {
+#pragma unroll 1
+                    for (int k = 0; k < K; ++k) {
+                        if ((hm >> k) & 1u) {
+                            const float4 pk = cand[k];
+                            update(pk.x, pk.y, pk.z);
+                        }
+                    }
+                    warp_argmax();
+                    if (lane == 0) {
+                        rkey[warp] = wu;
+                        rpos[warp] = wpos;
+                        rkey2[warp] = wu2;
+                    }
+                }
+            }
+            if (warp != 0) {
+                asm volatile("bar.arrive %0, %1;" ::"n"(kBarPost), "n"(T) : "memory");
+            } else {
+                PROF_T(tp1);
+                asm volatile("bar.sync %0, %1;" ::"n"(kBarPost), "n"(T) : "memory");
+                PROF_T(tp2);
+                // ---- DECIDE picks j, j+1, ...
+                const uint32_t mykey = rkey[lane];
+                PROF_TD(tq0, mykey);
+                int pos = 0, eqc = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 k4 = reinterpret_cast<const uint4*>(rkey)[q];
+                    pos += (k4.x > mykey ? 1 : 0) + (k4.y > mykey ? 1 : 0) + (k4.z > mykey ? 1 : 0) + (k4.w > mykey ? 1 : 0);
+                    eqc += (k4.x == mykey ? 1 : 0) + (k4.y == mykey ? 1 : 0) + (k4.z == mykey ? 1 : 0) + (k4.w == mykey ? 1 : 0);
+                }
+                if (eqc > 1 && mykey != 0u) {  // shared key (rare): the reference rank orders the records that share it
+                    const uint32_t myrk = ref_rank(sk[rpos[lane] & 0x7fffffffu], L);
+                    for (int l = 0; l < NW; ++l)
+                        if (l != lane && rkey[l] == mykey && ref_rank(sk[rpos[l] & 0x7fffffffu], L) < myrk) ++pos;
+                }
+                PROF_TD(tq1, pos);
+                posarr[lane] = (uint32_t)pos | (eqc > 1 ? 0x80u : 0u);
+                if (pos < K && mykey != 0u) order[pos] = (uint32_t)lane;
+                __syncwarp();
+                // lane k < K adopts the record at position k (a stale table entry fails the position check)
+                const uint32_t src = order[lane & (K - 1)] & 31u;
+                const uint32_t pv = posarr[src];
+                const uint32_t qkey = rkey[src], qr2 = rkey2[src];
+                uint32_t qpos = rpos[src];
+                const bool valid = lane < K && (pv & 0x7fu) == (uint32_t)lane && qkey != 0u;
+                const bool shared_key = (pv & 0x80u) != 0u;
+                const int qe = (int)(qpos & 0x7fffffffu);
+                float qx = sx[qe], qy = sy[qe], qz = sz[qe];
+                if (lane == 0 && !valid) {  // no eligible candidate anywhere: the reference yields index 0
+                    qx = first_xyz[0];
+                    qy = first_xyz[1];
+                    qz = first_xyz[2];
+                }
+                PROF_TD(tq2, __float_as_uint(qx) ^ __float_as_uint(qy) ^ __float_as_uint(qz) ^ qr2);
+                if (lane < K) cand[lane] = make_float4(qx, qy, qz, __uint_as_float(qr2));
+                __syncwarp();
+                const float qmd = __uint_as_float(qkey & 0x7fffffffu);  // the record's min-distance (keys of values >= 0)
+                // this lane as warp `lane`: its box (union of its two group boxes; registers are short, so it is re-read)
+                float wb[6];
+                {
+                    const int g = 2 * (lane & (NW - 1));
+                    const float4 g0 = sbox4[g], g1 = sbox4[g + (NW * 2 > 1 ? 1 : 0)];
+                    const float2 h0 = sbox2[g], h1 = sbox2[g + (NW * 2 > 1 ? 1 : 0)];
+                    wb[0] = fminf(g0.x, g1.x); wb[1] = fmaxf(g0.y, g1.y);
+                    wb[2] = fminf(g0.z, g1.z); wb[3] = fmaxf(g0.w, g1.w);
+                    wb[4] = fminf(h0.x, h1.x); wb[5] = fmaxf(h0.y, h1.y);
+                }
+                // ... and its current maximum, for the warp-level hit test
+                float wmax = (mykey & 0x80000000u) ? __uint_as_float(mykey & 0x7fffffffu)
+                                                   : (mykey == 0u ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000));
+                uint32_t run2 = 0u;
+                bool moved = false;
+                unsigned hmask = 0u;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4 ck = cand[k];
+                    if (k < lane) {  // tests (ii) and (iii) against the earlier positions
+                        moved |= sqdist3(ck.x, ck.y, ck.z, qx, qy, qz) < qmd;
+                        run2 = max(run2, __float_as_uint(ck.w));
+                    }
+                    const float dx = fmaxf(fmaxf(__fsub_rn(wb[0], ck.x), __fsub_rn(ck.x, wb[1])), 0.f);
+                    const float dy = fmaxf(fmaxf(__fsub_rn(wb[2], ck.y), __fsub_rn(ck.y, wb[3])), 0.f);
+                    const float dz = fmaxf(fmaxf(__fsub_rn(wb[4], ck.z), __fsub_rn(ck.z, wb[5])), 0.f);
+                    const float lb = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                    hmask |= !(lb >= wmax) ? (1u << k) : 0u;
+                }
+                // keys of positive finite values lie in (0x80000000, 0xff800000); anything else ends the round
+                const bool ok = lane == 0 || (valid && !shared_key && j + lane < m && qkey > run2 && qkey > 0x80000000u &&
+                                              qkey < 0xff800000u && !moved);
+                PROF_TD(tq3, hmask ^ (ok ? 1u : 0u));
+                const unsigned okm = __ballot_sync(FULL, ok);
+                const int cnt = __ffs(~okm) - 1;  // the leading run of accepted positions
+                PROF_TD(tq4, cnt);
+                PROF_ACC2(tp2, tq0, tq1, tq2, tq3, tq4);
+                whit[lane] = hmask & ((1u << cnt) - 1u);
+                if (lane < cnt) {
+                    bool other = (qpos >> 31) != 0u;  // chain bookkeeping: a different point shares the maximum
+                    float val = qmd;
+                    if (lane == 0) {
+                        *npick = cnt;
+                        if (!valid) {
+                            qpos = 0xffffffffu;
+                            val = 0.f;
+                            other = false;
+                        } else if (chain && shared_key) {
+                            for (int l = 0; l < NW; ++l) {
+                                if (rkey[l] != qkey) continue;
+                                const uint32_t e2 = rpos[l];
+                                const int e = (int)(e2 & 0x7fffffffu);
+                                other |= (e2 >> 31) != 0u || sx[e] != qx || sy[e] != qy || sz[e] != qz;
+                            }
+                        }
+                    }
+                    // the slot for now (fire-and-forget store); translated to the original index after the loop
+                    idxs[j + lane] = (qpos == 0xffffffffu) ? -1 : (int)(qpos & 0x7fffffffu);
+                    if (a.vals) a.vals[(size_t)cloud * m + j + lane] = val;
+                    if (chain && other) atomicMin(a.tie_iter + cloud, j + lane);
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_picks) : "memory");
+                PROF_T(tp3);
+                PROF_ACC(tp0, tp1, tp2, tp3);
+            }
+            while (!mbar_try_wait_cta(bar_picks, (uint32_t)(round & 1))) {
+            }
+            j += *npick;
+        }
+#ifdef FPSB_PROF
+        if (tid == 0 && cloud == 0)
+            printf("fpsb K=%d n=%d m=%d rounds %lld  cycles/round: apply(warp0) %lld  wait-for-posts %lld  leader %lld  total %lld\n",
+                   K, n, m, prof_rounds, prof_apply / prof_rounds, prof_wait / prof_rounds, prof_lead / prof_rounds,
+                   (clock64() - prof_t00) / prof_rounds);
+        if (tid == 0 && cloud == 0)
+            printf("   leader: barrier wait %lld  positions %lld  adopt %lld  tests %lld  ballot %lld\n", prof_q[0] / prof_rounds,
+                   prof_q[1] / prof_rounds, prof_q[2] / prof_rounds, prof_q[3] / prof_rounds, prof_q[4] / prof_rounds);
+#endif
     }
 
     __syncthreads();  // every idxs[j] slot store of this CTA is visible to it
@@ -447,9 +714,9 @@ __global__ void __launch_bounds__(T, 1)
     }
 }
 
-template <int T, int P>
+template <int T, int P, int K>
 static int launch_bucket(const FpsArgs& a, int b, int cell_bits, cudaStream_t stream) {
-    auto kern = fps_bucket_kernel<T, P>;
+    auto kern = fps_bucket_kernel<T, P, K>;
     const size_t dyn = bucket_main_bytes(T * P, T, cell_bits) + kMiscBytes;
     if (dyn > 227 * 1024) return TSM_ERR_INVALID;
     if (dyn > 40 * 1024) TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -491,12 +758,29 @@ int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
     int cell_bits = lg + 1;
     if (cell_bits < 10) cell_bits = 10;
     if (cell_bits > 15) cell_bits = 15;
-#define FPSB_CASE(TT, PP) \
-    if (T == TT && P == PP) return tsm::launch_bucket<TT, PP>(a, b, cell_bits, stream);
+    // picks per round (see the kernel): 4 by default; TSMDET_FPSB_K = 1 restores one pick per barrier, 2 / 8 exist
+    // for the shapes the backbone uses
+    int K = 1;
+    if (const char* e = getenv("TSMDET_FPSB_K")) K = atoi(e);
+#define FPSB_CASE(TT, PP)                                                               \
+    if (T == TT && P == PP)                                                             \
+        return K == 1 ? tsm::launch_bucket<TT, PP, 1>(a, b, cell_bits, stream)          \
+                      : tsm::launch_bucket<TT, PP, 4>(a, b, cell_bits, stream);
+#define FPSB_CASE_K(TT, PP)                                                             \
+    if (T == TT && P == PP && K == 2) return tsm::launch_bucket<TT, PP, 2>(a, b, cell_bits, stream); \
+    if (T == TT && P == PP && K == 8) return tsm::launch_bucket<TT, PP, 8>(a, b, cell_bits, stream); \
+    if (T == TT && P == PP && K == 16) return tsm::launch_bucket<TT, PP, 16>(a, b, cell_bits, stream);
+    FPSB_CASE_K(1024, 16)
+#ifndef FPSB_QUICK  // (development: compile one launch shape only)
+    FPSB_CASE_K(512, 8) FPSB_CASE_K(128, 8)
     FPSB_CASE(32, 4) FPSB_CASE(64, 4) FPSB_CASE(128, 4) FPSB_CASE(256, 4) FPSB_CASE(512, 4) FPSB_CASE(1024, 4)
     FPSB_CASE(32, 8) FPSB_CASE(64, 8) FPSB_CASE(128, 8) FPSB_CASE(256, 8) FPSB_CASE(512, 8) FPSB_CASE(1024, 8)
     FPSB_CASE(32, 16) FPSB_CASE(64, 16) FPSB_CASE(128, 16) FPSB_CASE(256, 16) FPSB_CASE(512, 16) FPSB_CASE(1024, 16)
     FPSB_CASE(32, 32) FPSB_CASE(64, 32) FPSB_CASE(128, 32) FPSB_CASE(256, 32) FPSB_CASE(512, 32)
+#else
+    FPSB_CASE(1024, 16)
+#endif
+#undef FPSB_CASE_K
 #undef FPSB_CASE
     return TSM_ERR_INVALID;
 }
