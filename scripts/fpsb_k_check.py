@@ -50,7 +50,7 @@ for name, xyz_np, m in cases:
     xyz = torch.from_numpy(xyz_np).to(dev)
     want = run(xyz, m, "cluster").cpu().numpy()
     n = xyz_np.shape[1]
-    shapes = [(None, None, 1), (None, None, 2), (None, None, 4), (None, None, 8), (None, None, 16)]
+    shapes = [(None, None, 1), (None, None, 2), (None, None, 4), (None, None, 8)]
     for T in (32, 128, 512, 1024):
         for P in (4, 8, 16, 32):
             if T * P >= n and T * P <= 16384: shapes.append((T, P, 4))
@@ -93,7 +93,7 @@ for (b, n, m, gen) in [(16, 16384, 4096, "obj"), (16, 16384, 4096, "uni"), (16, 
                        (16, 4096, 1024, "obj"), (16, 1024, 512, "obj"), (148, 16384, 4096, "obj")]:
     xyz_np = {"obj": synth.cloud_ground_objects, "uni": synth.cloud_uniform, "dup": synth.cloud_dup_padded}[gen](b, n, 1)
     xyz = torch.from_numpy(xyz_np).to(dev)
-    for K in (1, 2, 4, 8, 16):
+    for K in (1, 2, 4, 8):
         ms = timeit(lambda: run(xyz, m, "bucket", None, None, K))
         print(json.dumps(dict(b=b, n=n, m=m, gen=gen, K=K, ms=round(ms, 4), us_per_pick=round(1000 * ms / (m - 1), 4))), flush=True)
     if n == 4096:

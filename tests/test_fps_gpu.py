@@ -100,6 +100,42 @@ def test_fps_bucket_degenerate_clouds(orc, monkeypatch):
     assert torch.equal(temp.view(torch.int32), temp2.view(torch.int32))
 
 
+@pytest.mark.parametrize("picks", [1, 2, 4, 8])
+def test_fps_bucket_multi_pick_rounds(orc, picks, monkeypatch):
+    """Rounds of up to K picks per barrier pair (fps_bucket.cu, TSMDET_FPSB_K) accept a further pick only when it is
+    provably the pick the one-at-a-time algorithm would make next, so K never changes an index: duplicate-heavy
+    clouds (runner-up keys equal to the candidate's), lattices (key ties across warps, resolved by reference rank),
+    clouds with fewer distinct points than picks, initial min-distances from temp, and the chained bookkeeping."""
+    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
+    monkeypatch.setenv("TSMDET_FPSB_K", str(picks))
+    for name, xyz, m in [("dup16384", synth.cloud_dup_padded(2, 16384, 70), 2048),
+                         ("obj16384", synth.cloud_ground_objects(1, 16384, 71), 4096),
+                         ("lattice16384", synth.cloud_lattice(1, 16384, 72), 1500),
+                         ("lattice9000", synth.cloud_lattice(2, 9000, 73, step=1.0), 900),
+                         ("dup4096", synth.cloud_dup_padded(3, 4096, 74), 1024),
+                         ("few_unique", synth.cloud_dup_padded(1, 12000, 75, unique_frac=0.02), 600),
+                         ("all_same", np.ones((1, 10000, 3), np.float32), 40),
+                         ("n129", synth.cloud_uniform(2, 129, 76), 129)]:
+        got = _fps(xyz, m)
+        want = orc.fps(xyz, m)
+        assert np.array_equal(got, want), f"{name} K={picks}: first mismatch at {np.argwhere(got != want)[:3]}"
+    from tsmdet_b200 import pointnet2_batch_cuda as ext
+
+    rng = np.random.default_rng(77)
+    xyz = synth.cloud_dup_padded(2, 16000, 78)
+    t0 = rng.uniform(0.0, 30.0, size=(2, 16000)).astype(np.float32)
+    x = torch.from_numpy(xyz).to(_dev())
+    out = {}
+    for algo in ("bucket", "cluster"):
+        monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+        temp = torch.from_numpy(t0.copy()).to(_dev())
+        idx = torch.zeros((2, 700), dtype=torch.int32, device=_dev())
+        ext.farthest_point_sampling_wrapper(2, 16000, 700, x, temp, idx)
+        out[algo] = (idx, temp)
+    assert torch.equal(out["bucket"][0], out["cluster"][0])
+    assert torch.equal(out["bucket"][1].view(torch.int32), out["cluster"][1].view(torch.int32))
+
+
 @pytest.mark.parametrize("csize", [1, 2, 4, 8, 16])
 @pytest.mark.parametrize("threads", [128, 256, 512, 1024])
 def test_fps_every_launch_shape(orc, csize, threads, monkeypatch):

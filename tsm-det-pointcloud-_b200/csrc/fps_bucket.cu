@@ -29,6 +29,9 @@ namespace tsm {
 #define FPSB_U1 4
 #endif
 constexpr int kU1 = FPSB_U1;
+#ifndef FPSB_WAIT
+#define FPSB_WAIT 1
+#endif
 #ifndef FPSB_UPD
 #define FPSB_UPD 2
 #endif
@@ -401,14 +404,14 @@ __global__ void __launch_bounds__(T, 1)
             const uint32_t u2 = (t2[0] > -1.f) ? f32_ordered(t2[0]) : 0u;
             wu2 = __reduce_max_sync(FULL, (lane == __ffs(tie) - 1) ? u2 : u);
         }
-        if (wu != 0u && ((tie & (tie - 1u)) != 0u || (chain && lane_tie))) {
-            // shared maximum inside the warp: the reference rank decides between lanes, and (chain bookkeeping)
-            // bit 31 of the candidate says whether a point with DIFFERENT coordinates shares it
+        if (wu != 0u && ((tie & (tie - 1u)) != 0u || ((chain || K > 1) && lane_tie))) {
+            // shared maximum inside the warp: the reference rank decides between lanes, and bit 31 of the candidate
+            // says whether a point with DIFFERENT coordinates shares it (chain bookkeeping; runner-up below)
             const uint32_t rk = (u == wu) ? ref_rank(sk[lpos], L) : 0xffffffffu;
             const uint32_t wrk = __reduce_min_sync(FULL, rk);
             const int wl = __ffs(__ballot_sync(FULL, rk == wrk)) - 1;
             wpos = (uint32_t)__shfl_sync(FULL, lpos, wl);
-            if (chain) {
+            if (chain || K > 1) {
                 bool other = false;
                 if (u == wu) {
                     const float fx = sx[wpos], fy = sy[wpos], fz = sz[wpos];
@@ -420,7 +423,16 @@ __global__ void __launch_bounds__(T, 1)
                         other |= sx[e] != fx || sy[e] != fy || sz[e] != fz;
                     }
                 }
-                if (__any_sync(FULL, other)) wpos |= 0x80000000u;
+                other = __any_sync(FULL, other);
+                if (chain && other) wpos |= 0x80000000u;
+                if (K > 1 && !other) {
+                    // every point sharing the maximum is an exact duplicate of the candidate: picking the candidate
+                    // zeroes them, so the runner-up that matters is the largest key among the OTHER points
+                    float s2 = -2.f;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) s2 = fmaxf(s2, (u == wu && md[p] == lmax) ? -2.f : md[p]);
+                    wu2 = __reduce_max_sync(FULL, (s2 > -1.f) ? f32_ordered(s2) : 0u);
+                }
             }
         }
     };
@@ -515,28 +527,31 @@ __global__ void __launch_bounds__(T, 1)
         uint32_t* const rkey = reinterpret_cast<uint32_t*>(misc);          // [32] warp candidates: key
         uint32_t* const rpos = rkey + 32;                                  // [32] position (bit 31: chain bookkeeping)
         uint32_t* const rkey2 = rkey + 64;                                 // [32] runner-up key
-        uint32_t* const posarr = rkey + 96;                                // [32] leader: sorted position | tie << 7
-        uint32_t* const order = rkey + 128;                                // [32] leader: record lane at a position
-        uint32_t* const whit = rkey + 160;                                 // [32] per warp: picks that may reach it
-        float4* const cand = reinterpret_cast<float4*>(rkey + 192);        // [K] the round's candidates / picks
-        int* const npick = reinterpret_cast<int*>(rkey + 192 + 4 * K);     // how many of them are picks
-        const uint32_t bar_picks = smem_u32(rkey + 192 + 4 * K + 2);       // mbarrier: "the round is decided"
-        static_assert(K <= 16 && (192 + 4 * 16 + 4) * 4 <= 512 + 768 + 128, "round state must fit the prologue scratch");
-        constexpr int kBarPost = 1;
+        uint32_t* const rskey = rkey + 96;                                 // [32] sort key: (key & ~31) | (31 - warp), unique
+        uint32_t* const posarr = rkey + 128;                               // [32] leader: sorted position of a record
+        uint32_t* const sk_at = rkey + 160;                                // [32] leader: sort key at a position
+        uint32_t* const whitp = rkey + 192;                                // [3][32] per helper, per warp: picks that may reach it
+        float4* const cand = reinterpret_cast<float4*>(rkey + 288);        // [K] the round's candidates / picks: x, y, z
+        uint32_t* const ckey = rkey + 320;                                 // [K] ... their keys
+        uint32_t* const cr2 = rkey + 328;                                  // [K] ... the runner-up keys of their warps
+        int* const npick = reinterpret_cast<int*>(rkey + 336);             // how many of them are picks
+        static_assert(K <= 8 && NW >= 4 && 338 * 4 <= 512 + 768 + 128, "round state must fit the prologue scratch");
+        constexpr int kBarPost = 1, kBarDone = 2, kBarCand = 3;
         __syncthreads();  // the prologue scratch is dead
         if (tid < 32) {
             rkey[tid] = 0u;
             rpos[tid] = 0u;
             rkey2[tid] = 0u;
+            rskey[tid] = 31u - tid;
             posarr[tid] = 0x7fu;
-            order[tid] = 0u;
-            whit[tid] = 1u;  // round 0: every warp applies pick 0
+            sk_at[tid] = 0u;
+            whitp[tid] = 1u;  // round 0: every warp applies pick 0
+            whitp[32 + tid] = 0u;
+            whitp[64 + tid] = 0u;
         }
         if (tid < K) cand[tid] = make_float4(first_xyz[0], first_xyz[1], first_xyz[2], 0.f);
-        if (tid == 0) {
-            *npick = 1;
-            mbar_init(bar_picks, 1);
-        }
+        if (tid == 0) *npick = 1;
+        int c = 1;  // picks of the round being applied
         __syncthreads();
 #ifdef FPSB_PROF
         long long prof_apply = 0, prof_wait = 0, prof_lead = 0, prof_rounds = 0, prof_t00 = clock64();
@@ -546,39 +561,56 @@ __global__ void __launch_bounds__(T, 1)
         for (int j = 1; j < m; ++round) {
             PROF_T(tp0);
             // ---- APPLY the round's picks (cand[0..c)); j = the first pick the leader decides next
-            const unsigned wm = whit[warp];
+            // (no second, finer test here: the round is bound by the latency of this chain, not by issue slots, so an
+            // update that turns out to change nothing is cheaper than a test + warp vote that might avoid it)
+            const unsigned wm = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & ((1u << c) - 1u);
             if (wm != 0u) {
-                const float4 b4 = sbox4[tid >> 4];
-                const float2 b2 = sbox2[tid >> 4];
-                unsigned hm = 0u;
+                // The warp's record stays valid as long as its candidate point itself is not lowered: updates only lower
+                // min-distances, so the maximum stays where it is and the runner-up key stays an upper bound.  The test
+                // is the update's own expression on the candidate, evaluated by every lane alike (no vote).
+                const float cx = sx[wpos & 0x7fffffffu], cy = sy[wpos & 0x7fffffffu], cz = sz[wpos & 0x7fffffffu];
+                const float cval = __uint_as_float(wu & 0x7fffffffu);
+                bool redo = (wu & 0x80000000u) == 0u;  // no valid record yet (first round, ineligible warp)
 #pragma unroll 1
                 for (int k = 0; k < K; ++k) {
-                    if (((wm >> k) & 1u) == 0u) continue;
-                    const float4 pk = cand[k];
-                    // lmax only shrinks inside a round, so testing every pick against the round's initial lmax never
-                    // skips an update that could change a value; NaN bounds count as hits
-                    const bool hit = !(box_bound(pk.x, pk.y, pk.z, b4, b2) >= lmax) || round == 0;
-                    hm |= hit ? (1u << k) : 0u;
-                }
-                hm = __reduce_or_sync(FULL, hm);
-                if (hm != 0u) {
-#pragma unroll 1
-                    for (int k = 0; k < K; ++k) {
-                        if ((hm >> k) & 1u) {
-                            const float4 pk = cand[k];
-                            update(pk.x, pk.y, pk.z);
-                        }
+                    if ((wm >> k) & 1u) {
+                        const float4 pk = cand[k];
+                        redo |= sqdist3(pk.x, pk.y, pk.z, cx, cy, cz) < cval;
+                        update(pk.x, pk.y, pk.z);
                     }
+                }
+                if (redo) {
                     warp_argmax();
                     if (lane == 0) {
                         rkey[warp] = wu;
                         rpos[warp] = wpos;
                         rkey2[warp] = wu2;
+                        rskey[warp] = (wu & ~31u) | (31u - (uint32_t)warp);
                     }
                 }
             }
             if (warp != 0) {
                 asm volatile("bar.arrive %0, %1;" ::"n"(kBarPost), "n"(T) : "memory");
+                if (warp < 4) {
+                    // ---- HELPER h = warp - 1: which of the candidates h, h+3, ... may reach warp `lane`?  A candidate
+                    // reaches a warp when the bound to one of its two group boxes is below the warp's current maximum.
+                    asm volatile("bar.sync %0, 128;" ::"n"(kBarCand) : "memory");
+                    const uint32_t wkey = rkey[lane];
+                    const float wmax = (wkey & 0x80000000u) ? __uint_as_float(wkey & 0x7fffffffu)
+                                                            : (wkey == 0u ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000));
+                    const int g = 2 * (lane & (NW - 1));
+                    const float4 g0 = sbox4[g], g1 = sbox4[g + 1];
+                    const float2 h0 = sbox2[g], h1 = sbox2[g + 1];
+                    unsigned hmask = 0u;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (k % 3 != warp - 1) continue;
+                        const float4 ck = cand[k];
+                        const bool hit = !(box_bound(ck.x, ck.y, ck.z, g0, h0) >= wmax) || !(box_bound(ck.x, ck.y, ck.z, g1, h1) >= wmax);
+                        hmask |= hit ? (1u << k) : 0u;
+                    }
+                    whitp[32 * (warp - 1) + lane] = hmask;
+                }
             } else {
                 PROF_T(tp1);
                 asm volatile("bar.sync %0, %1;" ::"n"(kBarPost), "n"(T) : "memory");
@@ -586,29 +618,48 @@ __global__ void __launch_bounds__(T, 1)
                 // ---- DECIDE picks j, j+1, ...
                 const uint32_t mykey = rkey[lane];
                 PROF_TD(tq0, mykey);
-                int pos = 0, eqc = 0;
+                // Sorted position of every record.  The sort key drops the 5 lowest bits of the key and carries the warp
+                // instead, so keys are unique and one compare per record places a record; records whose keys agree in
+                // the upper 27 bits ("near ties", incl. real ties) are ordered arbitrarily and are re-examined below.
+                const uint32_t mysk = rskey[lane];
+                int pos;
+                {
+                    int gt[2] = {0, 0};
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint4 k4 = reinterpret_cast<const uint4*>(rkey)[q];
-                    pos += (k4.x > mykey ? 1 : 0) + (k4.y > mykey ? 1 : 0) + (k4.z > mykey ? 1 : 0) + (k4.w > mykey ? 1 : 0);
-                    eqc += (k4.x == mykey ? 1 : 0) + (k4.y == mykey ? 1 : 0) + (k4.z == mykey ? 1 : 0) + (k4.w == mykey ? 1 : 0);
-                }
-                if (eqc > 1 && mykey != 0u) {  // shared key (rare): the reference rank orders the records that share it
-                    const uint32_t myrk = ref_rank(sk[rpos[lane] & 0x7fffffffu], L);
-                    for (int l = 0; l < NW; ++l)
-                        if (l != lane && rkey[l] == mykey && ref_rank(sk[rpos[l] & 0x7fffffffu], L) < myrk) ++pos;
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 k4 = reinterpret_cast<const uint4*>(rskey)[q];
+                        gt[q & 1] += (k4.x > mysk ? 1 : 0) + (k4.y > mysk ? 1 : 0) + (k4.z > mysk ? 1 : 0) + (k4.w > mysk ? 1 : 0);
+                    }
+                    pos = gt[0] + gt[1];
                 }
                 PROF_TD(tq1, pos);
-                posarr[lane] = (uint32_t)pos | (eqc > 1 ? 0x80u : 0u);
-                if (pos < K && mykey != 0u) order[pos] = (uint32_t)lane;
+                posarr[lane] = (uint32_t)pos;
+                if (pos <= K && mykey != 0u) sk_at[pos] = mysk;
                 __syncwarp();
                 // lane k < K adopts the record at position k (a stale table entry fails the position check)
-                const uint32_t src = order[lane & (K - 1)] & 31u;
-                const uint32_t pv = posarr[src];
+                const uint32_t skk = sk_at[lane & 15], skn = sk_at[(lane & 15) + 1], skp = sk_at[(lane + 15) & 15];
+                uint32_t src = 31u - (skk & 31u);
+                bool valid = lane < K && posarr[src] == (uint32_t)lane && rkey[src] != 0u;
+                const bool near_tie = (skk >> 5) == (skn >> 5) || (lane != 0 && (skk >> 5) == (skp >> 5));
+                bool shared_key = false;
+                if (lane == 0 && valid && near_tie) {
+                    // (rare) the plain argmax among the records near the top: largest key, smallest reference rank
+                    uint32_t bk = 0u, brk = 0xffffffffu;
+                    for (int l = 0; l < NW; ++l) {
+                        if ((rskey[l] >> 5) != (skk >> 5)) continue;
+                        const uint32_t kl = rkey[l];
+                        if (kl < bk) continue;
+                        const uint32_t rl = ref_rank(sk[rpos[l] & 0x7fffffffu], L);
+                        if (kl > bk) {
+                            bk = kl; brk = rl; src = (uint32_t)l; shared_key = false;
+                        } else {
+                            shared_key = true;
+                            if (rl < brk) { brk = rl; src = (uint32_t)l; }
+                        }
+                    }
+                }
                 const uint32_t qkey = rkey[src], qr2 = rkey2[src];
                 uint32_t qpos = rpos[src];
-                const bool valid = lane < K && (pv & 0x7fu) == (uint32_t)lane && qkey != 0u;
-                const bool shared_key = (pv & 0x80u) != 0u;
                 const int qe = (int)(qpos & 0x7fffffffu);
                 float qx = sx[qe], qy = sy[qe], qz = sz[qe];
                 if (lane == 0 && !valid) {  // no eligible candidate anywhere: the reference yields index 0
@@ -617,47 +668,46 @@ __global__ void __launch_bounds__(T, 1)
                     qz = first_xyz[2];
                 }
                 PROF_TD(tq2, __float_as_uint(qx) ^ __float_as_uint(qy) ^ __float_as_uint(qz) ^ qr2);
-                if (lane < K) cand[lane] = make_float4(qx, qy, qz, __uint_as_float(qr2));
-                __syncwarp();
-                const float qmd = __uint_as_float(qkey & 0x7fffffffu);  // the record's min-distance (keys of values >= 0)
-                // this lane as warp `lane`: its box (union of its two group boxes; registers are short, so it is re-read)
-                float wb[6];
-                {
-                    const int g = 2 * (lane & (NW - 1));
-                    const float4 g0 = sbox4[g], g1 = sbox4[g + (NW * 2 > 1 ? 1 : 0)];
-                    const float2 h0 = sbox2[g], h1 = sbox2[g + (NW * 2 > 1 ? 1 : 0)];
-                    wb[0] = fminf(g0.x, g1.x); wb[1] = fmaxf(g0.y, g1.y);
-                    wb[2] = fminf(g0.z, g1.z); wb[3] = fmaxf(g0.w, g1.w);
-                    wb[4] = fminf(h0.x, h1.x); wb[5] = fmaxf(h0.y, h1.y);
+                if (lane < K) {
+                    cand[lane] = make_float4(qx, qy, qz, 0.f);
+                    ckey[lane] = qkey;
+                    cr2[lane] = qr2;
                 }
-                // ... and its current maximum, for the warp-level hit test
-                float wmax = (mykey & 0x80000000u) ? __uint_as_float(mykey & 0x7fffffffu)
-                                                   : (mykey == 0u ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000));
-                uint32_t run2 = 0u;
-                bool moved = false;
-                unsigned hmask = 0u;
+                __syncwarp();
+                asm volatile("bar.arrive %0, 128;" ::"n"(kBarCand) : "memory");  // the helpers may start
+                const float qmd = __uint_as_float(qkey & 0x7fffffffu);  // the record's min-distance (keys of values >= 0)
+                // test (iii), one (earlier, later) pair of positions per lane: does the earlier one change the later one?
+                bool pmoved = false;
+                {
+                    int hi = 1;  // pair index `lane` -> positions lo < hi: pairs of hi start at hi (hi - 1) / 2
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float4 ck = cand[k];
-                    if (k < lane) {  // tests (ii) and (iii) against the earlier positions
-                        moved |= sqdist3(ck.x, ck.y, ck.z, qx, qy, qz) < qmd;
-                        run2 = max(run2, __float_as_uint(ck.w));
+                    for (int t = 2; t < K; ++t) hi += (lane >= t * (t - 1) / 2) ? 1 : 0;
+                    const int lo = lane - hi * (hi - 1) / 2;
+                    if (lane < K * (K - 1) / 2) {
+                        const float4 pl = cand[lo], ph = cand[hi];
+                        pmoved = sqdist3(pl.x, pl.y, pl.z, ph.x, ph.y, ph.z) < __uint_as_float(ckey[hi] & 0x7fffffffu);
                     }
-                    const float dx = fmaxf(fmaxf(__fsub_rn(wb[0], ck.x), __fsub_rn(ck.x, wb[1])), 0.f);
-                    const float dy = fmaxf(fmaxf(__fsub_rn(wb[2], ck.y), __fsub_rn(ck.y, wb[3])), 0.f);
-                    const float dz = fmaxf(fmaxf(__fsub_rn(wb[4], ck.z), __fsub_rn(ck.z, wb[5])), 0.f);
-                    const float lb = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                    hmask |= !(lb >= wmax) ? (1u << k) : 0u;
+                }
+                const unsigned pm = __ballot_sync(FULL, pmoved);
+                const bool moved = lane < K && ((pm >> (lane * (lane - 1) / 2)) & ((1u << lane) - 1u)) != 0u;
+                // test (ii): the runner-up keys of the earlier positions' warps
+                uint32_t run2 = 0u;
+#pragma unroll
+                for (int q = 0; q < (K + 3) / 4; ++q) {
+                    const uint4 v = reinterpret_cast<const uint4*>(cr2)[q];
+                    run2 = max(run2, 4 * q + 0 < lane ? v.x : 0u);
+                    run2 = max(run2, 4 * q + 1 < lane ? v.y : 0u);
+                    run2 = max(run2, 4 * q + 2 < lane ? v.z : 0u);
+                    run2 = max(run2, 4 * q + 3 < lane ? v.w : 0u);
                 }
                 // keys of positive finite values lie in (0x80000000, 0xff800000); anything else ends the round
-                const bool ok = lane == 0 || (valid && !shared_key && j + lane < m && qkey > run2 && qkey > 0x80000000u &&
+                const bool ok = lane == 0 || (valid && !near_tie && j + lane < m && qkey > run2 && qkey > 0x80000000u &&
                                               qkey < 0xff800000u && !moved);
-                PROF_TD(tq3, hmask ^ (ok ? 1u : 0u));
+                PROF_TD(tq3, (ok ? 1u : 0u));
                 const unsigned okm = __ballot_sync(FULL, ok);
                 const int cnt = __ffs(~okm) - 1;  // the leading run of accepted positions
                 PROF_TD(tq4, cnt);
                 PROF_ACC2(tp2, tq0, tq1, tq2, tq3, tq4);
-                whit[lane] = hmask & ((1u << cnt) - 1u);
                 if (lane < cnt) {
                     bool other = (qpos >> 31) != 0u;  // chain bookkeeping: a different point shares the maximum
                     float val = qmd;
@@ -681,14 +731,24 @@ __global__ void __launch_bounds__(T, 1)
                     if (a.vals) a.vals[(size_t)cloud * m + j + lane] = val;
                     if (chain && other) atomicMin(a.tie_iter + cloud, j + lane);
                 }
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_picks) : "memory");
                 PROF_T(tp3);
                 PROF_ACC(tp0, tp1, tp2, tp3);
             }
-            while (!mbar_try_wait_cta(bar_picks, (uint32_t)(round & 1))) {
+            asm volatile("bar.sync %0, %1;" ::"n"(kBarDone), "n"(T) : "memory");
+            c = *npick;
+            j += c;
+        }
+        if (a.temp != nullptr && c > 1) {
+            // temp leaves with the min-distances to picks 0..m-2 (the reference never applies its last pick): the last
+            // round's picks but the final one are still outstanding
+            const unsigned wm = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & ((1u << (c - 1)) - 1u);
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                if ((wm >> k) & 1u) {
+                    const float4 pk = cand[k];
+                    update(pk.x, pk.y, pk.z);
+                }
             }
-            j += *npick;
         }
 #ifdef FPSB_PROF
         if (tid == 0 && cloud == 0)
@@ -725,6 +785,15 @@ static int launch_bucket(const FpsArgs& a, int b, int cell_bits, cudaStream_t st
     return TSM_OK;
 }
 
+// one pick per barrier (K = 1), or rounds of up to 4 picks where the CTA has the helper warps for it
+template <int T, int P>
+static int launch_bucket_k(const FpsArgs& a, int b, int cell_bits, cudaStream_t stream, int K) {
+    if constexpr (T >= 128) {
+        if (K > 1) return launch_bucket<T, P, 4>(a, b, cell_bits, stream);
+    }
+    return launch_bucket<T, P, 1>(a, b, cell_bits, stream);
+}
+
 }  // namespace tsm
 
 bool tsm_fps_bucket_supports(int n, bool weighted) { return !weighted && n >= 1 && n <= tsm::kBucketMaxN; }
@@ -758,18 +827,16 @@ int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
     int cell_bits = lg + 1;
     if (cell_bits < 10) cell_bits = 10;
     if (cell_bits > 15) cell_bits = 15;
-    // picks per round (see the kernel): 4 by default; TSMDET_FPSB_K = 1 restores one pick per barrier, 2 / 8 exist
-    // for the shapes the backbone uses
-    int K = 1;
+    // Picks per round (see the kernel).  Measured on B200 (profiles/r01_fps_multipick.txt): rounds of up to 8 picks pay
+    // for clouds of 8193..16384 points (1024 x 16: 2.74 -> 1.80 ms at 16384 -> 4096, 2.04 ms on duplicate-padded
+    // clouds); smaller clouds keep one pick per barrier.  TSMDET_FPSB_K = 1 | 2 | 4 | 8 overrides.
+    int K = (T == 1024 && P == 16) ? 8 : 1;
     if (const char* e = getenv("TSMDET_FPSB_K")) K = atoi(e);
 #define FPSB_CASE(TT, PP)                                                               \
-    if (T == TT && P == PP)                                                             \
-        return K == 1 ? tsm::launch_bucket<TT, PP, 1>(a, b, cell_bits, stream)          \
-                      : tsm::launch_bucket<TT, PP, 4>(a, b, cell_bits, stream);
+    if (T == TT && P == PP) return tsm::launch_bucket_k<TT, PP>(a, b, cell_bits, stream, K);
 #define FPSB_CASE_K(TT, PP)                                                             \
     if (T == TT && P == PP && K == 2) return tsm::launch_bucket<TT, PP, 2>(a, b, cell_bits, stream); \
-    if (T == TT && P == PP && K == 8) return tsm::launch_bucket<TT, PP, 8>(a, b, cell_bits, stream); \
-    if (T == TT && P == PP && K == 16) return tsm::launch_bucket<TT, PP, 16>(a, b, cell_bits, stream);
+    if (T == TT && P == PP && K == 8) return tsm::launch_bucket<TT, PP, 8>(a, b, cell_bits, stream);
     FPSB_CASE_K(1024, 16)
 #ifndef FPSB_QUICK  // (development: compile one launch shape only)
     FPSB_CASE_K(512, 8) FPSB_CASE_K(128, 8)
