@@ -7,7 +7,7 @@ from tsmdet_b200 import pointnet2_utils as pu
 dev = torch.device("cuda:0")
 os.environ["TSMDET_FPS_ALGO"] = "bucket"
 for (n, m) in ((16384, 4096),):
-    xyz = torch.from_numpy(synth.cloud_ground_objects(16, n, 1)).to(dev)
-    for K in (2, 4, 8):
+    xyz = torch.from_numpy(getattr(synth, os.environ.get("GEN", "cloud_ground_objects"))(16, n, 1)).to(dev)
+    for K in (4, 8):
         os.environ["TSMDET_FPSB_K"] = str(K)
         pu.farthest_point_sample(xyz, m); torch.cuda.synchronize()

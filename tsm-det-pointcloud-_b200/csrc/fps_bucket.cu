@@ -505,25 +505,28 @@ __global__ void __launch_bounds__(T, 1)
         }
     } else {
         // ================= rounds of up to K picks =================
-        // Warp-collectives (SHFL / VOTE / REDUX) cost ~50 cycles each and do not overlap inside one warp (measured with
-        // clock(): 32 back-to-back shuffles = 1600 cycles), and every instruction an idle warp issues is taken from the
-        // few warps with real work.  So the round is organised around shared memory instead:
-        //  * APPLY: a warp reads ONE word, its hit mask over the round's picks (computed by the leader against the warp's
-        //    box and current maximum).  Zero -> it does nothing at all.  Otherwise its lanes test their 16-lane group box
-        //    against those picks, the P updates run for the picks that may reach a lane, and the warp posts its new
-        //    candidate (key, position) and runner-up key.
+        // Measured on B200 with clock64(): warp collectives (SHFL / VOTE / REDUX) cost ~30-50 cycles each and do not
+        // overlap inside one warp; a lone warp issues dependent instructions ~4.5 cycles apart; and every instruction an
+        // idle warp issues is taken from the few warps with real work.  So a round is organised around shared memory:
+        //  * APPLY: a warp reads its hit masks over the round's picks (three words, one per helper).  Zero -> it does
+        //    nothing.  Otherwise the P updates run for the picks that may reach it, and it re-runs its argmax and posts
+        //    (key, position, runner-up key, sort key) only if its candidate point itself was lowered.
         //  * DECIDE (leader = warp 0, lane w = warp w's record): every lane finds its record's sorted position by
-        //    comparing against all 32 keys read as 8 LDS.128 (key ties: ordered by reference rank in a lane-local slow
-        //    path), position k < K is adopted by lane k through two small tables, candidates are exchanged through
-        //    shared memory, and one ballot yields the number of picks.  Position 0 is the plain argmax (largest key,
-        //    smallest reference rank among equals).  The candidate q at position k is ALSO the pick that would follow
-        //    -- with no update in between -- when
-        //      (i)   no other warp's candidate shares its key,
+        //    comparing its sort key against all 32 (8 LDS.128); position k < K is adopted by lane k through a
+        //    position table; the K (K-1) / 2 "does pick i lower candidate k" tests run one pair per lane; one ballot
+        //    yields the number of picks.  Position 0 is the plain argmax (largest key, smallest reference rank among
+        //    equals; records within 32 ulp of the top are re-examined exactly).  The candidate q at position k is ALSO
+        //    the pick that would follow -- with no update in between -- when
+        //      (i)   no other warp's candidate has a key within 32 ulp of q's (the order needs no rank decision),
         //      (ii)  its key is strictly larger than the runner-up key of every warp an earlier pick of this round came
-        //            from, and
+        //            from (exact duplicates of that warp's candidate excepted: picking the candidate zeroes them), and
         //      (iii) no earlier pick of this round changes it: !(sqdist(pick, q) < md[q]), the update's own expression;
         //    every other point is below q now and updates only lower min-distances, so q is the exact next argmax.  The
         //    round stops at the first position that fails a test.
+        //  * HELPERS (warps 1..3, one per other SM sub-partition) meanwhile test each candidate against every warp's two
+        //    group boxes and current maximum: the hit masks of the next APPLY.
+        // Barriers: 1 = "records posted" (bar.arrive by everyone, bar.sync by the leader), 3 = "candidates written"
+        // (leader arrives, helpers wait), 2 = "round decided" (everyone).
         uint32_t* const rkey = reinterpret_cast<uint32_t*>(misc);          // [32] warp candidates: key
         uint32_t* const rpos = rkey + 32;                                  // [32] position (bit 31: chain bookkeeping)
         uint32_t* const rkey2 = rkey + 64;                                 // [32] runner-up key
