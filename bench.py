@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- frames/s of the SA backbone + rotated NMS hot path (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5                  # this repo's sm_100a path
+    python bench.py --gpus 1 --steps 50 --warmup 8                  # this repo's sm_100a path
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...                             # reference CPU arm (oracle port)
 
@@ -211,8 +211,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "8")),

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 for N in "$@"; do
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_g$N.log 2> gpurun_out/bench_g$N.err; echo "bench N=$N exit $?"
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 40 --warmup 8 --no-cpu-baseline > gpurun_out/bench_g$N.log 2> gpurun_out/bench_g$N.err; echo "bench N=$N exit $?"
 python - <<PY
 import json
 try:
