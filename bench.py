@@ -288,6 +288,25 @@ def main():
         dev_step()
     runner.sync()
     barrier()
+    gather_transport = None
+    if gather:
+        # outside the timed region: whatever transport the gather uses, every rank must now hold exactly what an NCCL
+        # all_gather of the last step's packed records returns
+        from tsmdet_b200.sharding import gather_packed
+
+        for eng in runner.engines[:2]:
+            res = eng.forward_device(*lane_inputs[0], gather=True)
+            torch.cuda.synchronize(dev)
+            pg = getattr(eng, "_pg", None)
+            gather_transport = "peer-memory stores (tsmdet_peer_put), one kernel per step" if pg is not None else "nccl all_gather"
+            if pg is not None:
+                pg.wait()
+            f, k = res["det"].shape[0], res["det"].shape[1]
+            ref_det, ref_num, _ = gather_packed(res["det_packed"], f, k)
+            torch.cuda.synchronize(dev)
+            if not (torch.equal(res["all_det"], ref_det) and torch.equal(res["all_num"], ref_num)):
+                raise RuntimeError("detection gather differs from the NCCL all_gather of the same records")
+        barrier()
     sampler = ClockSampler(dev)
     sampler.start()
     l0 = _lib.launch_count
@@ -341,7 +360,8 @@ def main():
                    "l2": "256 MB buffer written before every step, inside the timed region",
                    "execution": "one CUDA graph per step (FPS chain, query+MLP, NMS on 3 concurrent streams); "
                                 f"{depth} step(s) in flight on separate streams/buffers",
-                   "pipeline_depth": depth, "ms_per_step_single_in_flight": lat[len(lat) // 2]},
+                   "pipeline_depth": depth, "ms_per_step_single_in_flight": lat[len(lat) // 2],
+                   "gather": gather_transport},
         "e2e": {"value": e2e, "unit": "frames/s",
                 "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h)),
                 "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h_out.values()))},

@@ -157,6 +157,19 @@ int tsmdet_nms_batch(int frames, int nmax, const float* boxes, int box_stride, c
 int tsmdet_nms_normal_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
                             long long* keep, int* num_keep, void* stream);
 
+/* Detection gather without a rendezvous: store `numel` floats from `src` into rows[r] for r < world (row `rank` of
+ * every rank's receive buffer, peers mapped through CUDA IPC), then publish the step number (++sync2[1]) into
+ * flags[r].  sync2 = two zero-initialised device ints owned by the caller.  src and rows 16-byte aligned.
+ * ref: replaces pcdet/utils/common_utils.py:224-245 merge_results_dist (pickle files + barriers). */
+int tsmdet_peer_put(const float* src, long long numel, int world, void* const* rows, void* const* flags, int* sync2,
+                    void* stream);
+/* Enables access from the current device to memory on `peer_device` (needed before kernels store into IPC-mapped
+ * peer buffers); already-enabled is not an error. */
+int tsmdet_enable_peer_access(int peer_device);
+/* Consumer side, stream-ordered: returns once this rank's flag words (world of them) have all reached `want`
+ * (want < 0: the step of this rank's last tsmdet_peer_put on the same stream, read from sync2[1]). */
+int tsmdet_peer_wait(const long long* flags, int world, const int* sync2, long long want, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

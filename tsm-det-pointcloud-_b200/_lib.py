@@ -74,6 +74,9 @@ SIGNATURES = {
     "tsmdet_nms_normal_gpu": [c_int, c_void_p, c_float, c_void_p, _i, c_void_p],
     "tsmdet_nms_batch": [c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
     "tsmdet_nms_normal_batch": [c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
+    "tsmdet_peer_put": [c_void_p, c_longlong, c_int, _pp, _pp, c_void_p, c_void_p],
+    "tsmdet_peer_wait": [c_void_p, c_int, c_void_p, c_longlong, c_void_p],
+    "tsmdet_enable_peer_access": [c_int],
 }
 _RESTYPES = {"tsmdet_version": c_char_p, "tsmdet_error_string": c_char_p}
 
@@ -106,7 +109,7 @@ def check(status: int, where: str) -> None:
 KERNELS_PER_CALL = {
     "tsmdet_nms_batch": 6, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 6, "tsmdet_nms_normal_gpu": 3,
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
-    "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3,
+    "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_enable_peer_access": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3,
 }
 launch_count = 0
 

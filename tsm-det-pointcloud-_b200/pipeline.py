@@ -18,13 +18,14 @@ reference-facing call with HOST buffers: pinned H2D copies in, results copied ba
 from __future__ import annotations
 
 import os
+import sys
 from typing import Dict, Optional
 
 import torch
 
 from . import _lib, iou3d_nms_utils, pointnet2_utils
 from .pointnet2_modules import gather_xyz, kitti_sa_stack, sa_mlp_maxpool
-from .sharding import gather_detections, gather_packed, pack_detections
+from .sharding import PeerGather, gather_detections, gather_packed, pack_detections
 
 
 class SABackboneNMS(torch.nn.Module):
@@ -215,11 +216,34 @@ class SABackboneNMS(torch.nn.Module):
             # packed buffer the graph produced -- no size exchange, no host sync, no other kernels
             if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
                 f, k = res["det"].shape[0], res["det"].shape[1]
-                res["all_det"], res["all_num"], self._gather_out = gather_packed(
-                    res["det_packed"], f, k, out=getattr(self, "_gather_out", None))
+                pg = self._peer_gather(res["det_packed"])
+                if pg is not None:  # one-sided copies into every rank's receive buffer (sharding.PeerGather)
+                    pg.put(res["det_packed"])
+                    res["all_det"], res["all_num"] = pg.views(f, k)
+                else:
+                    res["all_det"], res["all_num"], self._gather_out = gather_packed(
+                        res["det_packed"], f, k, out=getattr(self, "_gather_out", None))
             else:
                 res["all_det"], res["all_num"] = res["det"].unsqueeze(0), res["det_num"].unsqueeze(0)
         return res
+
+    def _peer_gather(self, packed):
+        """The transport of the detection gather: peer-memory copies (TSMDET_GATHER=peer, the default on GPUs) or the
+        NCCL all_gather (TSMDET_GATHER=nccl, and whenever the IPC set-up fails -- every rank takes the same branch)."""
+        if not hasattr(self, "_pg"):
+            self._pg = None
+            want = os.environ.get("TSMDET_GATHER", "nccl") == "peer" and packed.is_cuda
+            ok = torch.zeros((1,), dtype=torch.int32, device=packed.device)
+            if want:
+                try:
+                    self._pg = PeerGather(packed.numel(), packed.device)
+                    ok += 1
+                except Exception as e:  # noqa: BLE001 -- fall back to NCCL together with everybody else
+                    print(f"[tsmdet] peer-memory gather unavailable ({e}); using the NCCL all_gather", file=sys.stderr)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self._pg = None
+        return self._pg
 
     def static_inputs(self, xyz, feats, boxes, scores):
         """The engine-owned input buffers for these shapes (write into them to skip the D2D copy)."""
@@ -279,8 +303,10 @@ class PipelinedRunner:
         for eng, lane in zip(self.engines, self.lanes):
             lane.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(lane):
-                eng.forward_device(xyz, feats, boxes, scores)
+                res = eng.forward_device(xyz, feats, boxes, scores)
                 ins.append(eng.static_inputs(xyz, feats, boxes, scores))
+                if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+                    eng._peer_gather(res["det_packed"])  # map the peers' receive buffers now, not in a timed step
         self.sync()
         return ins
 
@@ -306,6 +332,8 @@ class PipelinedRunner:
             for s, t in zip(d_in, h_in):
                 s.copy_(t, non_blocking=True)
             res = eng.forward_device(*d_in, gather=gather)
+            if gather and getattr(eng, "_pg", None) is not None:
+                eng._pg.wait_stream()  # the copies below read the gathered records: wait for the peers' stores
             if self._h_out[lane_id] is None:
                 self._h_out[lane_id] = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in res.items()}
             for k, v in res.items():
