@@ -232,7 +232,7 @@ class SABackboneNMS(torch.nn.Module):
         NCCL all_gather (TSMDET_GATHER=nccl, and whenever the IPC set-up fails -- every rank takes the same branch)."""
         if not hasattr(self, "_pg"):
             self._pg = None
-            want = os.environ.get("TSMDET_GATHER", "nccl") == "peer" and packed.is_cuda
+            want = os.environ.get("TSMDET_GATHER", "peer") == "peer" and packed.is_cuda
             ok = torch.zeros((1,), dtype=torch.int32, device=packed.device)
             if want:
                 try:

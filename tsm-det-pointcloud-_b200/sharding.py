@@ -132,10 +132,18 @@ class PeerGather:
             if r == self.rank:
                 pr, pf = self.recv, self.flags
             else:
+                # torch's rebuild would open the IPC handle in the context of the PRODUCER's device index; kernels on
+                # my device fault on such a mapping (measured, scripts/peer_diag.py).  Opening it with my own device
+                # current (argument 6 of rebuild_cuda_tensor = the device to open under) maps the peer's memory into my
+                # device's address space with peer access -- the pattern NCCL itself uses.
                 (f0, a0), (f1, a1) = handles[r]
-                pr, pf = f0(*a0), f1(*a1)
-                with torch.cuda.device(self.recv.device):  # kernels on MY device will store into the peer's memory
-                    _lib.call("tsmdet_enable_peer_access", pr.device.index)
+                a0, a1 = list(a0), list(a1)
+                assert isinstance(a0[6], int) and isinstance(a1[6], int), "unexpected torch IPC handle layout"
+                peer_dev = a0[6]
+                a0[6] = a1[6] = self.recv.device.index
+                with torch.cuda.device(self.recv.device):
+                    _lib.call("tsmdet_enable_peer_access", peer_dev)
+                    pr, pf = f0(*a0), f1(*a1)
             self._peers.append((pr, pf))
             rows[r] = pr.data_ptr() + self.rank * self.stride * 4
             flags[r] = pf.data_ptr() + self.rank * 8
