@@ -9,7 +9,8 @@ A "step" = one pass of the hot path over one batch of synthetic frames per GPU:
   config 2  KITTI SA stack 16384 -> 4096 -> 1024 -> 512 (radii 0.2/0.8/1.6, nsample 16/32/32,
             MLPs [4,16,16,32] [35,64,64,128] [131,128,128,256]), batch 16 frames per GPU, plus
   config 3  rotated NMS on 4096 proposals per frame, IoU 0.01 then 0.1 on the survivors; at N > 1 the
-            padded detections are all-gathered over NCCL (frames are sharded, weak scaling).
+            padded detections are gathered on every rank (frames are sharded, weak scaling): one kernel of
+            peer-memory stores per step by default, the NCCL all_gather with TSMDET_GATHER=nccl.
 Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
 through the host-buffer API (pinned H2D of the inputs + D2H of the results inside the timed region).
 """
