@@ -53,7 +53,8 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.skipif(torch.cuda.device_count() < 2 or os.environ.get("TSMDET_TEST_MULTI_GPU", "0") != "1",
+                    reason="needs two GPUs and TSMDET_TEST_MULTI_GPU=1 (bench.py checks the same equality at N > 1)")
 def test_peer_gather_equals_nccl_all_gather():
     world = 2
     ctx = mp.get_context("spawn")
