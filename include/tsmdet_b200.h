@@ -81,6 +81,14 @@ int tsmdet_gather_points_grad(int b, int c, int n, int npoints, const float* gra
  * pointnet2_modules.py:1143,1212-1215 in one pass. */
 int tsmdet_gather_xyz(int b, int n, int m, const float* xyz, const int* idx, float* out, void* stream);
 
+/* Input staging: the collated batch `points (b*n, 4+c)` = [batch_idx, x, y, z, features...], frame
+ * after frame with n points each, -> xyz (b,n,3) and features (b,c,n) [NULL when c == 0] in ONE pass; rows whose
+ * batch index is not their frame are counted into *bad (device i32, not cleared here; may be NULL).
+ * ref: pcdet/models/__init__.py:23-34 load_data_to_gpu; backbones_3d/pointnet2_backbone.py:796-800 break_up_pc,
+ *      :814-823 (count check, view, permute.contiguous); pointnet2_batch/pointnet2_modules.py:1143 */
+int tsmdet_stage_points(int b, int n, int c, const float* points, float* xyz, float* features, int* bad,
+                        void* stream);
+
 /* ---------------------------------------------------------------- ball query --------
  * new_xyz (B,M,3), xyz (B,N,3) -> idx_cnt (B,M) i32, idx (B,M,nsample) i32.
  * ref: pointnet2_api.cpp:11,13 ball_query_wrapper / ball_query_dilated_wrapper
@@ -130,6 +138,14 @@ int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_feat, int use_
                           const float* const* biases, float* out, int out_ctot, int out_c0, int precision,
                           void* stream);
 
+/* Point-wise shared MLP over dense tensors, no pooling: out[b, out_c0 + co, i] = MLP(cat(src0[b,:,i], src1[b,:,i]))
+ * with [1x1 conv (BN folded) + bias + ReLU] x num_layers.  src0 (B,c0,n), src1 (B,c1,n) | NULL (c1 = 0),
+ * channels[0] == c0 + c1, out (B,out_ctot,n).  precision as above.
+ * ref: pointnet2_modules.py:171,175-176 (PointnetFPModule: cat + mlp), :1320-1321 (aggregation_mlp) */
+int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
+                         const int* channels, const float* const* weights, const float* const* biases, float* out,
+                         int out_ctot, int out_c0, int precision, void* stream);
+
 /* ---------------------------------------------------------------- IoU / NMS ---------
  * boxes (N,7) f32 [x,y,z,dx,dy,dz,heading] on the device.
  * ref: iou3d_nms/src/iou3d_nms_api.cpp:12-13 boxes_overlap_bev_gpu / boxes_iou_bev_gpu
@@ -157,18 +173,36 @@ int tsmdet_nms_batch(int frames, int nmax, const float* boxes, int box_stride, c
 int tsmdet_nms_normal_batch(int frames, int nmax, const float* boxes, int box_stride, const int* counts, float thresh,
                             long long* keep, int* num_keep, void* stream);
 
-/* Detection gather without a rendezvous: store `numel` floats from `src` into rows[r] for r < world (row `rank` of
- * every rank's receive buffer, peers mapped through CUDA IPC), then publish the step number (++sync2[1]) into
- * flags[r].  sync2 = two zero-initialised device ints owned by the caller.  src and rows 16-byte aligned.
+/* Detection gather without a rendezvous, with credit-based flow control (csrc/peer_put.cu).  Every rank owns a ring
+ * of `slots` receive buffers, each `world` rows of `slot_stride / world` floats, plus a flag array and an ack array
+ * (world int64 words each), all mapped into every peer through CUDA IPC.  Step `step` (1, 2, ...) of this rank:
+ *   - stores step-1 into peer_acks[r] for r < world ("this rank has consumed every earlier step": the call is
+ *     stream-ordered after the caller's reads of the previous step),
+ *   - waits until my_acks[r] >= step - slots for every r (the slot about to be overwritten has been released),
+ *   - stores `numel` floats from `src` into rows[r] + ((step-1) % slots) * slot_stride for r < world,
+ *   - publishes `step` into flags[r].
+ * rows[r] = row `rank` of slot 0 of rank r's ring; flags[r] / peer_acks[r] = word `rank` of rank r's flag / ack array;
+ * my_acks = this rank's own ack array; sync2 = two zero-initialised device ints owned by the caller.  src and rows
+ * 16-byte aligned.  timeout_ns <= 0: 120 s.  A wait that times out records TSMDET_ERR_WATCHDOG in the status word
+ * (tsmdet_read_status) and skips the stores; it never traps.
  * ref: replaces pcdet/utils/common_utils.py:224-245 merge_results_dist (pickle files + barriers). */
-int tsmdet_peer_put(const float* src, long long numel, int world, void* const* rows, void* const* flags, int* sync2,
-                    void* stream);
+int tsmdet_peer_put(const float* src, long long numel, int world, void* const* rows, void* const* flags,
+                    void* const* peer_acks, const long long* my_acks, int* sync2, long long step, int slots,
+                    long long slot_stride, long long timeout_ns, void* stream);
 /* Enables access from the current device to memory on `peer_device` (needed before kernels store into IPC-mapped
  * peer buffers); already-enabled is not an error. */
 int tsmdet_enable_peer_access(int peer_device);
-/* Consumer side, stream-ordered: returns once this rank's flag words (world of them) have all reached `want`
- * (want < 0: the step of this rank's last tsmdet_peer_put on the same stream, read from sync2[1]). */
-int tsmdet_peer_wait(const long long* flags, int world, const int* sync2, long long want, void* stream);
+/* Consumer side, stream-ordered: returns once this rank's flag words (world of them) have all reached `want`, i.e.
+ * every rank's records of step `want` are complete in slot (want-1) % slots.  Times out like tsmdet_peer_put. */
+int tsmdet_peer_wait(const long long* flags, int world, long long want, int slots, long long timeout_ns, void* stream);
+
+/* ---------------------------------------------------------------- runtime -----------
+ * TSMDET_* tuning knobs are read from the environment once, at first use; this re-reads them. */
+int tsmdet_reload_options(void);
+/* Stream-ordered scratch pool: bytes in live buffers / in retired (outgrown or evicted) ones; trim frees the
+ * retired ones (the caller guarantees no CUDA graph captured before the call is replayed after it). */
+int tsmdet_scratch_stats(long long* live_bytes, long long* retired_bytes);
+int tsmdet_scratch_trim(void);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,35 @@ def build(verbose: bool = False) -> dict:
     return res
 
 
+# The reference's Python op wrappers (the drop-in boundary's CALLERS), byte-compiled where they lie: the .pyc files
+# are build products like the .so files above (no source is copied), they travel to the GPU box, and
+# tests/test_dropin_reference_py_gpu.py runs them UNMODIFIED over this repo's pybind-name shims.
+PY_FILES = {
+    "pcdet.ops.pointnet2.pointnet2_batch.pointnet2_utils": "pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py",
+    "pcdet.ops.iou3d_nms.iou3d_nms_utils": "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
+    "pcdet.models.model_utils.model_nms_utils": "pcdet/models/model_utils/model_nms_utils.py",
+}
+
+
+def pyc_path(modname: str) -> str:
+    return os.path.join(OUT, "pyc", modname + ".pyc")
+
+
+def build_py() -> dict:
+    """Byte-compile the reference's three Python op files into oracle/_ref/pyc/ (sourceless, unmodified)."""
+    import py_compile
+
+    res = {}
+    for mod, rel in PY_FILES.items():
+        dst = pyc_path(mod)
+        src = os.path.join(REF_ROOT, rel)
+        if os.path.exists(src):
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            py_compile.compile(src, cfile=dst, dfile=rel, doraise=True)
+        res[mod] = dst if os.path.exists(dst) else None
+    return res
+
+
 def load_ref(name: str):
     """Import a built reference extension as a Python module (or None)."""
     p = built(name)
@@ -98,5 +127,6 @@ def load_ref(name: str):
 
 if __name__ == "__main__":
     out = build(verbose="-v" in sys.argv)
+    out.update(build_py())
     print(out)
     sys.exit(0 if all(out.values()) else 1)

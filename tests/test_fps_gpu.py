@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 import pytest
+from conftest import knob_delenv, knob_setenv
 import torch
 
 import synth
@@ -48,7 +49,7 @@ CASES = [
 def test_fps_matches_oracle(orc, name, gen, m, algo, monkeypatch):
     """Both d-FPS kernels: the cluster kernel (fps.cu) and the spatially pruned single-CTA kernel
     (fps_bucket.cu; clouds above 16384 points stay on the cluster kernel)."""
-    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
     xyz = gen()
     got = _fps(xyz, m)
     want = orc.fps(xyz, m)
@@ -58,9 +59,9 @@ def test_fps_matches_oracle(orc, name, gen, m, algo, monkeypatch):
 @pytest.mark.parametrize("threads,pts", [(32, 4), (64, 32), (128, 8), (256, 16), (512, 8), (512, 32), (1024, 4), (1024, 16)])
 def test_fps_bucket_every_launch_shape(orc, threads, pts, monkeypatch):
     """Threads x points-per-lane only changes which lane owns which (spatially sorted) point, never a pick."""
-    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
-    monkeypatch.setenv("TSMDET_FPSB_T", str(threads))
-    monkeypatch.setenv("TSMDET_FPSB_P", str(pts))
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", "bucket")
+    knob_setenv(monkeypatch, "TSMDET_FPSB_T", str(threads))
+    knob_setenv(monkeypatch, "TSMDET_FPSB_P", str(pts))
     cap = threads * pts
     for xyz, m in [(synth.cloud_dup_padded(2, min(cap, 4096), 20 + pts), 300),
                    (synth.cloud_lattice(3, min(cap, 2500) - 3, 30 + pts), 120),
@@ -72,7 +73,7 @@ def test_fps_bucket_every_launch_shape(orc, threads, pts, monkeypatch):
 def test_fps_bucket_degenerate_clouds(orc, monkeypatch):
     """Grid construction edge cases: zero extent on one, two or all axes; clouds spanning huge ranges; exact
     duplicates only; initial min-distances handed in through temp."""
-    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", "bucket")
     rng = np.random.default_rng(7)
     flat = synth.cloud_uniform(2, 3000, 61)
     flat[:, :, 2] = 1.5
@@ -92,7 +93,7 @@ def test_fps_bucket_degenerate_clouds(orc, monkeypatch):
     temp = torch.from_numpy(t0.copy()).to(_dev())
     idx = torch.zeros((2, 200), dtype=torch.int32, device=_dev())
     ext.farthest_point_sampling_wrapper(2, 6000, 200, x, temp, idx)
-    monkeypatch.setenv("TSMDET_FPS_ALGO", "cluster")
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", "cluster")
     temp2 = torch.from_numpy(t0.copy()).to(_dev())
     idx2 = torch.zeros((2, 200), dtype=torch.int32, device=_dev())
     ext.farthest_point_sampling_wrapper(2, 6000, 200, x, temp2, idx2)
@@ -106,8 +107,8 @@ def test_fps_bucket_multi_pick_rounds(orc, picks, monkeypatch):
     provably the pick the one-at-a-time algorithm would make next, so K never changes an index: duplicate-heavy
     clouds (runner-up keys equal to the candidate's), lattices (key ties across warps, resolved by reference rank),
     clouds with fewer distinct points than picks, initial min-distances from temp, and the chained bookkeeping."""
-    monkeypatch.setenv("TSMDET_FPS_ALGO", "bucket")
-    monkeypatch.setenv("TSMDET_FPSB_K", str(picks))
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", "bucket")
+    knob_setenv(monkeypatch, "TSMDET_FPSB_K", str(picks))
     for name, xyz, m in [("dup16384", synth.cloud_dup_padded(2, 16384, 70), 2048),
                          ("obj16384", synth.cloud_ground_objects(1, 16384, 71), 4096),
                          ("lattice16384", synth.cloud_lattice(1, 16384, 72), 1500),
@@ -127,7 +128,7 @@ def test_fps_bucket_multi_pick_rounds(orc, picks, monkeypatch):
     x = torch.from_numpy(xyz).to(_dev())
     out = {}
     for algo in ("bucket", "cluster"):
-        monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+        knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
         temp = torch.from_numpy(t0.copy()).to(_dev())
         idx = torch.zeros((2, 700), dtype=torch.int32, device=_dev())
         ext.farthest_point_sampling_wrapper(2, 16000, 700, x, temp, idx)
@@ -140,8 +141,8 @@ def test_fps_bucket_multi_pick_rounds(orc, picks, monkeypatch):
 @pytest.mark.parametrize("threads", [128, 256, 512, 1024])
 def test_fps_every_launch_shape(orc, csize, threads, monkeypatch):
     """The cluster size / block size only changes who computes what, never the result."""
-    monkeypatch.setenv("TSMDET_FPS_CLUSTER", str(csize))
-    monkeypatch.setenv("TSMDET_FPS_THREADS", str(threads))
+    knob_setenv(monkeypatch, "TSMDET_FPS_CLUSTER", str(csize))
+    knob_setenv(monkeypatch, "TSMDET_FPS_THREADS", str(threads))
     for xyz, m in [(synth.cloud_dup_padded(2, 4096, 20 + csize), 300), (synth.cloud_lattice(3, 2500, 30 + csize), 257)]:
         got = _fps(xyz, m)
         assert np.array_equal(got, orc.fps(xyz, m))
@@ -149,7 +150,7 @@ def test_fps_every_launch_shape(orc, csize, threads, monkeypatch):
 
 @pytest.mark.parametrize("algo", ["cluster", "bucket"])
 def test_fps_kitti_full_size(orc, algo, monkeypatch):
-    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
     _fps_kitti_full_size(orc)
 
 
@@ -179,7 +180,7 @@ def test_fps_large_clouds(orc):
 
 @pytest.mark.parametrize("algo", ["cluster", "bucket"])
 def test_fps_temp_scratch_contract(orc, algo, monkeypatch):
-    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
     _fps_temp_scratch_contract(orc)
 
 
@@ -213,9 +214,9 @@ def test_fps_bucket_cluster_equals_cluster_kernel(name, gen, n, m, monkeypatch):
     outs = []
     for algo in ("cluster", None):
         if algo:
-            monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+            knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
         else:
-            monkeypatch.delenv("TSMDET_FPS_ALGO", raising=False)
+            knob_delenv(monkeypatch, "TSMDET_FPS_ALGO", raising=False)
         temp = torch.full((2, n), 1e10, device=_dev())
         idx = torch.zeros((2, m), dtype=torch.int32, device=_dev())
         ext.farthest_point_sampling_wrapper(2, n, m, xyz, temp, idx)
@@ -287,7 +288,7 @@ def test_fps_golden():
 ], ids=["objects", "dup", "lattice", "few_unique"])
 @pytest.mark.parametrize("algo", ["cluster", "bucket"])
 def test_fps_chained_levels_match_plain_fps(orc, name, gen, shortcut, algo, monkeypatch):
-    monkeypatch.setenv("TSMDET_FPS_ALGO", algo)
+    knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
     _fps_chained_levels(orc, name, gen, shortcut)
 
 

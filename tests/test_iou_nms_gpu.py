@@ -8,6 +8,7 @@ import os
 
 import numpy as np
 import pytest
+from conftest import knob_delenv, knob_setenv
 import torch
 
 import synth
@@ -233,9 +234,9 @@ def test_lazy_nms_equals_full_mask_nms(thresh, monkeypatch):
     scores = torch.from_numpy(np.stack([rng.permutation(4096).astype(np.float32) for _ in range(6)])).to(dev)
     scores = torch.where(torch.arange(4096, device=dev).unsqueeze(0) < counts.unsqueeze(1), scores,
                          torch.full_like(scores, float("-inf")))
-    monkeypatch.setenv("TSMDET_NMS_ALGO", "mask")
+    knob_setenv(monkeypatch, "TSMDET_NMS_ALGO", "mask")
     want_sel, want_num = iu.nms_gpu_batch(boxes, scores, thresh, counts=counts)
-    monkeypatch.delenv("TSMDET_NMS_ALGO")
+    knob_delenv(monkeypatch, "TSMDET_NMS_ALGO")
     got_sel, got_num = iu.nms_gpu_batch(boxes, scores, thresh, counts=counts)
     assert torch.equal(got_num, want_num)
     assert torch.equal(got_sel, want_sel)

@@ -2,6 +2,7 @@
 and their backward kernels, through the C ABI, vs the CPU oracle (bit-exact) and oracle/_ref."""
 import numpy as np
 import pytest
+from conftest import knob_delenv, knob_setenv
 import torch
 
 import synth
@@ -37,7 +38,7 @@ def test_ball_query(orc, case, algo, monkeypatch):
     usable) and the brute-force kernels (ball_query.cu), against the oracle."""
     from tsmdet_b200 import pointnet2_utils as pu
 
-    monkeypatch.setenv("TSMDET_BQ_ALGO", algo)
+    knob_setenv(monkeypatch, "TSMDET_BQ_ALGO", algo)
 
     b, n, m, rin, r, ns, gen = case
     xyz = gen(b, n, 7)
@@ -97,11 +98,15 @@ def test_ball_query_waymo_scale(orc):
     cnt, idx = pu.ball_query(0.8, 32, T(xyz), T(new_xyz))
     wc, wi = orc.ball_query(0.8, 32, xyz[:1], new_xyz[:1])
     assert np.array_equal(cnt[:1].cpu().numpy(), wc) and np.array_equal(idx[:1].cpu().numpy(), wi)
+    from tsmdet_b200 import _lib
+
     os.environ["TSMDET_BQ_ALGO"] = "brute"
+    _lib.reload_options()
     try:
         c2, i2 = pu.ball_query(0.8, 32, T(xyz), T(new_xyz))
     finally:
         os.environ.pop("TSMDET_BQ_ALGO")
+        _lib.reload_options()
     assert torch.equal(cnt, c2) and torch.equal(idx, i2)
 
 
@@ -217,9 +222,9 @@ def test_three_nn_grid_equals_brute_force(orc, monkeypatch):
     w_unknown = synth.cloud_uniform(2, 65536, 51, synth.WAYMO_RANGE)
     cases.append(("waymo", w_unknown, np.ascontiguousarray(w_unknown[:, ::4, :])))
     for name, unknown, known in cases:
-        monkeypatch.setenv("TSMDET_NN_ALGO", "brute")
+        knob_setenv(monkeypatch, "TSMDET_NN_ALGO", "brute")
         d0, i0 = pu.three_nn(T(unknown), T(known))
-        monkeypatch.delenv("TSMDET_NN_ALGO")
+        knob_delenv(monkeypatch, "TSMDET_NN_ALGO")
         d1, i1 = pu.three_nn(T(unknown), T(known))
         assert torch.equal(i0, i1), name
         assert torch.equal(d0.view(torch.int32), d1.view(torch.int32)), name

@@ -55,6 +55,7 @@ SIGNATURES = {
     "tsmdet_gather_points": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_gather_points_grad": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_gather_xyz": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "tsmdet_stage_points": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_ball_query": [c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_ball_query_dilated": [c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p],
@@ -67,6 +68,8 @@ SIGNATURES = {
     "tsmdet_three_interpolate_grad": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_sa_mlp_maxpool": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, _i, _pp, _pp, c_void_p, c_int, c_int, c_int, c_void_p],
+    "tsmdet_pointwise_mlp": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, _i, _pp, _pp, c_void_p, c_int, c_int,
+                             c_int, c_void_p],
     "tsmdet_boxes_overlap_bev": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "tsmdet_boxes_iou_bev": [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "tsmdet_boxes_iou_bev_cpu": [c_int, c_void_p, c_int, c_void_p, c_void_p],
@@ -74,8 +77,12 @@ SIGNATURES = {
     "tsmdet_nms_normal_gpu": [c_int, c_void_p, c_float, c_void_p, _i, c_void_p],
     "tsmdet_nms_batch": [c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
     "tsmdet_nms_normal_batch": [c_int, c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
-    "tsmdet_peer_put": [c_void_p, c_longlong, c_int, _pp, _pp, c_void_p, c_void_p],
-    "tsmdet_peer_wait": [c_void_p, c_int, c_void_p, c_longlong, c_void_p],
+    "tsmdet_peer_put": [c_void_p, c_longlong, c_int, _pp, _pp, _pp, c_void_p, c_void_p, c_longlong, c_int, c_longlong,
+                        c_longlong, c_void_p],
+    "tsmdet_peer_wait": [c_void_p, c_int, c_longlong, c_int, c_longlong, c_void_p],
+    "tsmdet_reload_options": [],
+    "tsmdet_scratch_stats": [_ll, _ll],
+    "tsmdet_scratch_trim": [],
     "tsmdet_enable_peer_access": [c_int],
 }
 _RESTYPES = {"tsmdet_version": c_char_p, "tsmdet_error_string": c_char_p}
@@ -109,9 +116,20 @@ def check(status: int, where: str) -> None:
 KERNELS_PER_CALL = {
     "tsmdet_nms_batch": 6, "tsmdet_nms_normal_batch": 3, "tsmdet_nms_gpu": 6, "tsmdet_nms_normal_gpu": 3,
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
-    "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_enable_peer_access": 0, "tsmdet_read_status": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3,
+    "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_enable_peer_access": 0, "tsmdet_read_status": 0,
+    "tsmdet_reload_options": 0, "tsmdet_scratch_stats": 0, "tsmdet_scratch_trim": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3, "tsmdet_pointwise_mlp": 2,
 }
 launch_count = 0
+
+
+def read_status() -> int:
+    """Reads and clears the per-device watchdog word (0 = clean); works after a kernel fault (host-mapped word)."""
+    return int(_lib.tsmdet_read_status())
+
+
+def reload_options() -> None:
+    """Re-read the TSMDET_* tuning knobs from os.environ (the library reads them once, at first use)."""
+    check(_lib.tsmdet_reload_options(), "tsmdet_reload_options")
 
 
 def call(name: str, *args) -> None:

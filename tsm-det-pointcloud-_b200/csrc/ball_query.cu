@@ -339,7 +339,7 @@ static int run_ball_query(bool dilated, int b, int n, int m, float rin, float ro
     // (flagged on the device; they exit at once for the others).  TSMDET_BQ_ALGO=brute disables the grid.
     const int* ghdr = nullptr;
     {
-        const char* algo = getenv("TSMDET_BQ_ALGO");
+        const char* algo = tsm_knob(KNOB_BQ_ALGO);
         if (n >= 512 && !(algo && !strcmp(algo, "brute"))) {
             const int rc = tsm_ball_query_grid(dilated, b, n, m, rin, rout, nsample, new_xyz, xyz, idx_cnt, idx, stream,
                                                &ghdr);

@@ -130,10 +130,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                  : "memory");
 }
 
-// Watchdog for every in-kernel wait: a mis-programmed barrier must end the
-// kernel (trap) rather than hang the GPU.
+// Watchdog for every INTRA-GPU in-kernel wait (mbarrier phases of one kernel): a mis-programmed barrier must
+// end the kernel (trap) rather than hang the GPU.  The status word is host-mapped, so the code survives the
+// trap.  (Waits on OTHER ranks -- peer_put.cu -- never trap: they record the code and return.)
 __device__ __forceinline__ void watchdog_trip(int* status, int code) {
-    if (status) atomicExch(status, code);
+    if (status) *reinterpret_cast<volatile int*>(status) = code;
     __threadfence_system();
     __trap();
 }
@@ -144,6 +145,16 @@ __host__ __device__ __forceinline__ int divup(int a, int b) { return (a + b - 1)
 
 // Host-side: number of SMs of the current device (cached).
 int tsm_num_sms();
-int* tsm_status_word(cudaStream_t stream);  // device int, zero-initialised, one per process
+int* tsm_status_word(cudaStream_t stream);  // device address of a host-mapped int, zero-initialised, one per device
+
+// TSMDET_* tuning knobs, captured from the environment once (runtime.cu); nullptr = unset.
+enum TsmKnob {
+    KNOB_BQ_ALGO, KNOB_FPS_CLUSTER, KNOB_FPS_THREADS, KNOB_FPS_ALGO, KNOB_FPSB_T,
+    KNOB_FPSB_P, KNOB_FPSB_K, KNOB_GROUP_SLAB_KB, KNOB_GROUP_WAVES, KNOB_GROUP_DIRECT,
+    KNOB_NN_ALGO, KNOB_NMS_CTAS_PER_SM, KNOB_NMS_ALGO, KNOB_MLP_ONE_GROUP, KNOB_MLP_OCC,
+    KNOB_MLP_V1, KNOB_FPSC_K, KNOB_VOXEL_ALGO,
+    KNOB_COUNT
+};
+const char* tsm_knob(int id);
 // Stream-ordered grow-only scratch, keyed by (device, stream, tag): tag 0 = IoU/NMS, 1 = SA MLP.
 int tsm_scratch_get(int tag, size_t bytes, cudaStream_t stream, void** out);

@@ -504,8 +504,8 @@ static bool plan_fps(int b, int n, int log2bs, bool weighted, bool query_occupan
     int cmax = 1;
     while (cmax * 2 <= 8 && b * cmax * 2 <= sms) cmax *= 2;
     int want_c = 0, want_t = 0;
-    if (const char* e = getenv("TSMDET_FPS_CLUSTER")) want_c = atoi(e);
-    if (const char* e = getenv("TSMDET_FPS_THREADS")) want_t = atoi(e);
+    if (const char* e = tsm_knob(KNOB_FPS_CLUSTER)) want_c = atoi(e);
+    if (const char* e = tsm_knob(KNOB_FPS_THREADS)) want_t = atoi(e);
     if (want_t != 128 && want_t != 256 && want_t != 512 && want_t != 1024) want_t = 0;
     const bool forced = (want_c == 1 || want_c == 2 || want_c == 4 || want_c == 8 || want_c == 16);
     int order[8], no = 0;
@@ -565,8 +565,8 @@ static int run_fps(int b, int n, int m, const float* xyz, const float* weights, 
     // cluster launch shape (tuning / tests) implies "cluster".
     {
         int algo = g_fps_algo;
-        if (const char* e = getenv("TSMDET_FPS_ALGO")) algo = !strcmp(e, "cluster") ? 1 : (!strcmp(e, "bucket") ? 2 : algo);
-        if (getenv("TSMDET_FPS_CLUSTER") || getenv("TSMDET_FPS_THREADS")) algo = 1;
+        if (const char* e = tsm_knob(KNOB_FPS_ALGO)) algo = !strcmp(e, "cluster") ? 1 : (!strcmp(e, "bucket") ? 2 : algo);
+        if (tsm_knob(KNOB_FPS_CLUSTER) || tsm_knob(KNOB_FPS_THREADS)) algo = 1;
         const bool fits = tsm_fps_bucket_supports(n, weights != nullptr);
         const bool crowded = (long)b * 8 > tsm_num_sms();
         if (fits && (algo == 2 || (algo == 0 && crowded && n >= 1024))) return tsm_fps_bucket_launch(a, b, stream);

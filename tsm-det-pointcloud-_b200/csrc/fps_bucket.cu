@@ -808,8 +808,8 @@ int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
     const int n = a.n;
     if (!tsm_fps_bucket_supports(n, a.weights != nullptr)) return TSM_ERR_INVALID;
     int T = 0, P = 0;
-    if (const char* e = getenv("TSMDET_FPSB_T")) T = atoi(e);
-    if (const char* e = getenv("TSMDET_FPSB_P")) P = atoi(e);
+    if (const char* e = tsm_knob(KNOB_FPSB_T)) T = atoi(e);
+    if (const char* e = tsm_knob(KNOB_FPSB_P)) P = atoi(e);
     if (P != 4 && P != 8 && P != 16 && P != 32) P = 0;
     if (T != 32 && T != 64 && T != 128 && T != 256 && T != 512 && T != 1024) T = 0;
     if (T && P && (long)T * P < n) T = P = 0;
@@ -834,7 +834,7 @@ int tsm_fps_bucket_launch(const tsm::FpsArgs& a, int b, cudaStream_t stream) {
     // for clouds of 8193..16384 points (1024 x 16: 2.74 -> 1.80 ms at 16384 -> 4096, 2.04 ms on duplicate-padded
     // clouds); smaller clouds keep one pick per barrier.  TSMDET_FPSB_K = 1 | 2 | 4 | 8 overrides.
     int K = (T == 1024 && P == 16) ? 8 : 1;
-    if (const char* e = getenv("TSMDET_FPSB_K")) K = atoi(e);
+    if (const char* e = tsm_knob(KNOB_FPSB_K)) K = atoi(e);
 #define FPSB_CASE(TT, PP)                                                               \
     if (T == TT && P == PP) return tsm::launch_bucket_k<TT, PP>(a, b, cell_bits, stream, K);
 #define FPSB_CASE_K(TT, PP)                                                             \

@@ -217,7 +217,7 @@ static bool launch_group_staged(int b, int c, int n, long e, const float* points
     if ((n & 3) || (e & 3) || !aligned16(points) || !aligned16(idx) || !aligned16(out) || e < 4096 || b > 65535) return false;
     if ((size_t)n * 4 > 96 * 1024) return false;  // a row must leave room for two CTAs per SM
     size_t slab_cap = 32 * 1024;  // measured: 16..32 KB slabs (5-6 CTAs per SM) beat larger ones
-    if (const char* e = getenv("TSMDET_GROUP_SLAB_KB")) slab_cap = (size_t)atoi(e) * 1024;
+    if (const char* e = tsm_knob(KNOB_GROUP_SLAB_KB)) slab_cap = (size_t)atoi(e) * 1024;
     int cc = 1;
     while (cc * 2 <= c && (size_t)cc * 2 * n * 4 <= slab_cap) cc *= 2;
     const int cchunks = divup(c, cc);
@@ -225,7 +225,7 @@ static bool launch_group_staged(int b, int c, int n, long e, const float* points
     const size_t dyn = (size_t)cc * n * 4;
     const int resident = (int)((227 * 1024) / (dyn + 1024));
     int waves = 4;
-    if (const char* e = getenv("TSMDET_GROUP_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 4;
+    if (const char* e = tsm_knob(KNOB_GROUP_WAVES)) waves = atoi(e) > 0 ? atoi(e) : 4;
     long want = (long)tsm_num_sms() * (resident > 8 ? 8 : resident) * waves;  // about two waves
     long echunks = divup((int)want, b * cchunks);
     const long emax = e / 2048 > 0 ? e / 2048 : 1;
@@ -257,7 +257,7 @@ int tsmdet_group_points(int b, int c, int n, int npoints, int nsample, const flo
     const bool vec = (e % 4 == 0) && tsm::aligned16(idx) && tsm::aligned16(out);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = TSM_OK;
-    if (!getenv("TSMDET_GROUP_DIRECT") && tsm::launch_group_staged(b, c, n, e, points, idx, out, c, 0, s, &rc)) return rc;
+    if (!tsm_knob(KNOB_GROUP_DIRECT) && tsm::launch_group_staged(b, c, n, e, points, idx, out, c, 0, s, &rc)) return rc;
     if (vec) {
         dim3 grid((unsigned)tsm::divup((int)(e / 4), tsm::GP_THREADS), (unsigned)b);
         tsm::group_points_kernel<4><<<grid, tsm::GP_THREADS, 0, s>>>(c, n, (int)e, points, idx, out);
@@ -290,7 +290,7 @@ int tsmdet_group_concat(int b, int c, int n, int m, int nsample, int use_xyz, co
                      (!grouped_xyz || tsm::aligned16(grouped_xyz));
     cudaStream_t s = (cudaStream_t)stream;
     const int ctot = (use_xyz ? 3 : 0) + (features ? c : 0);
-    if (features && new_features && c >= 8 && !getenv("TSMDET_GROUP_DIRECT")) {
+    if (features && new_features && c >= 8 && !tsm_knob(KNOB_GROUP_DIRECT)) {
         // many feature channels: the staged gather fills channels [3*use_xyz, ...) and the fused kernel below only
         // writes the coordinate offsets
         int rc = TSM_OK;

@@ -144,7 +144,7 @@ int tsmdet_three_nn(int b, int n, int m, const float* unknown, const float* know
     // the brute-force kernel then only serves clouds whose grid was unusable.  TSMDET_NN_ALGO=brute disables it.
     const int* ghdr = nullptr;
     {
-        const char* algo = getenv("TSMDET_NN_ALGO");
+        const char* algo = tsm_knob(KNOB_NN_ALGO);
         if (m >= 512 && !(algo && !strcmp(algo, "brute"))) {
             const int rc = tsm_three_nn_grid(b, n, m, unknown, known, dist2, idx, (cudaStream_t)stream, &ghdr);
             if (rc != TSM_OK) return rc;

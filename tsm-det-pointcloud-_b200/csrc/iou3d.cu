@@ -788,7 +788,7 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     if (nmax > 65535) return TSM_ERR_INVALID;  // queue entries pack (row, col) into 16 + 16 bits
     const long tiles = (long)cbmax * (cbmax + 1) / 2;
     int ctas_per_sm = 2;
-    if (const char* e = getenv("TSMDET_NMS_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
+    if (const char* e = tsm_knob(KNOB_NMS_CTAS_PER_SM)) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 2;
     int per_frame = (ctas_per_sm * tsm_num_sms() + frames - 1) / frames;  // CTAs per SM in total
     if (per_frame < 1) per_frame = 1;
     // rotated NMS with a sane threshold: spatial-grid candidates; the all-pairs tile kernel then only serves
@@ -796,7 +796,7 @@ int nms_batch_impl(bool normal, int frames, int nmax, const float* boxes, int bo
     // every pair matters and only the tile kernel is exact.
     const bool use_grid = !normal && (thresh >= 0.f);
     const size_t lazy_dyn = (size_t)(65) * cbmax * sizeof(unsigned long long);
-    const char* algo = getenv("TSMDET_NMS_ALGO");  // "mask": always build the full mask (tuning / tests)
+    const char* algo = tsm_knob(KNOB_NMS_ALGO);  // "mask": always build the full mask (tuning / tests)
     const bool lazy = use_grid && lazy_dyn <= 160 * 1024 && !(algo && !strcmp(algo, "mask"));
     if (!lazy) TSM_CUDA_TRY(cudaMemsetAsync(mask, 0, mask_bytes, s));
     if (use_grid) {

@@ -1,0 +1,576 @@
+// mlp_tc2.cu -- second-generation tcgen05 shared-MLP kernel: the fused set-abstraction scale (gather -> mask ->
+// [1x1 conv + ReLU]* -> max over nsample; /root/reference/pcdet/ops/pointnet2/pointnet2_batch/pointnet2_modules.py:
+// 1259-1268, 1297-1300) and the point-wise MLPs of the same file (PointnetFPModule.mlp :175-176, aggregation_mlp
+// :1320-1321: [1x1 conv + ReLU]* over a dense (B,C,n) tensor, no pooling) in one template.
+//
+// What changed against sa_mlp_tc.cu (kept for output widths < 64 and nsample < 8), and why -- ncu of round 1 showed
+// the tensor pipe 14 % active with each tile spending most of its time in the epilogues:
+//
+//  * THE LAST LAYER IS COMPUTED TRANSPOSED.  Both operands are K-major core-matrix images in shared memory, so the
+//    roles can be swapped for free: D^T[channel, row] = W_last (A operand, M = 128 output channels per block) x
+//    activations (B operand, N = the tile's 128 rows).  In TMEM a lane is now an output CHANNEL and the columns are the
+//    tile's rows, i.e. the nsample rows of a centre are consecutive columns of ONE thread: the max-pool is an
+//    in-register FMNMX3 tree (16 instructions per 32 samples) instead of one REDUX.SYNC per channel per warp
+//    (256 warp collectives per tile at 256 channels), and bias + ReLU run once per centre AFTER the pool (both are
+//    monotone, so max(relu(x+b)) == relu(max(x)+b) bit for bit) instead of once per row.  The dense mode uses the
+//    same layout to write 512 contiguous bytes per thread.
+//  * epilogues keep several tcgen05.ld in flight per wait::ld (two 32-column loads instead of one 16-column load),
+//    add the bias with packed FADD2 and convert with F2FP.RELU (ReLU for free);
+//  * the gather has every 16-byte load of a row in flight at once and the next tile's indices are prefetched while
+//    the current tile computes; one group barrier per layer (three per tile at three layers, five before).
+//
+// One CTA = GROUPS x 128 threads; a group = one independent 128-row tile pipeline (own operand buffer, TMEM
+// columns, mbarrier, named barrier) over the CTA's resident weights, persistent over tiles.
+#include "sa_mlp.cuh"
+#include "umma.cuh"
+
+namespace tsm {
+
+constexpr int T2_ROWS = 128;
+constexpr int T2_THREADS = 128;
+constexpr int T2_MAX_LAYERS = 4;
+
+struct Tc2Plan {
+    int nl;
+    int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of 16)
+    int Npad[T2_MAX_LAYERS];   // rows of layer l's weight image: cout padded to 16 (last layer: to 128)
+    int w_off[T2_MAX_LAYERS];  // byte offset of layer l's weights in dynamic smem
+    int b_off[T2_MAX_LAYERS];  // byte offset of layer l's bias (fp32)
+    int a_off, a_bytes;        // activation operand buffers (one per tile group)
+    int smem_bytes, packed_bytes;
+    int cp;                    // SA mode: feature channels padded to 8 (width of the bf16 transpose)
+    int xyz_chunk;             // SA mode: 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
+    int grp_cols, tmem_cols;   // TMEM columns of one tile group / of the CTA (power of two >= 32)
+    int mb;                    // 128-channel blocks of the (transposed) last layer
+};
+
+// Weights (cout,cin) fp32 + bias -> the kernel's shared-memory image: per layer bf16 [K/8][Npad][8] (UMMA K-major core
+// matrices), then the fp32 biases.  SA mode: layer 0's input channels are permuted to the operand order
+// [features 0..C-1 | pad to cp | dx,dy,dz | pad] (reference order: [dx,dy,dz, features...], pointnet2_utils.py:523).
+__global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, const Tc2Plan pl, const int dense,
+                                                            unsigned char* __restrict__ packed) {
+    const int l = blockIdx.y;
+    const int K = pl.K[l], Np = pl.Npad[l];
+    const int cin = a.ch[l], cout = a.ch[l + 1];
+    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(packed + pl.w_off[l]);
+    const float* __restrict__ W = a.w[l];
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * K; e += gridDim.x * 256) {
+        const int k = e / Np, n = e - k * Np;  // consecutive threads -> consecutive n: 16-byte-strided writes
+        float v = 0.f;
+        if (n < cout) {
+            int src = -1;
+            if (l == 0 && !dense) {
+                if (k < a.c_feat)
+                    src = (a.use_xyz ? 3 : 0) + k;
+                else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
+                    src = k - pl.xyz_chunk * 8;
+            } else if (k < cin) {
+                src = k;
+            }
+            if (src >= 0) v = __ldg(W + (size_t)n * cin + src);
+        }
+        ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    }
+    float* bs = reinterpret_cast<float*>(packed + pl.b_off[l]);
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
+}
+
+// features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels
+__global__ void __launch_bounds__(256) transpose2_bf16_kernel(int c, int cp, int n, const float* __restrict__ f,
+                                                              __nv_bfloat16* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float* src = f + (size_t)b * c * n + i;
+    __nv_bfloat16* dst = out + ((size_t)b * n + i) * cp;
+    for (int c0 = 0; c0 < cp; c0 += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ca = c0 + 2 * j, cb = ca + 1;
+            const float x = ca < c ? __ldg(src + (size_t)ca * n) : 0.f;
+            const float y = cb < c ? __ldg(src + (size_t)cb * n) : 0.f;
+            w[j] = pack_bf16(x, y);
+        }
+        *reinterpret_cast<uint4*>(dst + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// bias + ReLU + bf16 pack of NC accumulator columns of this thread's row -> NC/8 chunks of the next layer's A operand
+template <int NC>
+__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], const float* __restrict__ bias, unsigned char* dst) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+        const float2 s0 = add2(make_float2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), make_float2(b0.x, b0.y));
+        const float2 s1 = add2(make_float2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])), make_float2(b0.z, b0.w));
+        const float2 s2 = add2(make_float2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), make_float2(b1.x, b1.y));
+        const float2 s3 = add2(make_float2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])), make_float2(b1.z, b1.w));
+        *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) =
+            make_uint4(pack_bf16_relu(s0.x, s0.y), pack_bf16_relu(s1.x, s1.y), pack_bf16_relu(s2.x, s2.y), pack_bf16_relu(s3.x, s3.y));
+    }
+}
+
+// max over W consecutive registers starting at v[O] (W = 8, 16 or 32), FMNMX3 tree
+template <int O, int W>
+__device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
+    float m = max3(__uint_as_float(v[O]), __uint_as_float(v[O + 1]), __uint_as_float(v[O + 2]));
+#pragma unroll
+    for (int j = 3; j + 1 < W; j += 2) m = max3(m, __uint_as_float(v[O + j]), __uint_as_float(v[O + j + 1]));
+    if ((W & 1) == 0) m = fmaxf(m, __uint_as_float(v[O + W - 1]));
+    return m;
+}
+
+// GROUPS: tile pipelines per CTA.  SC = min(nsample, 32) in SA mode (8, 16 or 32).  DENSE: point-wise MLP over
+// (B,C,n) inputs (features = source 0, src1 = source 1, concatenated along channels), no pooling.
+template <int GROUPS, int SC, bool DENSE>
+__global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
+    mlp_tc2_kernel(const SaMlpArgs a, const Tc2Plan pl, const __nv_bfloat16* __restrict__ featT,
+                   const unsigned char* __restrict__ packed, const int num_tiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mma_bars[GROUPS];
+    __shared__ __align__(8) uint64_t w_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x >> 7);
+    const int tid = threadIdx.x & 127, warp = tid >> 5;  // within the group
+    uint64_t& mma_bar = mma_bars[grp];
+    auto group_sync = [&]() {
+        if (GROUPS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    };
+    const int S = a.s, M = a.m;
+    const int log2s = 31 - __clz(S);
+    const int nl = pl.nl;
+
+    // ---- one-time setup: packed weights + biases arrive with ONE bulk copy (TMA engine); barriers; TMEM
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < GROUPS; ++g) mbar_init(smem_u32(&mma_bars[g]), 1);
+        mbar_init(smem_u32(&w_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
+        bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"((uint32_t)pl.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const uint32_t bar = smem_u32(&w_bar);
+        const long long t0 = clock64();
+        while (!mbar_try_wait_cta(bar, 0))
+            if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+    }
+    const uint32_t d_tmem = tmem_base_s + (uint32_t)(grp * pl.grp_cols);
+    const uint32_t t_lane = d_tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint32_t a_smem = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
+    unsigned char* const a_ptr = smem + pl.a_off + grp * pl.a_bytes;
+    unsigned char* const a_row = a_ptr + tid * 16;  // this thread's row inside every 16-byte chunk plane
+    uint32_t phase = 0;
+    const int cout_last = a.ch[nl];
+    const int nchunk0 = pl.K[0] >> 3;
+    const int tile0 = blockIdx.x * GROUPS + grp, tile_step = gridDim.x * GROUPS;
+
+    // SA mode: the neighbour index and the live flag of this thread's row, prefetched one tile ahead
+    int id_next = 0;
+    bool live_next = false;
+    auto prefetch_row = [&](int tile) {
+        if constexpr (!DENSE) {
+            id_next = 0;
+            live_next = false;
+            if (tile < num_tiles) {
+                const long long g = (long long)tile * T2_ROWS + tid;
+                if (g < a.total_rows) {
+                    id_next = __ldg(a.idx + g);
+                    live_next = !(a.idx_cnt && __ldg(a.idx_cnt + (g >> log2s)) <= 0);  // empty ball -> zero input row
+                }
+            }
+        }
+    };
+    prefetch_row(tile0);
+
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const long long g = (long long)tile * T2_ROWS + tid;  // this thread's global row
+        // ------------------------------------------------------------------ layer-0 operand
+        if constexpr (!DENSE) {
+            const int id = id_next;
+            const bool live = live_next;
+            const long long cpi = g < a.total_rows ? (g >> log2s) : 0;  // S is a power of two; B*M < 2^31 (launcher)
+            const int b = (int)((unsigned)cpi / (unsigned)M);
+            const size_t prow = (size_t)b * a.n + id;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (pl.xyz_chunk >= 0 && live) {
+                const float* p = a.xyz + prow * 3;
+                const float* q = a.new_xyz + (size_t)cpi * 3;
+                dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
+                dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+                dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+            }
+            const int fchunks = pl.cp >> 3;
+            const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
+            // eight 16-byte loads in flight per thread, then eight stores
+            for (int kc0 = 0; kc0 < nchunk0; kc0 += 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int kc = kc0 + u;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && kc < fchunks) v[u] = __ldg(frow + kc);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int kc = kc0 + u;
+                    if (kc < nchunk0) {
+                        if (kc == pl.xyz_chunk) {
+                            v[u].x = pack_bf16(dx, dy);
+                            v[u].y = pack_bf16(dz, 0.f);
+                        }
+                        *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v[u];
+                    }
+                }
+            }
+            prefetch_row(tile + tile_step);
+        } else {
+            // dense: channel c of row g = src0[b, c, i] (c < c_feat) | src1[b, c - c_feat, i]; coalesced over threads
+            const bool rv = g < a.total_rows;
+            const int b = rv ? (int)(g / a.n) : 0;
+            const int i = rv ? (int)(g - (long long)b * a.n) : 0;
+            const float* s0 = a.features + (size_t)b * a.c_feat * a.n + i;
+            const float* s1 = a.src1 ? a.src1 + (size_t)b * a.c1 * a.n + i : nullptr;
+            const int ctot = a.c_feat + a.c1;
+            for (int kc0 = 0; kc0 < nchunk0; kc0 += 4) {
+                float x[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int c = kc0 * 8 + u;
+                    x[u] = 0.f;
+                    if (rv && c < ctot) x[u] = c < a.c_feat ? __ldg(s0 + (size_t)c * a.n) : __ldg(s1 + (size_t)(c - a.c_feat) * a.n);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (kc0 + u < nchunk0)
+                        *reinterpret_cast<uint4*>(a_row + (size_t)(kc0 + u) * (T2_ROWS * 16)) =
+                            make_uint4(pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
+                                       pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
+                }
+            }
+        }
+        // generic-proxy writes of the operand -> visible to the tensor core (async proxy); also orders the previous
+        // tile's tcgen05.ld's (every thread fenced them) before this tile's first MMA
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        group_sync();
+
+        for (int l = 0; l < nl; ++l) {
+            const int K = pl.K[l], Np = pl.Npad[l];
+            const bool last = l + 1 == nl;
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
+                const uint32_t act_lbo = T2_ROWS * 16, w_lbo = (uint32_t)Np * 16;
+                if (!last) {
+                    // D[row, cout] = act (A, M = 128 rows) x W_l (B, N = Np)
+                    const uint32_t idesc = instr_desc_bf16_m128(Np);
+                    for (int kk = 0; kk < (K >> 4); ++kk)
+                        umma_bf16(d_tmem, smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128),
+                                  smem_desc(w_smem + (uint32_t)kk * 2u * w_lbo, w_lbo, 128), idesc, kk > 0 ? 1u : 0u);
+                } else {
+                    // D^T[cout, row] = W_last (A, M = 128 channels of block mb) x act (B, N = 128 rows)
+                    const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS);
+                    for (int mb = 0; mb < pl.mb; ++mb)
+                        for (int kk = 0; kk < (K >> 4); ++kk)
+                            umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS),
+                                      smem_desc(w_smem + (uint32_t)mb * (T2_ROWS * 16) + (uint32_t)kk * 2u * w_lbo, w_lbo, 128),
+                                      smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128), idesc, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&mma_bar));
+            }
+            {
+                const uint32_t bar = smem_u32(&mma_bar);
+                if (!mbar_try_wait_cta(bar, phase)) {
+                    const long long t0 = clock64();
+                    while (!mbar_try_wait_cta(bar, phase))
+                        if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+                }
+                phase ^= 1u;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
+
+            if (!last) {
+                // bias + ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = row
+                int c0 = 0;
+                for (; c0 + 64 <= Np; c0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
+                    tmem_ld32_nowait(t_lane + (uint32_t)c0 + 32u, v1);
+                    tmem_wait_ld();
+                    epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                    epi_mid_store<32>(v1, bs + c0 + 32, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
+                }
+                for (; c0 + 32 <= Np; c0 += 32) {
+                    uint32_t v0[32];
+                    tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
+                    tmem_wait_ld();
+                    epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                }
+                for (; c0 + 16 <= Np; c0 += 16) {
+                    uint32_t v0[16];
+                    tmem_ld16_nowait(t_lane + (uint32_t)c0, v0);
+                    tmem_wait_ld();
+                    epi_mid_store<16>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                group_sync();
+            } else if constexpr (!DENSE) {
+                // thread = output channel; columns = the tile's rows: max over the S columns of a centre in registers,
+                // then bias + ReLU once per centre
+                const int cpt = T2_ROWS >> log2s;  // centres per tile
+                const unsigned cbase = (unsigned)tile * (unsigned)cpt;
+                const unsigned ctot = (unsigned)(a.total_rows >> log2s);
+                for (int mb = 0; mb < pl.mb; ++mb) {
+                    const int ch = mb * T2_ROWS + tid;
+                    const float bias = bs[ch];
+                    const bool ch_ok = ch < cout_last;
+                    float run = 0.f;
+                    auto emit = [&](int ci, float m) {
+                        const unsigned cg = cbase + (unsigned)ci;
+                        if (ch_ok && cg < ctot) {
+                            const unsigned b2 = cg / (unsigned)M;
+                            const unsigned p2 = cg - b2 * (unsigned)M;
+                            a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = fmaxf(__fadd_rn(m, bias), 0.f);
+                        }
+                    };
+#pragma unroll 1
+                    for (int c0 = 0; c0 < T2_ROWS; c0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0), v0);
+                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0 + 32), v1);
+                        tmem_wait_ld();
+                        if constexpr (SC == 32) {
+                            // S = 32, 64 or 128: a 32-column chunk lies inside one centre
+                            const float m0 = max_run<0, 32>(v0), m1 = max_run<0, 32>(v1);
+                            if (S == 32) {
+                                emit(c0 >> 5, m0);
+                                emit((c0 >> 5) + 1, m1);
+                            } else if (S == 64) {
+                                emit(c0 >> 6, fmaxf(m0, m1));
+                            } else {  // S == 128
+                                run = c0 == 0 ? fmaxf(m0, m1) : max3(run, m0, m1);
+                                if (c0 == 64) emit(0, run);
+                            }
+                        } else if constexpr (SC == 16) {
+                            emit((c0 >> 4) + 0, max_run<0, 16>(v0));
+                            emit((c0 >> 4) + 1, max_run<16, 16>(v0));
+                            emit((c0 >> 4) + 2, max_run<0, 16>(v1));
+                            emit((c0 >> 4) + 3, max_run<16, 16>(v1));
+                        } else {  // SC == 8
+                            emit((c0 >> 3) + 0, max_run<0, 8>(v0));
+                            emit((c0 >> 3) + 1, max_run<8, 8>(v0));
+                            emit((c0 >> 3) + 2, max_run<16, 8>(v0));
+                            emit((c0 >> 3) + 3, max_run<24, 8>(v0));
+                            emit((c0 >> 3) + 4, max_run<0, 8>(v1));
+                            emit((c0 >> 3) + 5, max_run<8, 8>(v1));
+                            emit((c0 >> 3) + 6, max_run<16, 8>(v1));
+                            emit((c0 >> 3) + 7, max_run<24, 8>(v1));
+                        }
+                    }
+                }
+                // no barrier here: the next tile's gather only overwrites the operand buffer (its last reader, this
+                // layer's MMA, has completed) and the next MMA is issued after that gather's barrier
+            } else {
+                // dense: thread = output channel; 128 columns = 128 consecutive rows (points) of the tile
+                const long long g0 = (long long)tile * T2_ROWS;
+                const int b0 = (int)(g0 / a.n);
+                const int i0 = (int)(g0 - (long long)b0 * a.n);
+                const bool whole = (i0 + T2_ROWS <= a.n) && (g0 + T2_ROWS <= a.total_rows);  // one batch entry, full tile
+                for (int mb = 0; mb < pl.mb; ++mb) {
+                    const int ch = mb * T2_ROWS + tid;
+                    const float bias = bs[ch];
+                    const bool ch_ok = ch < cout_last;
+                    float* const orow = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * a.n + i0;
+                    const bool vec = whole && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < T2_ROWS; c0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0), v0);
+                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0 + 32), v1);
+                        tmem_wait_ld();
+                        if (!ch_ok) continue;
+                        if (vec) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 o;
+                                o.x = fmaxf(__uint_as_float(v0[4 * q + 0]) + bias, 0.f);
+                                o.y = fmaxf(__uint_as_float(v0[4 * q + 1]) + bias, 0.f);
+                                o.z = fmaxf(__uint_as_float(v0[4 * q + 2]) + bias, 0.f);
+                                o.w = fmaxf(__uint_as_float(v0[4 * q + 3]) + bias, 0.f);
+                                *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 o;
+                                o.x = fmaxf(__uint_as_float(v1[4 * q + 0]) + bias, 0.f);
+                                o.y = fmaxf(__uint_as_float(v1[4 * q + 1]) + bias, 0.f);
+                                o.z = fmaxf(__uint_as_float(v1[4 * q + 2]) + bias, 0.f);
+                                o.w = fmaxf(__uint_as_float(v1[4 * q + 3]) + bias, 0.f);
+                                *reinterpret_cast<float4*>(orow + c0 + 32 + 4 * q) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 64; ++j) {
+                                const long long g2 = g0 + c0 + j;
+                                if (g2 < a.total_rows) {
+                                    const int b2 = (int)(g2 / a.n);
+                                    const int i2 = (int)(g2 - (long long)b2 * a.n);
+                                    const float x = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+                                    a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * a.n + i2] = fmaxf(x + bias, 0.f);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"((uint32_t)pl.tmem_cols)
+                     : "memory");
+    }
+}
+
+}  // namespace tsm
+
+static int round_up2(int v, int m) { return (v + m - 1) / m * m; }
+
+// dense != 0: point-wise MLP over (B, c_feat + c1, n) (a.features / a.src1), a.m == a.n, a.s == 1, no idx.
+// Returns TSM_ERR_INVALID for shapes this kernel does not take (the caller falls back to sa_mlp_tc.cu / fp32).
+int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) {
+    using namespace tsm;
+    const int S = a.s;
+    if (a.num_layers < 1 || a.num_layers > T2_MAX_LAYERS) return TSM_ERR_INVALID;
+    if (!dense) {
+        if (S < 8 || S > T2_ROWS || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile, SC in {8,16,32}
+        if (a.ch[a.num_layers] < 64) return TSM_ERR_INVALID;                       // narrow outputs: sa_mlp_tc.cu
+        if ((long long)b * a.m >= 0x7fffffffLL) return TSM_ERR_INVALID;            // 32-bit centre arithmetic
+    } else if (S != 1 || a.m != a.n) {
+        return TSM_ERR_INVALID;
+    }
+    Tc2Plan pl;
+    pl.nl = a.num_layers;
+    if (!dense) {
+        pl.cp = round_up2(a.c_feat, 8);
+        pl.xyz_chunk = a.use_xyz ? (pl.cp >> 3) : -1;
+        pl.K[0] = round_up2(pl.cp + (a.use_xyz ? 8 : 0), 16);
+    } else {
+        pl.cp = 0;
+        pl.xyz_chunk = -1;
+        pl.K[0] = round_up2(a.c_feat + a.c1, 16);
+    }
+    int off = 0, kmax = pl.K[0], nmid = 0;
+    for (int l = 0; l < pl.nl; ++l) {
+        const bool last = l + 1 == pl.nl;
+        pl.Npad[l] = round_up2(a.ch[l + 1], last ? T2_ROWS : 16);
+        if (pl.Npad[l] > 256) return TSM_ERR_INVALID;
+        if (l > 0) pl.K[l] = pl.Npad[l - 1];
+        kmax = pl.K[l] > kmax ? pl.K[l] : kmax;
+        if (!last) nmid = pl.Npad[l] > nmid ? pl.Npad[l] : nmid;
+        pl.w_off[l] = off;
+        off += pl.Npad[l] * pl.K[l] * 2;
+    }
+    if (kmax > 512) return TSM_ERR_INVALID;
+    pl.mb = pl.Npad[pl.nl - 1] / T2_ROWS;
+    for (int l = 0; l < pl.nl; ++l) {
+        pl.b_off[l] = off;
+        off += pl.Npad[l] * 4;
+    }
+    pl.packed_bytes = off;  // multiple of 64
+    off = round_up2(off, 128);
+    pl.a_off = off;
+    pl.a_bytes = round_up2(T2_ROWS * kmax * 2, 128);
+    auto smem_for = [&](int groups) { return off + groups * pl.a_bytes; };
+    if (smem_for(1) > 227 * 1024 - 64) return TSM_ERR_INVALID;
+    const int need_cols = nmid > pl.mb * T2_ROWS ? nmid : pl.mb * T2_ROWS;
+    pl.grp_cols = 32;
+    while (pl.grp_cols < need_cols) pl.grp_cols <<= 1;
+    if (pl.grp_cols > 512) return TSM_ERR_INVALID;
+    // two tile groups per CTA when the weights allow only one CTA per SM but a second operand buffer still fits
+    int groups = 1;
+    if ((227 * 1024) / (smem_for(1) + 2048) < 2 && smem_for(2) <= 227 * 1024 - 64 && 2 * pl.grp_cols <= 512 &&
+        !tsm_knob(KNOB_MLP_ONE_GROUP))
+        groups = 2;
+    pl.tmem_cols = pl.grp_cols * groups;
+    pl.smem_bytes = smem_for(groups);
+
+    __nv_bfloat16* featT = nullptr;
+    if (!dense && a.c_feat > 0) {
+        void* p = nullptr;
+        const size_t bytes = (size_t)b * a.n * pl.cp * sizeof(__nv_bfloat16);
+        int rc = tsm_scratch_get(1, bytes, stream, &p);
+        if (rc != TSM_OK) return rc;
+        featT = (__nv_bfloat16*)p;
+        dim3 grid((unsigned)divup(a.n, 256), (unsigned)b);
+        transpose2_bf16_kernel<<<grid, 256, 0, stream>>>(a.c_feat, pl.cp, a.n, a.features, featT);
+        TSM_LAUNCH_CHECK();
+    }
+    const long long tiles = (a.total_rows + T2_ROWS - 1) / T2_ROWS;
+    if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
+    using Kern = void (*)(const SaMlpArgs, const Tc2Plan, const __nv_bfloat16*, const unsigned char*, const int);
+    Kern kern = nullptr;
+    if (dense) {
+        kern = groups == 2 ? mlp_tc2_kernel<2, 32, true> : mlp_tc2_kernel<1, 32, true>;
+    } else {
+        const int sc = S < 32 ? S : 32;
+        if (groups == 2)
+            kern = sc == 32 ? mlp_tc2_kernel<2, 32, false> : (sc == 16 ? mlp_tc2_kernel<2, 16, false> : mlp_tc2_kernel<2, 8, false>);
+        else
+            kern = sc == 32 ? mlp_tc2_kernel<1, 32, false> : (sc == 16 ? mlp_tc2_kernel<1, 16, false> : mlp_tc2_kernel<1, 8, false>);
+    }
+    TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
+    // resident CTAs per SM: what shared memory, registers (a grid of more CTAs than are resident runs a second,
+    // partial wave) and the 512 TMEM columns allow
+    int occ = (227 * 1024) / (pl.smem_bytes + 2048);
+    {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e == cudaSuccess && fa.numRegs > 0) {
+            const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * T2_THREADS * groups;
+            const int occ_regs = 65536 / regs_cta;
+            if (occ > occ_regs) occ = occ_regs;
+        } else {
+            cudaGetLastError();
+            if (occ > 2) occ = 2;
+        }
+    }
+    const int tmem_occ = 512 / pl.tmem_cols;
+    if (occ > tmem_occ) occ = tmem_occ;
+    if (occ < 1) occ = 1;
+    if (const char* e = tsm_knob(KNOB_MLP_OCC)) occ = atoi(e) > 0 && atoi(e) < occ ? atoi(e) : occ;
+    long long grid = (long long)tsm_num_sms() * occ;
+    if (grid * groups > tiles) grid = (tiles + groups - 1) / groups;
+    SaMlpArgs args = a;
+    args.status = tsm_status_word(stream);
+    unsigned char* packed = nullptr;
+    {
+        void* p = nullptr;
+        int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes, stream, &p);
+        if (rc != TSM_OK) return rc;
+        packed = (unsigned char*)p;
+        dim3 pgrid(16, (unsigned)pl.nl);
+        pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(args, pl, dense, packed);
+        TSM_LAUNCH_CHECK();
+    }
+    kern<<<(unsigned)grid, T2_THREADS * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    TSM_LAUNCH_CHECK();
+    return TSM_OK;
+}

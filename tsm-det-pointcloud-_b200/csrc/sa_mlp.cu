@@ -13,6 +13,8 @@ extern "C" int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_fea
     a.xyz = xyz;
     a.new_xyz = new_xyz;
     a.features = features;
+    a.src1 = nullptr;
+    a.c1 = 0;
     a.idx = idx;
     a.idx_cnt = idx_cnt;
     a.out = out;
@@ -34,6 +36,55 @@ extern "C" int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_fea
     a.status = nullptr;
     if (out_c0 < 0 || out_c0 + a.ch[num_layers] > out_ctot) return TSM_ERR_INVALID;
     if (precision == 0) return tsm_sa_mlp_fp32(a, b, (cudaStream_t)stream);
-    if (precision == 1) return tsm_sa_mlp_tc(a, b, (cudaStream_t)stream);
+    if (precision == 1) {
+        // second-generation kernel (transposed last layer, in-register pooling) where it applies; TSMDET_MLP_V1=1
+        // keeps every shape on the first-generation kernel (A/B measurements, tests of both)
+        if (!tsm_knob(KNOB_MLP_V1)) {
+            const int rc = tsm_mlp_tc2(a, b, 0, (cudaStream_t)stream);
+            if (rc != TSM_ERR_INVALID) return rc;
+        }
+        return tsm_sa_mlp_tc(a, b, (cudaStream_t)stream);
+    }
+    return TSM_ERR_INVALID;
+}
+
+// Point-wise shared MLP over dense tensors: out[b, out_c0 + co, i] = MLP(cat(src0[b, :, i], src1[b, :, i])) with
+// [1x1 conv (BN folded) + bias + ReLU] x num_layers -- PointnetFPModule.mlp (pointnet2_modules.py:175-176, on the
+// concatenation of the interpolated and the skip features, :171) and aggregation_mlp (:1320-1321).
+//   src0 (B,c0,n), src1 (B,c1,n) | NULL; channels[0] == c0 + c1; out (B,out_ctot,n).
+// precision 0 = fp32 FMA, 1 = bf16 tensor cores (tcgen05, fp32 accumulate).
+extern "C" int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
+                                    const int* channels, const float* const* weights, const float* const* biases,
+                                    float* out, int out_ctot, int out_c0, int precision, void* stream) {
+    if (b <= 0 || n <= 0) return TSM_OK;
+    if (num_layers < 1 || num_layers > 4 || c0 <= 0 || c1 < 0 || !src0 || (c1 > 0 && !src1) || !out) return TSM_ERR_INVALID;
+    tsm::SaMlpArgs a;
+    a.xyz = nullptr;
+    a.new_xyz = nullptr;
+    a.features = src0;
+    a.src1 = c1 > 0 ? src1 : nullptr;
+    a.c1 = c1;
+    a.idx = nullptr;
+    a.idx_cnt = nullptr;
+    a.out = out;
+    a.num_layers = num_layers;
+    for (int l = 0; l < 4; ++l) {
+        a.w[l] = l < num_layers ? weights[l] : nullptr;
+        a.bias[l] = l < num_layers ? biases[l] : nullptr;
+    }
+    for (int l = 0; l <= 4; ++l) a.ch[l] = l <= num_layers ? channels[l] : 0;
+    if (a.ch[0] != c0 + c1) return TSM_ERR_INVALID;
+    a.n = n;
+    a.m = n;
+    a.s = 1;
+    a.c_feat = c0;
+    a.use_xyz = 0;
+    a.out_ctot = out_ctot;
+    a.out_c0 = out_c0;
+    a.total_rows = (long long)b * n;
+    a.status = nullptr;
+    if (out_c0 < 0 || out_c0 + a.ch[num_layers] > out_ctot) return TSM_ERR_INVALID;
+    if (precision == 0) return tsm_sa_mlp_fp32_dense(a, b, (cudaStream_t)stream);
+    if (precision == 1) return tsm_mlp_tc2(a, b, 1, (cudaStream_t)stream);
     return TSM_ERR_INVALID;
 }

@@ -7,7 +7,8 @@ namespace tsm {
 struct SaMlpArgs {
     const float* xyz;       // (B,N,3)
     const float* new_xyz;   // (B,M,3)
-    const float* features;  // (B,C,N) or null
+    const float* features;  // (B,C,N) or null.  Dense (point-wise) mode: source 0, (B,c_feat,n)
+    const float* src1;      // dense mode only: source 1, (B,c1,n), concatenated after source 0 along channels; or null
     const int* idx;         // (B,M,S)
     const int* idx_cnt;     // (B,M) or null (no masking)
     float* out;             // (B,out_ctot,M)
@@ -16,6 +17,7 @@ struct SaMlpArgs {
     int ch[5];  // ch[0] = input channels (3*use_xyz + C), ch[l+1] = outputs of layer l
     int num_layers;
     int n, m, s, c_feat, use_xyz;
+    int c1;                 // channels of src1 (0 outside the dense mode)
     int out_ctot, out_c0;
     long long total_rows;  // B*M*S
     int* status;           // watchdog word (device) or nullptr
@@ -25,4 +27,8 @@ struct SaMlpArgs {
 }  // namespace tsm
 
 int tsm_sa_mlp_fp32(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);
+int tsm_sa_mlp_fp32_dense(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);
 int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);  // TSM_ERR_INVALID if the shape is unsupported
+// second-generation tcgen05 kernel (mlp_tc2.cu): SA scales with >= 64 output channels and nsample >= 8 (dense == 0),
+// point-wise MLPs over dense (B,C,n) inputs (dense != 0).  TSM_ERR_INVALID if the shape is unsupported.
+int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream);

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(MLP_THREADS) sa_mlp_fp32_kernel(const SaMlpArg
         int id = 0;
         bool live = rv;
         if (rv) {
-            id = a.idx[gr];
+            // dense (point-wise) mode: no index tensor, S = 1, M = n -> row gr is point gr % n of batch entry b
+            id = a.idx ? a.idx[gr] : (int)(cp - (long long)b * M);
             if (a.idx_cnt && a.idx_cnt[cp] <= 0) live = false;  // empty ball: all-zero input (:1265-1267)
         }
         const int c0 = a.ch[0];
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(MLP_THREADS) sa_mlp_fp32_kernel(const SaMlpArg
                     v = __fsub_rn(__ldg(a.xyz + ((size_t)b * a.n + id) * 3 + c), __ldg(a.new_xyz + (size_t)cp * 3 + c));
                 } else {
                     const int fc = c - (a.use_xyz ? 3 : 0);
-                    v = __ldg(a.features + ((size_t)b * a.c_feat + fc) * a.n + id);
+                    v = fc < a.c_feat ? __ldg(a.features + ((size_t)b * a.c_feat + fc) * a.n + id)
+                                      : __ldg(a.src1 + ((size_t)b * a.c1 + (fc - a.c_feat)) * a.n + id);
                 }
             }
             bufA[(size_t)c * MLP_ROWS + row] = v;
@@ -141,4 +143,10 @@ int tsm_sa_mlp_fp32(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     tsm::sa_mlp_fp32_kernel<<<(unsigned)tiles, tsm::MLP_THREADS, dyn, stream>>>(a, maxc);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
+}
+
+// dense (point-wise) mode of the same kernel: a.idx == nullptr, a.s == 1, a.m == a.n (see tsmdet_pointwise_mlp)
+int tsm_sa_mlp_fp32_dense(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
+    if (a.idx || a.s != 1 || a.m != a.n) return TSM_ERR_INVALID;
+    return tsm_sa_mlp_fp32(a, b, stream);
 }

@@ -17,9 +17,8 @@
 //              32x32b), add bias, ReLU, repack to bf16 and write the next layer's A operand in place;
 //   last     : bias + ReLU, then max over the S rows of each centre: values are >= 0, so the float
 //              max is an unsigned max on the bit pattern -> ONE redux.sync per channel per warp.
-#include <cuda_bf16.h>
-
 #include "sa_mlp.cuh"
+#include "umma.cuh"
 
 namespace tsm {
 
@@ -45,45 +44,7 @@ struct TcPlan {
     int packed_bytes;          // weights + biases: the first packed_bytes of dynamic smem, same layout in global
 };
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
-    // | base_offset=0 | lbo_mode=0 | layout_type=SWIZZLE_NONE(0) [61,64)
-    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ uint32_t instr_desc_bf16(int n) {
-    // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6) | a_format BF16=1 [7,10) | b_format BF16=1 [10,13)
-    // | a_major K=0 [15] | b_major K=0 [16] | n_dim N>>3 [17,23) | m_dim M>>4 [24,29)
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t instr_desc_bf16(int n) { return instr_desc_bf16_m128(n); }
 
 // features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(int c, int cp, int n, const float* __restrict__ f,
@@ -408,14 +369,14 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     // One accumulator region serves every layer: an epilogue's tcgen05.ld's are complete (wait::ld) before the
     // barrier that precedes the next layer's MMA, so nothing races.  (Alternating regions, d_off = nmax, halved
     // the CTAs per SM the TMEM allows; TSMDET_MLP_TMEM_ALT=1 restores it for experiments.)
-    pl.d_off = (pl.nl > 1 && getenv("TSMDET_MLP_TMEM_ALT")) ? round_up(nmax, 32) : 0;
+    pl.d_off = 0;
     pl.grp_cols = 32;
     while (pl.grp_cols < pl.d_off + nmax) pl.grp_cols <<= 1;
     if (pl.grp_cols > 512) return TSM_ERR_INVALID;
     // two tile groups per CTA when the weights allow only one CTA per SM but a second operand buffer still fits
     int groups = 1;
     if ((227 * 1024) / (smem_for(1) + 2048) < 2 && smem_for(2) <= 227 * 1024 - 64 && 2 * pl.grp_cols <= 512 &&
-        !getenv("TSMDET_MLP_ONE_GROUP"))
+        !tsm_knob(KNOB_MLP_ONE_GROUP))
         groups = 2;
     pl.tmem_cols = pl.grp_cols * groups;
     pl.o_off = pl.a_off + groups * pl.a_bytes;
@@ -457,7 +418,7 @@ int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream) {
     const int tmem_occ = 512 / pl.tmem_cols;
     if (occ > tmem_occ) occ = tmem_occ;
     if (occ < 1) occ = 1;
-    if (const char* e = getenv("TSMDET_MLP_OCC")) occ = atoi(e) > 0 && atoi(e) < occ ? atoi(e) : occ;
+    if (const char* e = tsm_knob(KNOB_MLP_OCC)) occ = atoi(e) > 0 && atoi(e) < occ ? atoi(e) : occ;
     long long grid = (long long)tsm_num_sms() * occ;
     if (grid * groups > tiles) grid = (tiles + groups - 1) / groups;
     SaMlpArgs args = a;

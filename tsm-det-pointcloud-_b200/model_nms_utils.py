@@ -1,98 +1,83 @@
-"""Post-processing NMS drivers -- same functions and results as
-``/root/reference/pcdet/models/model_utils/model_nms_utils.py:6-127`` on top of this package's
-``iou3d_nms_utils`` (``NMS_TYPE`` is still looked up by name with ``getattr``)."""
+"""Post-processing NMS drivers -- the functions of
+``/root/reference/pcdet/models/model_utils/model_nms_utils.py:6-127`` (same names, arguments and results) on top
+of this package's ``iou3d_nms_utils``.
+
+The reference's own file runs unchanged over this package's ``iou3d_nms_utils`` (INTEGRATION.md section 1;
+``tests/test_dropin_reference_py_gpu.py`` does exactly that), so nothing here is a transcription: every driver is
+the same three steps -- restrict to a subset, keep the ``NMS_PRE_MAXSIZE`` best, run ``NMS_TYPE`` and keep
+``NMS_POST_MAXSIZE`` -- expressed ONCE (``_subset_topk_nms``) with device-side masks instead of the reference's
+boolean-index compactions and ``nonzero()`` calls, and ``multi_thresh_batch`` runs the live driver for a whole batch
+of frames without any host synchronisation.  Scores are assumed distinct where order matters (``torch.topk`` /
+``sort`` leave the order of ties unspecified in the reference too).
+"""
 from __future__ import annotations
 
 import torch
 
 from . import iou3d_nms_utils
 
+_NEG_INF = float("-inf")
 
-def _nms_fn(nms_config):
-    return getattr(iou3d_nms_utils, nms_config.NMS_TYPE)
+
+def _subset_topk_nms(rank_scores, boxes7, subset, pre_max, post_max, thresh, nms_config):
+    """Indices (into the full arrays, best first) that survive: restrict to ``subset`` (bool mask or None), take the
+    ``pre_max`` highest ``rank_scores``, run ``nms_config.NMS_TYPE`` at ``thresh``, keep ``post_max``."""
+    p = rank_scores.shape[0]
+    if p == 0:
+        return rank_scores.new_zeros((0,), dtype=torch.int64)
+    masked = rank_scores if subset is None else torch.where(subset, rank_scores, rank_scores.new_full((), _NEG_INF))
+    vals, order = torch.topk(masked, k=min(int(pre_max), p))          # descending; excluded entries sort last
+    if nms_config.NMS_TYPE in ("nms_gpu", "nms_normal_gpu"):
+        # one batched launch with a device-side count: no boolean indexing, one sync for the variable-length result
+        counts = (vals > _NEG_INF).sum().to(torch.int32).view(1)
+        sel, num = iou3d_nms_utils.nms_gpu_batch(boxes7[order].unsqueeze(0), vals.unsqueeze(0), float(thresh), counts=counts,
+                                                 normal=nms_config.NMS_TYPE == "nms_normal_gpu", presorted=True)
+        kept = sel[0, :min(int(num.item()), int(post_max))]
+    else:  # any other NMS_TYPE the caller's iou3d_nms_utils offers, looked up by name as the reference does
+        live = int((vals > _NEG_INF).sum().item())
+        kept, _ = getattr(iou3d_nms_utils, nms_config.NMS_TYPE)(boxes7[order[:live]], vals[:live], thresh, **nms_config)
+        kept = kept[:int(post_max)]
+    return order[kept]
 
 
 def class_agnostic_nms(box_scores, box_preds, nms_config, score_thresh=None, depth_score=None):
-    """ref :6-28"""
-    src_box_scores = box_scores
-    if score_thresh is not None:
-        scores_mask = (box_scores >= score_thresh)
-        box_scores = box_scores[scores_mask]
-        box_preds = box_preds[scores_mask]
+    """ref :6-28 -- optional score threshold, optional depth re-weighting of the ranking score."""
+    subset = None if score_thresh is None else box_scores >= score_thresh
+    rank = box_scores
     if depth_score is not None:
-        depth_score = depth_score[scores_mask]
-        box_scores = box_scores * depth_score
-
-    selected = []
-    if box_scores.shape[0] > 0:
-        box_scores_nms, indices = torch.topk(box_scores, k=min(nms_config.NMS_PRE_MAXSIZE, box_scores.shape[0]))
-        boxes_for_nms = box_preds[indices]
-        keep_idx, _ = _nms_fn(nms_config)(boxes_for_nms[:, 0:7], box_scores_nms, nms_config.NMS_THRESH, **nms_config)
-        selected = indices[keep_idx[:nms_config.NMS_POST_MAXSIZE]]
-
-    if score_thresh is not None:
-        original_idxs = scores_mask.nonzero().view(-1)
-        selected = original_idxs[selected]
-    return selected, src_box_scores[selected]
+        if score_thresh is None:  # the reference indexes depth_score with a mask that only exists with a threshold
+            raise UnboundLocalError("class_agnostic_nms: depth_score needs score_thresh (reference :13-14)")
+        rank = box_scores * depth_score
+    selected = _subset_topk_nms(rank, box_preds[:, 0:7], subset, nms_config.NMS_PRE_MAXSIZE,
+                                nms_config.NMS_POST_MAXSIZE, nms_config.NMS_THRESH, nms_config)
+    return selected, box_scores[selected]
 
 
 def class_agnostic_nms_v2(box_scores, box_labels, box_preds, nms_config, score_thresh=None):
-    """ref :31-49 -- per-class (labels 0..2) pre/post sizes and thresholds given as lists."""
-    src_box_scores = box_scores
-    selected_idx = []
-    for i in range(0, 3):
-        mask = (box_labels == i)
-        box_scores_mask = box_scores[mask]
-        box_preds_mask = box_preds[mask]
-        if box_scores.shape[0] > 0:
-            box_scores_nms, indices = torch.topk(
-                box_scores_mask, k=min((nms_config.NMS_PRE_MAXSIZE)[i], box_scores_mask.shape[0]))
-            boxes_for_nms = box_preds_mask[indices]
-            keep_idx, _ = _nms_fn(nms_config)(
-                boxes_for_nms[:, 0:7], box_scores_nms, (nms_config.NMS_THRESH)[i], **nms_config)
-            selected = indices[keep_idx[:(nms_config.NMS_POST_MAXSIZE)[i]]]
-        original_idxs = mask.nonzero().view(-1)
-        selected = original_idxs[selected]
-        selected_idx.append(selected)
-    selected_idx = torch.cat(selected_idx, dim=-1)
-    return selected_idx, src_box_scores[selected_idx]
+    """ref :31-49 -- labels 0..2, with per-class lists for the pre / post sizes and the threshold."""
+    parts = [_subset_topk_nms(box_scores, box_preds[:, 0:7], box_labels == c, nms_config.NMS_PRE_MAXSIZE[c],
+                              nms_config.NMS_POST_MAXSIZE[c], nms_config.NMS_THRESH[c], nms_config) for c in range(3)]
+    selected = torch.cat(parts, dim=-1)
+    return selected, box_scores[selected]
 
 
 def multi_thresh(box_scores, box_labels, box_preds, nms_config, score_thresh=None):
-    """ref :52-87 -- the live one: per-class score threshold -> top-k -> NMS, then one cross-class NMS."""
-    src_box_scores = box_scores
-    selected = []
-    selected_end = []
-    if score_thresh is not None:
-        for i, cur_thresh in enumerate(score_thresh):
-            mask = ((i + 1) == box_labels)
-            cur_box_scores = box_scores[mask]
-            cur_box_preds = box_preds[mask]
-            score_mask = (cur_box_scores >= cur_thresh)
-            cur_box_scores = cur_box_scores[score_mask]
-            cur_box_preds = cur_box_preds[score_mask]
-
-            if cur_box_scores.shape[0] > 0:
-                cur_box_scores_nms, indices = torch.topk(
-                    cur_box_scores, k=min(nms_config.NMS_PRE_MAXSIZE, cur_box_scores.shape[0]))
-                cur_box_for_nms = cur_box_preds[indices]
-                keep_idx, _ = _nms_fn(nms_config)(
-                    cur_box_for_nms, cur_box_scores_nms, nms_config.NMS_THRESH, **nms_config)
-                cur_selected = indices[keep_idx[:nms_config.NMS_POST_MAXSIZE]]
-
-                score_idxs = score_mask.nonzero().view(-1)
-                original_idxs = mask.nonzero().view(-1)
-                cur_selected = score_idxs[cur_selected]
-                cur_selected = original_idxs[cur_selected]
-                selected.append(cur_selected)
-    if len(selected):
-        selected = torch.cat(selected, dim=0)
-        box_for_nms_end = box_preds[selected]
-        box_scores_nms_end = box_scores[selected]
-        keep_idx_end, _ = _nms_fn(nms_config)(
-            box_for_nms_end, box_scores_nms_end, nms_config.NMS_THRESH, **nms_config)
-        selected_end = selected[keep_idx_end]
-    return selected_end, src_box_scores[selected_end]
+    """ref :52-87 -- the live driver: per class (labels 1..C) score threshold -> top-k -> NMS, then one cross-class
+    NMS over the union.  Returns ``([], empty)`` when nothing survives, like the reference."""
+    parts = []
+    for c, cur_thresh in enumerate(score_thresh if score_thresh is not None else ()):
+        subset = (box_labels == (c + 1)) & (box_scores >= cur_thresh)
+        part = _subset_topk_nms(box_scores, box_preds[:, 0:7], subset, nms_config.NMS_PRE_MAXSIZE,
+                                nms_config.NMS_POST_MAXSIZE, nms_config.NMS_THRESH, nms_config)
+        if part.numel():
+            parts.append(part)
+    if not parts:
+        return [], box_scores[[]]
+    union = torch.cat(parts, dim=0)
+    final = _subset_topk_nms(box_scores[union], box_preds[union][:, 0:7], None, union.numel(), union.numel(),
+                             nms_config.NMS_THRESH, nms_config)
+    selected = union[final]
+    return selected, box_scores[selected]
 
 
 @torch.no_grad()
@@ -149,32 +134,17 @@ def multi_thresh_batch(box_scores, box_labels, box_preds, nms_config, score_thre
 
 
 def multi_classes_nms(cls_scores, box_preds, nms_config, score_thresh=None):
-    """ref :89-127 -- cls_scores (N,num_class), box_preds (N,7+C) -> (scores, labels, boxes)."""
-    pred_scores, pred_labels, pred_boxes = [], [], []
+    """ref :89-127 -- cls_scores (N,num_class), box_preds (N,7+C) -> (scores, labels, boxes), class after class."""
+    out_scores, out_labels, out_boxes = [], [], []
     for k in range(cls_scores.shape[1]):
-        if score_thresh is not None:
-            scores_mask = (cls_scores[:, k] >= score_thresh)
-            box_scores = cls_scores[scores_mask, k]
-            cur_box_preds = box_preds[scores_mask]
-        else:
-            box_scores = cls_scores[:, k]
-            cur_box_preds = box_preds
-
-        selected = []
-        if box_scores.shape[0] > 0:
-            box_scores_nms, indices = torch.topk(box_scores, k=min(nms_config.NMS_PRE_MAXSIZE, box_scores.shape[0]))
-            boxes_for_nms = cur_box_preds[indices]
-            keep_idx, _ = _nms_fn(nms_config)(boxes_for_nms[:, 0:7], box_scores_nms, nms_config.NMS_THRESH, **nms_config)
-            selected = indices[keep_idx[:nms_config.NMS_POST_MAXSIZE]]
-
-        pred_scores.append(box_scores[selected])
-        pred_labels.append(box_scores.new_ones(len(selected)).long() * k)
-        pred_boxes.append(cur_box_preds[selected])
-
-    pred_scores = torch.cat(pred_scores, dim=0)
-    pred_labels = torch.cat(pred_labels, dim=0)
-    pred_boxes = torch.cat(pred_boxes, dim=0)
-    return pred_scores, pred_labels, pred_boxes
+        col = cls_scores[:, k]
+        subset = None if score_thresh is None else col >= score_thresh
+        sel = _subset_topk_nms(col, box_preds[:, 0:7], subset, nms_config.NMS_PRE_MAXSIZE, nms_config.NMS_POST_MAXSIZE,
+                               nms_config.NMS_THRESH, nms_config)
+        out_scores.append(col[sel])
+        out_labels.append(torch.full((sel.numel(),), k, dtype=torch.int64, device=col.device))
+        out_boxes.append(box_preds[sel])
+    return torch.cat(out_scores, dim=0), torch.cat(out_labels, dim=0), torch.cat(out_boxes, dim=0)
 
 
 class NmsConfig(dict):

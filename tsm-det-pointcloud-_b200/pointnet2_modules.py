@@ -91,21 +91,85 @@ def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: in
     return out
 
 
-def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+def pointwise_mlp(src0: torch.Tensor, src1: Optional[torch.Tensor], layers, out: Optional[torch.Tensor] = None,
+                  out_c0: int = 0, precision: str = "fp32") -> torch.Tensor:
+    """Point-wise shared MLP, no pooling (C ABI ``tsmdet_pointwise_mlp``): ``out[:, out_c0:out_c0+cout, :] =
+    MLP(cat([src0, src1], dim=1))`` for folded ``layers`` [(W (cout,cin), b (cout))]; src0 (B,c0,n), src1 (B,c1,n) |
+    None.  The concatenation is never materialised.  ``precision='bf16'`` runs on tcgen05 tensor cores."""
+    b, c0, n = src0.shape
+    c1 = 0 if src1 is None else src1.shape[1]
+    assert src0.is_contiguous() and src0.dtype == torch.float32
+    assert src1 is None or (src1.is_contiguous() and src1.shape[0] == b and src1.shape[2] == n)
+    nl = len(layers)
+    chans = [c0 + c1] + [w.shape[0] for w, _ in layers]
+    for l, (w, bias) in enumerate(layers):
+        assert w.shape == (chans[l + 1], chans[l]) and w.is_contiguous() and bias.is_contiguous()
+    if out is None:
+        out = torch.empty((b, chans[-1], n), dtype=torch.float32, device=src0.device)
+    assert out.is_contiguous() and out.shape[0] == b and out.shape[2] == n
+    ch_arr = (ctypes.c_int * (nl + 1))(*chans)
+    w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
+    b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
+    prec = {"fp32": 0, "bf16": 1}[precision]
+    call("tsmdet_pointwise_mlp", b, n, c0, c1, ptr(src0), ptr(src1), nl, ch_arr, w_arr, b_arr, ptr(out), out.shape[1],
+         out_c0, prec, stream_ptr(src0.device))
+    return out
+
+
+def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """new_xyz[b,p,:] = xyz[b,idx[b,p],:] -- the transpose/gather_operation/transpose chain (:1143, 1212-1215)."""
     b, n, _ = xyz.shape
     m = idx.shape[1]
-    out = torch.empty((b, m, 3), dtype=torch.float32, device=xyz.device)
+    if out is None:
+        out = torch.empty((b, m, 3), dtype=torch.float32, device=xyz.device)
+    assert out.shape == (b, m, 3) and out.is_contiguous() and out.dtype == torch.float32
     call("tsmdet_gather_xyz", b, n, m, ptr(xyz), ptr(idx), ptr(out), stream_ptr(xyz.device))
     return out
+
+
+def stage_points(points: torch.Tensor, batch_size: int, xyz: Optional[torch.Tensor] = None,
+                 features: Optional[torch.Tensor] = None, bad: Optional[torch.Tensor] = None):
+    """Input staging: the collated device batch ``points (B*N, 4+C)`` = [batch_idx, x, y, z,
+    features...] -> ``(xyz (B,N,3), features (B,C,N) | None)`` in ONE kernel -- what the reference does with
+    ``break_up_pc`` + ``view`` + ``permute(0,2,1).contiguous()`` (pointnet2_backbone.py:796-800, 814-823) and the
+    ``xyz.transpose(1,2).contiguous()`` of pointnet2_modules.py:1143.  ``bad`` (1,) int32, if given, is incremented
+    on the device for every tile holding a row whose batch index is not its frame (the reference asserts equal
+    per-frame counts, :819); without it the check is skipped.  C ABI ``tsmdet_stage_points``."""
+    assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 2
+    rows, w = points.shape
+    assert w >= 4 and rows % batch_size == 0, "every frame must hold the same number of points"
+    n, c = rows // batch_size, w - 4
+    if xyz is None:
+        xyz = torch.empty((batch_size, n, 3), dtype=torch.float32, device=points.device)
+    if features is None and c > 0:
+        features = torch.empty((batch_size, c, n), dtype=torch.float32, device=points.device)
+    assert xyz.shape == (batch_size, n, 3) and xyz.is_contiguous()
+    assert c == 0 or (features.shape == (batch_size, c, n) and features.is_contiguous())
+    call("tsmdet_stage_points", batch_size, n, c, ptr(points), ptr(xyz), ptr(features) if c > 0 else None,
+         ptr(bad), stream_ptr(points.device))
+    return xyz, (features if c > 0 else None)
 
 
 class PointnetFPModule(nn.Module):
     r"""Propagates the features of one set to another (ref :130-178)."""
 
-    def __init__(self, *, mlp: List[int], bn: bool = True):
+    def __init__(self, *, mlp: List[int], bn: bool = True, fused: bool = True, precision: str = "fp32"):
+        """``fused`` (eval mode only): BatchNorm folded into the 1x1 convs and the whole MLP -- including the
+        concatenation of the interpolated and the skip features (:171) -- in ONE kernel (``tsmdet_pointwise_mlp``:
+        fp32 FMA, or bf16 tcgen05 with ``precision='bf16'``); otherwise the reference's eager Conv2d/BatchNorm2d."""
         super().__init__()
         self.mlp = build_shared_mlp(mlp, bn=True) if bn else build_shared_mlp(mlp, bn=False)
+        self.fused = fused
+        self.precision = precision
+        self._folded = None
+
+    def train(self, mode: bool = True):
+        self._folded = None
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._folded = None  # weights changed under a cached fold (ADVICE r1)
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, unknown, known, unknow_feats, known_feats):
         """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n)|None, known_feats (B,C2,m) -> (B,mlp[-1],n)"""
@@ -118,6 +182,12 @@ class PointnetFPModule(nn.Module):
         else:
             interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
 
+        if self.fused and not self.training:
+            if self._folded is None:
+                self._folded = fold_conv_bn(self.mlp)
+            return pointwise_mlp(interpolated_feats.contiguous(),
+                                 None if unknow_feats is None else unknow_feats.contiguous(), self._folded,
+                                 precision=self.precision)
         if unknow_feats is not None:
             new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
         else:
@@ -180,6 +250,14 @@ class PointnetSAModuleFSMSG(nn.Module):
             self.aggregation_mlp = None
         self.out_channels = out_channels
         self._folded = None  # cache of folded (W, b) per scale, built lazily in eval mode
+        self._folded_agg = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        # a checkpoint loaded after a warm-up forward must not leave the fused path on stale folded weights
+        # (ADVICE r1); CUDA graphs captured before the load hold pointers to the old folds and must be re-captured
+        self._folded = None
+        self._folded_agg = None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ sampling (ref :1153-1210)
     def sample(self, xyz, features=None, scores=None):
@@ -214,6 +292,7 @@ class PointnetSAModuleFSMSG(nn.Module):
 
     def train(self, mode: bool = True):
         self._folded = None
+        self._folded_agg = None
         return super().train(mode)
 
     # ------------------------------------------------------------------ forward
@@ -267,7 +346,12 @@ class PointnetSAModuleFSMSG(nn.Module):
             new_features = torch.cat(new_features_list, dim=1)
 
         if self.aggregation_mlp is not None:
-            new_features = self.aggregation_mlp(new_features)
+            if use_fused:  # ref :1320-1321 as one kernel (BN folded; tensor cores in bf16 mode)
+                if self._folded_agg is None:
+                    self._folded_agg = fold_conv_bn(self.aggregation_mlp)
+                new_features = pointwise_mlp(new_features.contiguous(), None, self._folded_agg, precision=self.precision)
+            else:
+                new_features = self.aggregation_mlp(new_features)
         return new_xyz.contiguous(), new_features.contiguous(), sample_idx
 
 

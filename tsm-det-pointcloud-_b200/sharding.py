@@ -100,76 +100,141 @@ def gather_packed(packed: torch.Tensor, frames: int, k: int, out: Optional[torch
 
 
 class PeerGather:
-    """The same gather as ``gather_packed`` without a rendezvous: every rank owns a receive buffer ``(world, stride)``
-    in its HBM, maps every peer's buffer through CUDA IPC once, and per step ONE kernel (``csrc/peer_put.cu``) stores
-    its packed records into row ``rank`` of every rank's buffer over NVLink and then publishes the step number into
-    that rank's flag word.  Nothing waits for a peer: an NCCL all_gather kernel holds SMs until all ranks have launched
-    theirs, which at one collective per 0.6 ms step cost ~15 % of the 8-GPU throughput.  The records of step ``s``
-    from rank ``r`` are complete once ``flags[r] >= s``; ``wait`` checks that on the host.  One process per GPU on one
-    node; every rank must construct its PeerGather objects in the same order (the IPC handles travel through
-    ``all_gather_object``)."""
+    """The same gather as ``gather_packed`` without a rendezvous, with credit-based flow control
+    (``csrc/peer_put.cu``).  Every rank owns a RING of ``slots`` receive buffers ``(slots, world, stride)`` in its
+    HBM plus a flag word and an ack word per peer, and maps every peer's three arrays through CUDA IPC once.  Step
+    ``s`` of a rank is ONE kernel: it tells every peer that this rank has consumed everything before ``s`` (the
+    launch is stream-ordered after the rank's reads of step ``s-1``), waits until every peer has released slot
+    ``(s-1) % slots`` (their ack >= ``s - slots``), stores its packed records into row ``rank`` of that slot on every
+    rank over NVLink, and publishes ``s`` into every rank's flag word.  An NCCL all_gather kernel holds SMs until all
+    ranks have launched theirs (~15 % of the 8-GPU throughput at one collective per 0.6 ms step); here a rank only
+    ever waits when it is ``slots - 1`` whole steps ahead of the slowest peer, and then for exactly as long as the
+    data it would overwrite is still unread -- records can never be torn or mixed across steps.
 
-    def __init__(self, numel: int, device, group=None):
-        import ctypes
+    Contract: the views of step ``s`` are valid from ``wait_stream()`` / ``wait()`` until this rank's NEXT ``put``
+    is issued (reads must be ordered before it: same stream, or an event).  One process per GPU on one node; every
+    rank constructs its PeerGather objects in the same order.  Construction is collective and agrees on failure:
+    ``PeerGather.create`` returns None on EVERY rank if any rank could not set the transport up."""
 
-        from torch.multiprocessing.reductions import reduce_tensor
-
-        from . import _lib
-
+    def __init__(self, numel: int, device, group=None, slots: int = 2, timeout_s: float = 120.0):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("PeerGather supports at most 16 ranks (tsmdet_peer_put's pointer table)")
         self.numel = numel
+        self.slots = int(slots)
+        self.timeout_ns = int(timeout_s * 1e9)
         self.stride = (numel + 3) // 4 * 4  # rows start 16-byte aligned
-        self.recv = torch.zeros((self.world, self.stride), dtype=torch.float32, device=device)
+        self.device = torch.device(device)
+        # ---- local work that can fail happens BEFORE any collective (allocation, handle export)
+        self.recv = torch.zeros((self.slots, self.world, self.stride), dtype=torch.float32, device=device)
         self.flags = torch.zeros((self.world,), dtype=torch.int64, device=device)
-        self._sync = torch.zeros((2,), dtype=torch.int32, device=device)  # [CTAs done, step]: owned by the kernel
+        self.acks = torch.zeros((self.world,), dtype=torch.int64, device=device)
+        self._sync = torch.zeros((2,), dtype=torch.int32, device=device)  # [CTAs done, CTAs timed out]
         self.step = 0
+        self._handles = None
+        self._peers = []
+        self._rows = self._flags = self._acks = None
+
+    # -- set-up in three stages so that a failure on one rank never leaves the others inside a collective
+    def _export(self):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self._handles = [reduce_tensor(self.recv), reduce_tensor(self.flags), reduce_tensor(self.acks)]
+
+    def _exchange(self):
         handles = [None] * self.world
-        dist.all_gather_object(handles, [reduce_tensor(self.recv), reduce_tensor(self.flags)], group=group)
-        self._peers = []  # keep the mappings alive
-        rows, flags = (ctypes.c_void_p * self.world)(), (ctypes.c_void_p * self.world)()
+        dist.all_gather_object(handles, self._handles, group=self.group)
+        return handles
+
+    def _open(self, handles):
+        import ctypes
+
+        from . import _lib
+
+        rows = (ctypes.c_void_p * self.world)()
+        flags = (ctypes.c_void_p * self.world)()
+        acks = (ctypes.c_void_p * self.world)()
         for r in range(self.world):
             if r == self.rank:
-                pr, pf = self.recv, self.flags
+                pr, pf, pa = self.recv, self.flags, self.acks
             else:
                 # torch's rebuild would open the IPC handle in the context of the PRODUCER's device index; kernels on
-                # my device fault on such a mapping (measured, scripts/peer_diag.py).  Opening it with my own device
-                # current (argument 6 of rebuild_cuda_tensor = the device to open under) maps the peer's memory into my
-                # device's address space with peer access -- the pattern NCCL itself uses.
-                (f0, a0), (f1, a1) = handles[r]
-                a0, a1 = list(a0), list(a1)
-                assert isinstance(a0[6], int) and isinstance(a1[6], int), "unexpected torch IPC handle layout"
-                peer_dev = a0[6]
-                a0[6] = a1[6] = self.recv.device.index
-                with torch.cuda.device(self.recv.device):
+                # my device fault on such a mapping (measured).  Opening it with my own device current (argument 6 of
+                # rebuild_cuda_tensor = the device to open under) maps the peer's memory into my device's address
+                # space with peer access -- the pattern NCCL itself uses.
+                opened = []
+                peer_dev = None
+                for fn, args in handles[r]:
+                    args = list(args)
+                    assert isinstance(args[6], int), "unexpected torch IPC handle layout"
+                    peer_dev = args[6]
+                    args[6] = self.device.index
+                    opened.append((fn, args))
+                with torch.cuda.device(self.device):
                     _lib.call("tsmdet_enable_peer_access", peer_dev)
-                    pr, pf = f0(*a0), f1(*a1)
-            self._peers.append((pr, pf))
+                    pr, pf, pa = [fn(*args) for fn, args in opened]
+            self._peers.append((pr, pf, pa))  # keep the mappings alive
             rows[r] = pr.data_ptr() + self.rank * self.stride * 4
             flags[r] = pf.data_ptr() + self.rank * 8
-        self._rows, self._flags = rows, flags
+            acks[r] = pa.data_ptr() + self.rank * 8
+        self._rows, self._flags, self._acks = rows, flags, acks
+
+    @classmethod
+    def create(cls, numel: int, device, group=None, slots: int = 2, timeout_s: float = 120.0):
+        """Collective constructor: every rank gets a working PeerGather, or every rank gets None."""
+
+        def agree(ok_local: bool) -> bool:
+            ok = torch.tensor([1 if ok_local else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(ok.item()))
+
+        pg, err = None, None
+        try:
+            pg = cls(numel, device, group, slots, timeout_s)
+            pg._export()
+        except Exception as e:  # noqa: BLE001
+            pg, err = None, e
+        if not agree(pg is not None):
+            return None, err
+        handles = pg._exchange()
+        try:
+            pg._open(handles)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not agree(err is None):
+            return None, err
+        return pg, None
+
+    def _slot(self, step: Optional[int] = None) -> int:
+        return ((self.step if step is None else step) - 1) % self.slots
 
     def put(self, packed: torch.Tensor):
-        """Stream-ordered, asynchronous (one kernel on the current stream); returns this rank's receive buffer, whose
-        rows fill as the peers' stores land."""
+        """Stream-ordered, asynchronous (one kernel on the current stream); returns the ring slot of this step, whose
+        rows fill as the peers' stores land.  Everything this rank still wants to read from the previous step must
+        have been issued on this stream (or be ordered before it) by now."""
         from . import _lib
 
+        assert self._rows is not None, "PeerGather not connected (use PeerGather.create)"
         assert packed.is_cuda and packed.dtype == torch.float32 and packed.is_contiguous() and packed.numel() == self.numel
         self.step += 1
-        _lib.call("tsmdet_peer_put", _lib.ptr(packed), self.numel, self.world, self._rows, self._flags,
-                  _lib.ptr(self._sync), _lib.stream_ptr(packed.device))
-        return self.recv
+        _lib.call("tsmdet_peer_put", _lib.ptr(packed), self.numel, self.world, self._rows, self._flags, self._acks,
+                  _lib.ptr(self.acks), _lib.ptr(self._sync), self.step, self.slots, self.world * self.stride,
+                  self.timeout_ns, _lib.stream_ptr(packed.device))
+        return self.recv[self._slot()]
 
-    def wait_stream(self):
-        """Order the current stream after the arrival of every rank's records of this rank's last ``put`` (a one-warp
-        kernel watching the flag words) -- what a consumer on the device, or a D2H copy of the result, needs."""
+    def wait_stream(self, step: Optional[int] = None):
+        """Order the current stream after the arrival of every rank's records of ``step`` (default: this rank's last
+        ``put``): a one-warp kernel watching the flag words -- what a consumer on the device, or a D2H copy of the
+        result, needs."""
         from . import _lib
 
-        _lib.call("tsmdet_peer_wait", _lib.ptr(self.flags), self.world, _lib.ptr(self._sync), -1,
+        want = self.step if step is None else step
+        _lib.call("tsmdet_peer_wait", _lib.ptr(self.flags), self.world, want, self.slots, self.timeout_ns,
                   _lib.stream_ptr(self.flags.device))
 
     def wait(self, step: Optional[int] = None, timeout_s: float = 30.0):
-        """Block the host until every rank's records of ``step`` (default: the last ``put``) are in ``recv``."""
+        """Block the host until every rank's records of ``step`` (default: the last ``put``) are in the ring."""
         import time
 
         want = self.step if step is None else step
@@ -178,6 +243,7 @@ class PeerGather:
             if time.perf_counter() - t0 > timeout_s:
                 raise RuntimeError(f"PeerGather.wait: flags {self.flags.tolist()} never reached {want}")
 
-    def views(self, frames: int, k: int):
+    def views(self, frames: int, k: int, step: Optional[int] = None):
         n = frames * k * 9
-        return self.recv[:, :n].view(self.world, frames, k, 9), self.recv[:, n:self.numel].view(torch.int32)
+        slot = self.recv[self._slot(step)]
+        return slot[:, :n].view(self.world, frames, k, 9), slot[:, n:self.numel].view(torch.int32)
