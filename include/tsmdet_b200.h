@@ -146,6 +146,32 @@ int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const 
                          const int* channels, const float* const* weights, const float* const* biases, float* out,
                          int out_ctot, int out_c0, int precision, void* stream);
 
+/* ---------------------------------------------------------------- centroid voxelisation ------
+ * The tail of the layer-0 branch (pointnet2/pointnet2_batch/pointnet2_modules.py:1323-1355) in one call:
+ * voxel indices ((xyz - range_min) / voxel_size truncated, pcdet/utils/voxel_aggregation_utils.py:48-83), the sorted
+ * unique voxels with inverse indices and counts (voxel_idxs.unique(dim=0, ...), :145) and the per-voxel means of
+ * [b, x, y, z, features] (:152-159), points added in ascending index order (deterministic; bit-equal to the reference
+ * functions on the CPU).  new_xyz (B,M,3) f32, features (B,C,M) f32 | NULL; M <= 16384.
+ * Outputs (capacity B*M rows; the first *num_unique rows of the last three are valid):
+ *   voxel_idxs (B*M,4) i64 [b,z,y,x], unique_idxs (B*M) i64, centroids (.,4+C) f32, centroid_voxel_idxs (.,4) i64,
+ *   labels_count (.) i64, num_unique (1) i32 device; err (1) i32 device, bit 0 = a voxel coordinate outside
+ *   [-32768, 32767] (may be NULL). */
+int tsmdet_voxel_centroids(int b, int m, int c, const float* new_xyz, const float* features, float vx, float vy, float vz,
+                           float x0, float y0, float z0, long long* voxel_idxs, float* centroids,
+                           long long* centroid_voxel_idxs, long long* labels_count, long long* unique_idxs,
+                           int* num_unique, int* err, void* stream);
+/* get_centroid_per_voxel (voxel_aggregation_utils.py:132-161) with the reference's own argument layout:
+ * points (B*M,4+F) f32 rows [b,x,y,z,f...], voxel_idxs (B*M,4) i64 [b,z,y,x], rows grouped frame after frame with M
+ * rows each (err bit 1 otherwise), num_points_in_voxel (B*M) i64 | NULL (weighted means, :147-150). */
+int tsmdet_centroid_per_voxel(int b, int m, int f, const float* points, const long long* voxel_idxs,
+                              const long long* num_points_in_voxel, float* centroids, long long* centroid_voxel_idxs,
+                              long long* labels_count, long long* unique_idxs, int* num_unique, int* err, void* stream);
+/* generate_voxel2pinds (pcdet/utils/common_utils.py:248-265): out (B,Z,Y,X) i32 = row number of the voxel in
+ * indices ((n,4) i32 [b,z,y,x]), -1 elsewhere.  prev_indices != NULL: out still holds the table of prev_indices and
+ * only those n_prev entries are reset (O(voxels)); NULL: the whole table is filled with -1 first. */
+int tsmdet_voxel2pinds(int n, const int* indices, int n_prev, const int* prev_indices, int nb, int nz, int ny, int nx,
+                       int* out, int* err, void* stream);
+
 /* ---------------------------------------------------------------- IoU / NMS ---------
  * boxes (N,7) f32 [x,y,z,dx,dy,dz,heading] on the device.
  * ref: iou3d_nms/src/iou3d_nms_api.cpp:12-13 boxes_overlap_bev_gpu / boxes_iou_bev_gpu

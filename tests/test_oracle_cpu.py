@@ -207,3 +207,26 @@ def test_empty_and_degenerate_inputs(orc):
     cnt, idx = orc.ball_query(1.0, 4, np.zeros((1, 0, 3), np.float32), np.zeros((1, 2, 3), np.float32))
     assert (cnt == 0).all() and (idx == 0).all()
     assert orc.fps(np.zeros((2, 1, 3), np.float32), 1).tolist() == [[0], [0]]
+
+
+def test_voxel_oracle_matches_reference_functions():
+    """oracle/voxel_oracle.py vs the reference's own get_voxel_indices / get_centroid_per_voxel / generate_voxel2pinds
+    (tests/golden/voxel_centroids.npz, made by tests/golden/make_golden_voxel.py from /root/reference): bit-exact."""
+    import torch
+
+    from oracle import voxel_oracle as vo
+
+    g = np.load(os.path.join(GOLD, "voxel_centroids.npz"))
+    out = vo.voxelize_centroids(torch.from_numpy(g["xyz"]), torch.from_numpy(g["feats"]), g["voxel_size"].tolist(),
+                                g["pc_range"].tolist())
+    assert np.array_equal(out["voxel_idxs"].numpy(), g["voxel_idxs"])
+    assert np.array_equal(out["centroid_voxel_idxs"].numpy(), g["centroid_voxel_idxs"])
+    assert np.array_equal(out["num_points_in_voxel"].numpy(), g["labels_count"])
+    assert np.array_equal(out["unique_idxs"].numpy(), g["unique_idxs"])
+    assert np.array_equal(out["centroids_coords_features"].numpy(), g["centroids"])  # same fp32 summation order
+    cw, _, cntw, _ = vo.get_centroid_per_voxel(torch.from_numpy(g["rows"]), torch.from_numpy(g["voxel_idxs"]),
+                                               torch.from_numpy(g["weights"]))
+    assert np.array_equal(cw.numpy(), g["centroids_w"]) and np.array_equal(cntw.numpy(), g["labels_count_w"])
+    v2p = vo.generate_voxel2pinds(torch.from_numpy(g["centroid_voxel_idxs"]).int(), g["xyz"].shape[0], g["spatial_shape"])
+    nz = np.stack(np.nonzero(v2p.numpy() >= 0), 1)
+    assert np.array_equal(nz, g["v2p_nonempty"]) and np.array_equal(v2p.numpy()[v2p.numpy() >= 0], g["v2p_values"])
