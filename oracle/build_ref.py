@@ -10,6 +10,9 @@ The reference's hot-path native code compiles from its own few source files:
 * ``/root/reference/pcdet/ops/iou3d_nms/src/*.{cpp,cu}``
   -> ``oracle/_ref/iou3d_nms_cuda.so``        (5 pybind functions,
   ``iou3d_nms_api.cpp:11-17``)
+* ``/root/reference/pcdet/ops/pointnet2/pointnet2_stack/src/*.{cpp,cu}``
+  -> ``oracle/_ref/pointnet2_stack_cuda.so``  (voxel query, stack grouping,
+  stack FPS: SURVEY.md 8 f3)
 
 The sources are compiled where they lie (read-only); only build products are
 written, and only under ``oracle/_ref/`` (git-ignored, but NOT gpurun-ignored, so
@@ -34,6 +37,8 @@ OUT = os.path.join(HERE, "_ref")
 EXTS = {
     "pointnet2_batch_cuda": "pcdet/ops/pointnet2/pointnet2_batch/src",
     "iou3d_nms_cuda": "pcdet/ops/iou3d_nms/src",
+    # voxel query (+dilated), stack grouping, stack FPS (15 pybind functions, src/pointnet2_api.cpp:12-32)
+    "pointnet2_stack_cuda": "pcdet/ops/pointnet2/pointnet2_stack/src",
 }
 
 
@@ -92,7 +97,7 @@ PY_FILES = {
 
 
 def pyc_path(modname: str) -> str:
-    return os.path.join(OUT, "pyc", modname + ".pyc")
+    return os.path.join(OUT, "pyc", modname + ".pycbin")  # not *.pyc: snapshot tools tend to drop those
 
 
 def build_py() -> dict:

@@ -29,7 +29,7 @@ _u64p = ctypes.POINTER(ctypes.c_uint64)
 
 def build(force: bool = False) -> str:
     """Compile ``liboracle.so`` with the committed Makefile (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("pointnet2_oracle.c", "iou3d_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pointnet2_oracle.c", "iou3d_oracle.c", "stack_oracle.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
@@ -274,3 +274,54 @@ def nms(boxes, scores, thresh: float, normal: bool = False, order=None):
     order = np.asarray(order, dtype=np.int64)
     keep = nms_sorted(boxes[order], thresh, normal)
     return order[keep]
+
+
+# --------------------------------------------------------------- pointnet2_stack
+def voxel_query(max_range, radius: float, nsample: int, xyz, new_xyz, new_coords, point_indices, stride=(1, 1, 1),
+                former_radius: float | None = None):
+    """voxel_query_gpu.cu:10-98 (former_radius None) / :125-215 (dilated) -> (idx (M,nsample), cnt_unique (M),
+    idx_cnt (M) | None), raw kernel outputs (idx[:,0] == -1 marks an empty ball)."""
+    xyz, new_xyz = _f(xyz), _f(new_xyz)
+    new_coords, point_indices = _i(new_coords), _i(point_indices)
+    m = new_coords.shape[0]
+    _, r1, r2, r3 = point_indices.shape
+    idx = np.zeros((m, nsample), dtype=np.int32)
+    cnt_unique = np.zeros((m,), dtype=np.int32)
+    idx_cnt = np.zeros((m,), dtype=np.int32) if former_radius is not None else None
+    lib().orc_voxel_query(
+        m, r1, r2, r3, nsample, ctypes.c_float(-1.0 if former_radius is None else former_radius), ctypes.c_float(radius),
+        int(max_range[0]), int(max_range[1]), int(max_range[2]), int(stride[0]), int(stride[1]), int(stride[2]),
+        _p(new_xyz, _f32p), _p(xyz, _f32p), _p(new_coords, _i32p), _p(point_indices, _i32p), _p(idx, _i32p),
+        _p(cnt_unique, _i32p), _p(idx_cnt, _i32p) if idx_cnt is not None else None)
+    return idx, cnt_unique, idx_cnt
+
+
+def stack_group_points(features, features_batch_cnt, idx, idx_batch_cnt):
+    features, idx = _f(features), _i(idx)
+    fb, ib = _i(features_batch_cnt), _i(idx_batch_cnt)
+    m, nsample = idx.shape
+    c = features.shape[1]
+    out = np.empty((m, c, nsample), dtype=np.float32)
+    lib().orc_stack_group_points(len(ib), m, c, nsample, _p(features, _f32p), _p(fb, _i32p), _p(idx, _i32p),
+                                 _p(ib, _i32p), _p(out, _f32p))
+    return out
+
+
+def stack_group_points_grad(grad_out, idx, idx_batch_cnt, features_batch_cnt, n: int):
+    grad_out, idx = _f(grad_out), _i(idx)
+    fb, ib = _i(features_batch_cnt), _i(idx_batch_cnt)
+    m, c, nsample = grad_out.shape
+    g = np.zeros((n, c), dtype=np.float32)
+    lib().orc_stack_group_points_grad(len(ib), m, c, n, nsample, _p(grad_out, _f32p), _p(idx, _i32p), _p(ib, _i32p),
+                                      _p(fb, _i32p), _p(g, _f32p))
+    return g
+
+
+def stack_fps(xyz, xyz_batch_cnt, npoints):
+    """sampling_gpu.cu:188-316: xyz (sum N,3), xyz_batch_cnt (B), npoints (B) -> (sum M) global row numbers."""
+    xyz = _f(xyz)
+    cnt, npts = _i(xyz_batch_cnt), _i(npoints)
+    temp = np.full((xyz.shape[0],), 1e10, dtype=np.float32)
+    out = np.zeros((max(int(npts.sum()), 1),), dtype=np.int32)
+    lib().orc_stack_fps(len(cnt), _p(xyz, _f32p), _p(temp, _f32p), _p(cnt, _i32p), _p(out, _i32p), _p(npts, _i32p))
+    return out[: int(npts.sum())]

@@ -13,7 +13,7 @@
  * Build: gcc -O2 -ffp-contract=off (so only the explicit fmaf() calls fuse).
  * Parity pin: tests/golden/ holds outputs of the reference's own CUDA kernels
  * (oracle/_ref, built from /root/reference by oracle/build_ref.py) run on a B200;
- * tests/test_oracle_golden.py checks this file against them bit for bit.
+ * tests/test_oracle_cpu.py checks this file against them bit for bit.
  *
  * Reference (all under /root/reference/pcdet/ops/pointnet2/pointnet2_batch/src):
  *   sampling_gpu.cu:93-98      __update (tree-reduction tie rule)

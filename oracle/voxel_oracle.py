@@ -57,7 +57,7 @@ def voxelize_centroids(new_xyz: torch.Tensor, new_features: torch.Tensor, voxel_
     batch_idx = torch.arange(b).view(b, 1).expand(b, m).reshape(-1, 1).long()
     voxel_idxs = torch.cat((batch_idx, torch.flip(vi, dims=[1])), dim=-1)
     xyz_for_voxel = torch.cat([batch_idx, new_xyz.view(-1, 3)], dim=-1)
-    feats = new_features.permute(0, 2, 1).contiguous().view(-1, c)
+    feats = new_features.permute(0, 2, 1).contiguous().reshape(b * m, c)
     point_for_voxel = torch.cat([xyz_for_voxel, feats], dim=-1)
     cent, cvi, counts, inverse = get_centroid_per_voxel(point_for_voxel, voxel_idxs)
     return {"voxel_idxs": voxel_idxs, "centroids_coords_features": cent, "centroid_voxel_idxs": cvi,

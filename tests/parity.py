@@ -8,9 +8,10 @@ Floating-point metrics, stated as measured instead of one loose bound (VERDICT r
   max_rel_all          max over |want| > 1e-3 * max|want| of |got - want| / |want|  -- elementwise, reported only:
                        after ReLU a near-zero output is a cancellation of O(scale) terms, so bf16 operands
                        (2^-9 relative each) give it an O(2^-9 * scale) ABSOLUTE error whatever the kernel does.
-Bars: fp32 path max_abs_over_scale <= 2e-5 (1e-5 * scale is the last-ulp noise of a K<=259 fp32 dot product in a
-different summation order than cuDNN's, the bar states what is met); bf16 path max_abs_over_scale <= 1e-2,
-rel_l2 <= 1e-2 and max_rel_big <= 5e-2.
+Bars (north_star: "max abs 1e-5 for fp32, 1e-2 rel for bf16 MLP"): fp32 path max_abs <= 1e-5 ABSOLUTE (measured on
+B200: <= 1.2e-6 over every test shape), rel_l2 <= 1e-5; bf16 path rel_l2 <= 1e-2 (the "1e-2 rel", as a norm; measured
+<= 2.8e-3), max_abs_over_scale <= 1e-2 (measured <= 4.3e-3) and max_rel_big <= 5e-2 (measured <= 3.1e-2: an output
+above a tenth of the largest one is within 5 % elementwise).
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ import numpy as np
 import torch
 
 BARS = {
-    "fp32": {"max_abs_over_scale": 2e-5, "rel_l2": 1e-5, "max_rel_big": 1e-4},
+    "fp32": {"max_abs": 1e-5, "rel_l2": 1e-5, "max_rel_big": 1e-4},
     "bf16": {"max_abs_over_scale": 1e-2, "rel_l2": 1e-2, "max_rel_big": 5e-2},
     "tf32": {"max_abs_over_scale": 2e-3, "rel_l2": 2e-3, "max_rel_big": 6e-3},
 }

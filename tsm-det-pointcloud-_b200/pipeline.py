@@ -115,6 +115,7 @@ class SABackboneNMS(torch.nn.Module):
         self._trace = None  # list of (name, event) when tracing (see trace_step)
         self._pg = None
         self._pg_tried = False
+        self._cap_stream = None
         self.eval()
 
     # ------------------------------------------------------------------ the DAG
@@ -256,11 +257,16 @@ class SABackboneNMS(torch.nn.Module):
             self._trace = None
 
     # ------------------------------------------------------------------ graph capture / replay
-    def _capture(self, key, static_in, run):
+    def _capture(self, key, static_in, run, keep=()):
         dev = static_in[0].device
         # the sampling chain is captured on the capture stream itself: TSMDET_FPS_PRIORITY=1 makes it a high-priority
-        # stream (its kernels' graph nodes inherit the priority), so FPS CTAs are placed first when SMs free up
-        cap = torch.cuda.Stream(dev, priority=-1 if os.environ.get("TSMDET_FPS_PRIORITY", "0") == "1" else 0)
+        # stream (its kernels' graph nodes inherit the priority), so FPS CTAs are placed first when SMs free up.
+        # ONE capture stream per engine, like its side streams: the library's scratch buffers are keyed by stream, and
+        # torch hands out streams round-robin from a pool of 32 -- a fresh stream per capture would eventually alias
+        # another lane's stream and share its scratch with a concurrently replaying graph.
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(dev, priority=-1 if os.environ.get("TSMDET_FPS_PRIORITY", "0") == "1" else 0)
+        cap = self._cap_stream
         cap.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap):
             for _ in range(2):  # warm-up on the capture stream: grows every scratch buffer, folds BN, plans FPS
@@ -272,7 +278,8 @@ class SABackboneNMS(torch.nn.Module):
             out = run()
         torch.cuda.current_stream(dev).wait_stream(cap)
         # kernels of this library inside one replay (the graph also holds a few torch sort/gather kernels)
-        ent = {"graph": graph, "in": static_in, "out": out, "launches": _lib.launch_count - l0}
+        # `keep`: tensors the captured kernels address that nothing else references (the graph holds raw pointers)
+        ent = {"graph": graph, "in": static_in, "out": out, "launches": _lib.launch_count - l0, "keep": keep}
         self._graphs[key] = ent
         return ent
 
@@ -302,7 +309,8 @@ class SABackboneNMS(torch.nn.Module):
         scores = flat[n_pts + n_box:].view(f, p)
         xyz = torch.empty((f, n, 3), dtype=torch.float32, device=dev)
         feats = torch.empty((f, c, n), dtype=torch.float32, device=dev)
-        return self._capture(key, [flat], lambda: self._run(xyz, feats, boxes, scores, points=points))
+        return self._capture(key, [flat], lambda: self._run(xyz, feats, boxes, scores, points=points),
+                             keep=(xyz, feats, points, boxes, scores))
 
     def _gather(self, res):
         """The one collective of the path, issued after the replay: equal shards, so a single exchange of the packed
