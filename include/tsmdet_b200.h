@@ -172,6 +172,32 @@ int tsmdet_centroid_per_voxel(int b, int m, int f, const float* points, const lo
 int tsmdet_voxel2pinds(int n, const int* indices, int n_prev, const int* prev_indices, int nb, int nz, int ny, int nx,
                        int* out, int* err, void* stream);
 
+/* ---------------------------------------------------------------- pointnet2_stack ops ---------
+ * ref: pointnet2/pointnet2_stack/src/pointnet2_api.cpp:13-14 voxel_query_wrapper / voxel_query_dilated_wrapper
+ *      (voxel_query.cpp:27-75; voxel_query_gpu.cu:10-98, 125-215).  new_xyz (M,3), xyz (N,3), new_coords (M,4) i32
+ *      [b,z,y,x], point_indices (B,R1,R2,R3) i32 dense voxel -> point table; idx (M,nsample) i32 ZEROED by the caller,
+ *      cnt_unique (M) i32, idx_cnt (M) i32.  Random replacement beyond nsample hits uses cuRAND XORWOW seeded with the
+ *      centre's row number, exactly as the reference: results are bit-identical to its kernels. */
+int tsmdet_voxel_query(int m, int r1, int r2, int r3, int nsample, float radius, int z_range, int y_range, int x_range,
+                       const float* new_xyz, const float* xyz, const int* new_coords, const int* point_indices, int* idx,
+                       int* cnt_unique, void* stream);
+int tsmdet_voxel_query_dilated(int m, int r1, int r2, int r3, int nsample, float former_radius, float radius, int z_range,
+                               int y_range, int x_range, int z_stride, int y_stride, int x_stride, const float* new_xyz,
+                               const float* xyz, const int* new_coords, const int* point_indices, int* idx, int* cnt_unique,
+                               int* idx_cnt, void* stream);
+/* ref: pointnet2_api.cpp:19-20 group_points(_grad)_wrapper (group_points_gpu.cu:14-95): features (N,C) stacked,
+ *      idx (M,nsample) frame-local rows, *_batch_cnt (B) i32 on the device -> out (M,C,nsample). */
+int tsmdet_stack_group_points(int b, int m, int c, int nsample, const float* features, const int* features_batch_cnt,
+                              const int* idx, const int* idx_batch_cnt, float* out, void* stream);
+int tsmdet_stack_group_points_grad(int b, int m, int c, int n, int nsample, const float* grad_out, const int* idx,
+                                   const int* idx_batch_cnt, const int* features_batch_cnt, float* grad_features,
+                                   void* stream);
+/* ref: pointnet2_api.cpp:17 stack_farthest_point_sampling_wrapper (sampling_gpu.cu:188-345): xyz (N,3) stacked, temp (N)
+ *      pre-filled (1e10; receives the final min-distances), counts (B) i32 on the device, idxs (sum M) GLOBAL rows.
+ *      n_total = N.  The reference's block size is 1024 for every cloud, and so is the tie rule here. */
+int tsmdet_stack_farthest_point_sampling(int n_total, int batch_size, const float* xyz, float* temp,
+                                         const int* xyz_batch_cnt, int* idxs, const int* num_sampled_points, void* stream);
+
 /* ---------------------------------------------------------------- IoU / NMS ---------
  * boxes (N,7) f32 [x,y,z,dx,dy,dz,heading] on the device.
  * ref: iou3d_nms/src/iou3d_nms_api.cpp:12-13 boxes_overlap_bev_gpu / boxes_iou_bev_gpu

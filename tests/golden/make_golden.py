@@ -156,15 +156,75 @@ def gpu_fixtures(out):
     nms["full_nz_j"] = nz[1].astype(np.int32)
     nms["full_nz_v"] = f[nz]
     np.savez_compressed(os.path.join(out, "iou_nms_gpu.npz"), **nms)
+    stack_fixtures(out, T)
     print("gpu fixtures written to", out)
+
+
+def stack_fixtures(out, T):
+    """pointnet2_stack: voxel query (+dilated), stacked grouping, stacked FPS by the reference kernels."""
+    import torch
+
+    st = build_ref.load_ref("pointnet2_stack_cuda")
+    assert st is not None, "oracle/_ref/pointnet2_stack_cuda.so missing: run python oracle/build_ref.py"
+    dev = torch.device("cuda:0")
+    sc = synth.voxel_scene(2, 3000, 300, seed=3)
+    g = {k: v for k, v in sc.items() if k != "point_indices"}
+    nzv = np.nonzero(sc["point_indices"] >= 0)
+    g["table_shape"] = np.array(sc["point_indices"].shape)
+    g["table_nz"] = np.stack(nzv, 1).astype(np.int32)
+    g["table_val"] = sc["point_indices"][nzv]
+    m = sc["new_coords"].shape[0]
+    _, r1, r2, r3 = sc["point_indices"].shape
+    xyz, new_xyz, coords, table = T(sc["xyz"]), T(sc["new_xyz"]), T(sc["new_coords"]), T(sc["point_indices"])
+    for name, rng, radius, ns in (("q_r4", (2, 4, 4), 1.6, 16), ("q_r8", (3, 8, 8), 3.2, 32)):
+        idx = torch.zeros((m, ns), dtype=torch.int32, device=dev)
+        cu = torch.zeros((m, 1), dtype=torch.int32, device=dev)
+        st.voxel_query_wrapper(m, r1, r2, r3, ns, radius, rng[0], rng[1], rng[2], new_xyz, xyz, coords, table, idx, cu)
+        g[name + "_idx"], g[name + "_cnt_unique"] = idx.cpu().numpy(), cu.cpu().numpy()
+        g[name + "_args"] = np.array([rng[0], rng[1], rng[2], ns], np.int32)
+        g[name + "_radius"] = np.float32(radius)
+    for name, rng, stride, r_in, r_out, ns in (("d_r8", (2, 8, 8), (1, 1, 1), 0.8, 3.2, 16), ("d_s2", (4, 8, 8), (2, 2, 2), 0.0, 3.2, 32)):
+        idx = torch.zeros((m, ns), dtype=torch.int32, device=dev)
+        cu = torch.zeros((m, 1), dtype=torch.int32, device=dev)
+        ic = torch.zeros((m, 1), dtype=torch.int32, device=dev)
+        st.voxel_query_dilated_wrapper(m, r1, r2, r3, ns, r_in, r_out, rng[0], rng[1], rng[2], stride[0], stride[1], stride[2],
+                                       new_xyz, xyz, coords, table, idx, cu, ic)
+        g[name + "_idx"], g[name + "_cnt_unique"], g[name + "_idx_cnt"] = idx.cpu().numpy(), cu.cpu().numpy(), ic.cpu().numpy()
+        g[name + "_args"] = np.array([*rng, *stride, ns], np.int32)
+        g[name + "_radii"] = np.array([r_in, r_out], np.float32)
+    # stacked grouping with frame-local indices
+    feats = np.random.default_rng(4).normal(size=(sc["xyz"].shape[0], 6)).astype(np.float32)
+    starts = np.concatenate([[0], np.cumsum(sc["xyz_batch_cnt"])[:-1]])
+    local = np.concatenate([np.random.default_rng(5 + f).integers(0, sc["xyz_batch_cnt"][f], size=(sc["new_xyz_batch_cnt"][f], 8))
+                            for f in range(2)]).astype(np.int32)
+    outg = torch.empty((m, 6, 8), dtype=torch.float32, device=dev)
+    st.group_points_wrapper(2, m, 6, 8, T(feats), T(sc["xyz_batch_cnt"]), T(local), T(sc["new_xyz_batch_cnt"]), outg)
+    g["grp_feats"], g["grp_idx"], g["grp_out"] = feats, local, outg.cpu().numpy()
+    # stacked FPS, ragged clouds incl. duplicates (ties) and one cloud smaller than the 1024-thread block
+    clouds = [synth.cloud_dup_padded(1, 5000, seed=6)[0], synth.cloud_uniform(1, 700, seed=7)[0], synth.cloud_lattice(1, 2500, seed=8)[0]]
+    pts = np.concatenate(clouds).astype(np.float32)
+    cnt = np.array([len(c) for c in clouds], np.int32)
+    npts = np.array([400, 100, 300], np.int32)
+    temp = torch.full((pts.shape[0],), 1e10, dtype=torch.float32, device=dev)
+    oi = torch.zeros((int(npts.sum()),), dtype=torch.int32, device=dev)
+    st.stack_farthest_point_sampling_wrapper(T(pts), temp, T(cnt), oi, T(npts))
+    g["sfps_xyz"], g["sfps_cnt"], g["sfps_npoint"], g["sfps_idx"] = pts, cnt, npts, oi.cpu().numpy()
+    np.savez_compressed(os.path.join(out, "stack_ops.npz"), **g)
+    print("stack fixtures: voxel query hits per centre up to", int(g["q_r8_cnt_unique"].max()))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.dirname(os.path.abspath(__file__)))
     ap.add_argument("--cpu-only", action="store_true")
+    ap.add_argument("--stack-only", action="store_true", help="only the pointnet2_stack fixtures (stack_ops.npz)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
+    if args.stack_only:
+        import torch
+
+        stack_fixtures(args.out, lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda())
+        raise SystemExit(0)
     cpu_fixtures(args.out)
     if not args.cpu_only:
         gpu_fixtures(args.out)

@@ -76,3 +76,37 @@ def boxes_clustered(n, seed=0, centres=200, sigma=0.3, sigma_theta=0.1):
 
 def scores_random(n, seed=0):
     return np.random.default_rng(seed + 7).uniform(0, 1, n).astype(np.float32)
+
+
+def voxel_scene(b, n_per, m_per, seed=0, voxel=(0.4, 0.4, 0.5), rng_range=KITTI_RANGE, crowd=True):
+    """Inputs of the pointnet2_stack voxel query as the SA layers >= 1 build them: `b` frames of `n_per` source points
+    (one per occupied voxel: duplicates of a voxel are dropped), their dense voxel -> row table `(b, Z, Y, X)`, and
+    `m_per` query centres per frame with their voxel coordinates.  Returns dict of numpy arrays (stacked layouts)."""
+    r = np.random.default_rng(seed)
+    lo, hi = np.array(rng_range[0]), np.array(rng_range[1])
+    vs = np.array(voxel)
+    grid = np.round((hi - lo) / vs).astype(np.int64)          # x, y, z cells
+    pts, cnts, new, new_cnt, coords = [], [], [], [], []
+    table = -np.ones((b, grid[2], grid[1], grid[0]), dtype=np.int32)
+    row0 = 0
+    for f in range(b):
+        p = r.uniform(lo, hi, size=(n_per, 3))
+        if crowd:  # a dense patch: far more than nsample hits per centre (exercises the random replacement)
+            p[: n_per // 2] = p[:1] + r.normal(0, 2.5, size=(n_per // 2, 3))
+            p = np.clip(p, lo, hi - 1e-3)
+        p = p.astype(np.float32)
+        v = np.floor((p - lo) / vs).astype(np.int64)
+        v = np.minimum(v, grid - 1)
+        _, first = np.unique(v[:, 2] * grid[1] * grid[0] + v[:, 1] * grid[0] + v[:, 0], return_index=True)
+        first.sort()
+        p, v = p[first], v[first]
+        table[f, v[:, 2], v[:, 1], v[:, 0]] = row0 + np.arange(len(p), dtype=np.int32)
+        q = p[r.choice(len(p), size=m_per, replace=len(p) < m_per)] + r.normal(0, 0.2, size=(m_per, 3)).astype(np.float32)
+        q = np.clip(q, lo, hi - 1e-3).astype(np.float32)
+        qv = np.minimum(np.floor((q - lo) / vs).astype(np.int64), grid - 1)
+        pts.append(p); cnts.append(len(p)); new.append(q); new_cnt.append(m_per)
+        coords.append(np.concatenate([np.full((m_per, 1), f), qv[:, ::-1]], 1).astype(np.int32))
+        row0 += len(p)
+    return {"xyz": np.concatenate(pts), "xyz_batch_cnt": np.array(cnts, np.int32), "new_xyz": np.concatenate(new),
+            "new_xyz_batch_cnt": np.array(new_cnt, np.int32), "new_coords": np.concatenate(coords),
+            "point_indices": table}
