@@ -3,7 +3,7 @@
 // 1259-1268, 1297-1300) and the point-wise MLPs of the same file (PointnetFPModule.mlp :175-176, aggregation_mlp
 // :1320-1321: [1x1 conv + ReLU]* over a dense (B,C,n) tensor, no pooling) in one template.
 //
-// What changed against sa_mlp_tc.cu (kept for output widths < 64 and nsample < 8), and why -- ncu of round 1 showed
+// What changed against sa_mlp_tc.cu (kept for nsample < 8 and as the A/B reference, TSMDET_MLP_V1=1), and why -- ncu of round 1 showed
 // the tensor pipe 14 % active with each tile spending most of its time in the epilogues:
 //
 //  * THE LAST LAYER IS COMPUTED TRANSPOSED.  Both operands are K-major core-matrix images in shared memory, so the
@@ -16,8 +16,12 @@
 //    same layout to write 512 contiguous bytes per thread.
 //  * epilogues keep several tcgen05.ld in flight per wait::ld (two 32-column loads instead of one 16-column load),
 //    add the bias with packed FADD2 and convert with F2FP.RELU (ReLU for free);
-//  * the gather has every 16-byte load of a row in flight at once and the next tile's indices are prefetched while
-//    the current tile computes; one group barrier per layer (three per tile at three layers, five before).
+//  * the gather of tile i+1 is issued as cp.async (LDGSTS, 16 bytes per feature chunk, zero-fill for masked rows)
+//    straight into the operand buffer as soon as tile i's last MMA has consumed it, and lands while tile i's pooling
+//    epilogue runs; the neighbour indices are prefetched one tile further ahead; one group barrier per layer
+//    (three per tile at three layers, five before);
+//  * kernel parameters are __grid_constant__ (the per-layer plan arrays are indexed dynamically: without it the
+//    compiler copies them to local memory -- LDL on the critical path in the ncu source view of the first version).
 //
 // One CTA = GROUPS x 128 threads; a group = one independent 128-row tile pipeline (own operand buffer, TMEM
 // columns, mbarrier, named barrier) over the CTA's resident weights, persistent over tiles.
@@ -42,6 +46,7 @@ struct Tc2Plan {
     int xyz_chunk;             // SA mode: 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
     int grp_cols, tmem_cols;   // TMEM columns of one tile group / of the CTA (power of two >= 32)
     int mb;                    // 128-channel blocks of the (transposed) last layer
+    int whole_tiles;           // SA mode: M % (centres per tile) == 0 -> a tile's centres share the frame, consecutive p
 };
 
 // Weights (cout,cin) fp32 + bias -> the kernel's shared-memory image: per layer bf16 [K/8][Npad][8] (UMMA K-major core
@@ -126,8 +131,8 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
 // (B,C,n) inputs (features = source 0, src1 = source 1, concatenated along channels), no pooling.
 template <int GROUPS, int SC, bool DENSE>
 __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
-    mlp_tc2_kernel(const SaMlpArgs a, const Tc2Plan pl, const __nv_bfloat16* __restrict__ featT,
-                   const unsigned char* __restrict__ packed, const int num_tiles) {
+    mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
+                   const __nv_bfloat16* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
@@ -193,51 +198,75 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
             }
         }
     };
-    prefetch_row(tile0);
-
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const long long g = (long long)tile * T2_ROWS + tid;  // this thread's global row
-        // ------------------------------------------------------------------ layer-0 operand
+    // ---- SA mode: the layer-0 operand of a tile is gathered asynchronously, one tile ahead.
+    // issue_gather(tile): cp.async of the row's feature chunks into the operand buffer (zero-fill when the row is masked
+    // or past the end) + the six coordinate loads; finish_gather(): the xyz chunk and the zero pad chunks from registers,
+    // then wait for the copies.  The operand buffer must be free: the caller issues it after the last MMA's commit.
+    float pend_dx = 0.f, pend_dy = 0.f, pend_dz = 0.f;
+    const uint32_t a_row_s = a_smem + (uint32_t)tid * 16u;
+    auto issue_gather = [&](int tile) {
         if constexpr (!DENSE) {
+            const long long g = (long long)tile * T2_ROWS + tid;
             const int id = id_next;
             const bool live = live_next;
             const long long cpi = g < a.total_rows ? (g >> log2s) : 0;  // S is a power of two; B*M < 2^31 (launcher)
             const int b = (int)((unsigned)cpi / (unsigned)M);
             const size_t prow = (size_t)b * a.n + id;
-            float dx = 0.f, dy = 0.f, dz = 0.f;
+            pend_dx = pend_dy = pend_dz = 0.f;
             if (pl.xyz_chunk >= 0 && live) {
                 const float* p = a.xyz + prow * 3;
                 const float* q = a.new_xyz + (size_t)cpi * 3;
-                dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
-                dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
-                dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+                pend_dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
+                pend_dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+                pend_dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
             }
             const int fchunks = pl.cp >> 3;
             const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
-            // eight 16-byte loads in flight per thread, then eight stores
-            for (int kc0 = 0; kc0 < nchunk0; kc0 += 8) {
-                uint4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int kc = kc0 + u;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (live && kc < fchunks) v[u] = __ldg(frow + kc);
+            const int nbytes = live ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+            for (int kc = 0; kc < fchunks; ++kc)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_row_s + (uint32_t)kc * (T2_ROWS * 16)),
+                             "l"(frow + kc), "r"(nbytes)
+                             : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+    auto finish_gather = [&]() {
+        if constexpr (!DENSE) {
+            const int fchunks = pl.cp >> 3;
+            for (int kc = fchunks; kc < nchunk0; ++kc) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (kc == pl.xyz_chunk) {
+                    v.x = pack_bf16(pend_dx, pend_dy);
+                    v.y = pack_bf16(pend_dz, 0.f);
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int kc = kc0 + u;
-                    if (kc < nchunk0) {
-                        if (kc == pl.xyz_chunk) {
-                            v[u].x = pack_bf16(dx, dy);
-                            v[u].y = pack_bf16(dz, 0.f);
-                        }
-                        *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v[u];
-                    }
-                }
+                *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v;
             }
-            prefetch_row(tile + tile_step);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+    };
+    auto wait_mma = [&]() {
+        const uint32_t bar = smem_u32(&mma_bar);
+        if (!mbar_try_wait_cta(bar, phase)) {  // try_wait suspends the thread for a hardware time slice per call
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (!mbar_try_wait_cta(bar, phase))
+                if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+        }
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+
+    prefetch_row(tile0);
+    if (tile0 < num_tiles) issue_gather(tile0);
+    prefetch_row(tile0 + tile_step);
+
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        // ------------------------------------------------------------------ layer-0 operand
+        if constexpr (!DENSE) {
+            finish_gather();
         } else {
             // dense: channel c of row g = src0[b, c, i] (c < c_feat) | src1[b, c - c_feat, i]; coalesced over threads
+            const long long g = (long long)tile * T2_ROWS + tid;  // this thread's global row
             const bool rv = g < a.total_rows;
             const int b = rv ? (int)(g / a.n) : 0;
             const int i = rv ? (int)(g - (long long)b * a.n) : 0;
@@ -267,85 +296,93 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         group_sync();
 
-        for (int l = 0; l < nl; ++l) {
+        // ------------------------------------------------------------------ layers 0 .. nl-2: D[row, cout] in TMEM
+        for (int l = 0; l + 1 < nl; ++l) {
             const int K = pl.K[l], Np = pl.Npad[l];
-            const bool last = l + 1 == nl;
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
                 const uint32_t act_lbo = T2_ROWS * 16, w_lbo = (uint32_t)Np * 16;
-                if (!last) {
-                    // D[row, cout] = act (A, M = 128 rows) x W_l (B, N = Np)
-                    const uint32_t idesc = instr_desc_bf16_m128(Np);
-                    for (int kk = 0; kk < (K >> 4); ++kk)
-                        umma_bf16(d_tmem, smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128),
-                                  smem_desc(w_smem + (uint32_t)kk * 2u * w_lbo, w_lbo, 128), idesc, kk > 0 ? 1u : 0u);
-                } else {
-                    // D^T[cout, row] = W_last (A, M = 128 channels of block mb) x act (B, N = 128 rows)
-                    const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS);
-                    for (int mb = 0; mb < pl.mb; ++mb)
-                        for (int kk = 0; kk < (K >> 4); ++kk)
-                            umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS),
-                                      smem_desc(w_smem + (uint32_t)mb * (T2_ROWS * 16) + (uint32_t)kk * 2u * w_lbo, w_lbo, 128),
-                                      smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128), idesc, kk > 0 ? 1u : 0u);
-                }
+                const uint32_t idesc = instr_desc_bf16_m128(Np);  // act (A, M = 128 rows) x W_l (B, N = Np)
+                for (int kk = 0; kk < (K >> 4); ++kk)
+                    umma_bf16(d_tmem, smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128),
+                              smem_desc(w_smem + (uint32_t)kk * 2u * w_lbo, w_lbo, 128), idesc, kk > 0 ? 1u : 0u);
                 umma_commit(smem_u32(&mma_bar));
             }
-            {
-                const uint32_t bar = smem_u32(&mma_bar);
-                if (!mbar_try_wait_cta(bar, phase)) {
-                    const long long t0 = clock64();
-                    while (!mbar_try_wait_cta(bar, phase))
-                        if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
-                }
-                phase ^= 1u;
+            wait_mma();
+            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
+            // bias + ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = row
+            int c0 = 0;
+            for (; c0 + 64 <= Np; c0 += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
+                tmem_ld32_nowait(t_lane + (uint32_t)c0 + 32u, v1);
+                tmem_wait_ld();
+                epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                epi_mid_store<32>(v1, bs + c0 + 32, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
             }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (; c0 + 32 <= Np; c0 += 32) {
+                uint32_t v0[32];
+                tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
+                tmem_wait_ld();
+                epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+            }
+            for (; c0 + 16 <= Np; c0 += 16) {
+                uint32_t v0[16];
+                tmem_ld16_nowait(t_lane + (uint32_t)c0, v0);
+                tmem_wait_ld();
+                epi_mid_store<16>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            group_sync();
+        }
+
+        // ------------------------------------------------------------------ last layer, transposed: D^T[cout, row]
+        {
+            const int l = nl - 1;
+            const int K = pl.K[l], Np = pl.Npad[l];
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
+                const uint32_t act_lbo = T2_ROWS * 16, w_lbo = (uint32_t)Np * 16;
+                const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS);  // W_last block (A, M = 128 channels) x act (B, N = 128 rows)
+                for (int mb = 0; mb < pl.mb; ++mb)
+                    for (int kk = 0; kk < (K >> 4); ++kk)
+                        umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS),
+                                  smem_desc(w_smem + (uint32_t)mb * (T2_ROWS * 16) + (uint32_t)kk * 2u * w_lbo, w_lbo, 128),
+                                  smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128), idesc, kk > 0 ? 1u : 0u);
+                umma_commit(smem_u32(&mma_bar));
+            }
+            wait_mma();
+            // the operand buffer is free again: start the next tile's gather now, it lands during the epilogue below
+            if (tile + tile_step < num_tiles) issue_gather(tile + tile_step);
+            prefetch_row(tile + 2 * tile_step);
             const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
 
-            if (!last) {
-                // bias + ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = row
-                int c0 = 0;
-                for (; c0 + 64 <= Np; c0 += 64) {
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
-                    tmem_ld32_nowait(t_lane + (uint32_t)c0 + 32u, v1);
-                    tmem_wait_ld();
-                    epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-                    epi_mid_store<32>(v1, bs + c0 + 32, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
-                }
-                for (; c0 + 32 <= Np; c0 += 32) {
-                    uint32_t v0[32];
-                    tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
-                    tmem_wait_ld();
-                    epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-                }
-                for (; c0 + 16 <= Np; c0 += 16) {
-                    uint32_t v0[16];
-                    tmem_ld16_nowait(t_lane + (uint32_t)c0, v0);
-                    tmem_wait_ld();
-                    epi_mid_store<16>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                group_sync();
-            } else if constexpr (!DENSE) {
+            if constexpr (!DENSE) {
                 // thread = output channel; columns = the tile's rows: max over the S columns of a centre in registers,
                 // then bias + ReLU once per centre
                 const int cpt = T2_ROWS >> log2s;  // centres per tile
                 const unsigned cbase = (unsigned)tile * (unsigned)cpt;
                 const unsigned ctot = (unsigned)(a.total_rows >> log2s);
+                const unsigned b0 = cbase / (unsigned)M, p0 = cbase - b0 * (unsigned)M;
                 for (int mb = 0; mb < pl.mb; ++mb) {
                     const int ch = mb * T2_ROWS + tid;
                     const float bias = bs[ch];
                     const bool ch_ok = ch < cout_last;
+                    float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
                     float run = 0.f;
                     auto emit = [&](int ci, float m) {
                         const unsigned cg = cbase + (unsigned)ci;
                         if (ch_ok && cg < ctot) {
-                            const unsigned b2 = cg / (unsigned)M;
-                            const unsigned p2 = cg - b2 * (unsigned)M;
-                            a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = fmaxf(__fadd_rn(m, bias), 0.f);
+                            const float y = fmaxf(__fadd_rn(m, bias), 0.f);
+                            if (pl.whole_tiles) {
+                                obase[ci] = y;
+                            } else {  // a tile may straddle two frames
+                                const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
+                                a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
+                            }
                         }
                     };
 #pragma unroll 1
@@ -383,8 +420,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
                         }
                     }
                 }
-                // no barrier here: the next tile's gather only overwrites the operand buffer (its last reader, this
-                // layer's MMA, has completed) and the next MMA is issued after that gather's barrier
+                // no barrier here: the next tile's MMA is issued after the barrier that follows finish_gather()
             } else {
                 // dense: thread = output channel; 128 columns = 128 consecutive rows (points) of the tile
                 const long long g0 = (long long)tile * T2_ROWS;
@@ -461,7 +497,6 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) 
     if (a.num_layers < 1 || a.num_layers > T2_MAX_LAYERS) return TSM_ERR_INVALID;
     if (!dense) {
         if (S < 8 || S > T2_ROWS || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile, SC in {8,16,32}
-        if (a.ch[a.num_layers] < 64) return TSM_ERR_INVALID;                       // narrow outputs: sa_mlp_tc.cu
         if ((long long)b * a.m >= 0x7fffffffLL) return TSM_ERR_INVALID;            // 32-bit centre arithmetic
     } else if (S != 1 || a.m != a.n) {
         return TSM_ERR_INVALID;
@@ -490,6 +525,7 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) 
     }
     if (kmax > 512) return TSM_ERR_INVALID;
     pl.mb = pl.Npad[pl.nl - 1] / T2_ROWS;
+    pl.whole_tiles = (!dense && (a.m % (T2_ROWS / S)) == 0) ? 1 : 0;
     for (int l = 0; l < pl.nl; ++l) {
         pl.b_off[l] = off;
         off += pl.Npad[l] * 4;
