@@ -1,6 +1,6 @@
 """One parametrised runner for profiling / timing single ops of the path (replaces the one-off scripts of round 1).
 
-    python scripts/prof.py mlp1|mlp2|mlp3|fp|fps|bq|nms|voxel [--reps 3] [--time]
+    python scripts/prof.py mlp1|mlp2|mlp3|fp|fps|bq|nms|voxel|step [--reps 3] [--time]
 
 Runs the op `reps` times on BASELINE-shaped inputs (config 2 / 3; `fp` = config 4's FP layer) so that
 `ncu -k regex:<kernel> ... python scripts/prof.py <op>` captures exactly that kernel; --time prints CUDA-event times.
@@ -68,6 +68,10 @@ def main():
         from tsmdet_b200 import voxel_aggregation_utils as vau
         nx, nf = levels[1][0], torch.rand((16, 64, 4096), device=dev)
         fn = lambda: vau.voxelize_centroids(nx, nf, [0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1])  # noqa: E731
+    elif a.op == "step":  # one whole un-graphed step (for `ncu --metrics gpu__time_duration.sum` launch lists)
+        b, s = torch.from_numpy(boxes_np).to(dev), torch.from_numpy(scores_np).to(dev)
+        eng.chain_fps = True
+        fn = lambda: eng.forward_device(xyz, feats, b, s)  # noqa: E731
     else:
         raise SystemExit(f"unknown op {a.op}")
     with torch.no_grad():
