@@ -17,6 +17,9 @@ for step in "$@"; do
              timeout 300 python scripts/prof.py $op --time > gpurun_out/${TAG}_prof_$op.log 2>&1 && \
              timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${TAG}_ncu_$op python scripts/prof.py $op > gpurun_out/${TAG}_ncu_$op.log 2>&1
              tail -n 2 gpurun_out/${TAG}_ncu_$op.log ;;
+    dur)     timeout 300 python scripts/prof.py $rest > /dev/null 2>&1 && \
+             timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_dur_$rest.csv python scripts/prof.py $rest > /dev/null 2>&1
+             grep -E "mlp|transpose|pack|fps|bq_|nms|voxel|stack" gpurun_out/${TAG}_dur_$rest.csv | awk -F'","' '{print $5, $NF}' | tail -n 12 ;;
     launches) timeout 300 python scripts/prof.py step > gpurun_out/${TAG}_step.log 2>&1 && \
              timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/prof.py step > gpurun_out/${TAG}_launches.log 2>&1
              tail -n 2 gpurun_out/${TAG}_launches.log ;;
