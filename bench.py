@@ -606,8 +606,10 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
             cnt, bidx = pointnet2_utils.ball_query(g.radius, ns, cur_xyz, new_xyz)
             ms_bq = t(lambda: pointnet2_utils.ball_query(g.radius, ns, cur_xyz, new_xyz))
             layers = layer._folded_layers()[0]
+            img = layer._packed_layers(c, True)[0]
             out = torch.empty((b, layers[-1][0].shape[0], m), device=dev)
-            ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, cur_f, bidx, cnt, layers, out, 0, precision=layer.precision))
+            ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, cur_f, bidx, cnt, layers, out, 0, precision=layer.precision,
+                                              packed=img))
             fps_bytes = b * (12 * n + 4 * m)
             bq_bytes = b * (12 * n + 12 * m + 4 * m * ns + 4 * m)
             chans = [3 + c] + [w.shape[0] for w, _ in layers]

@@ -146,6 +146,22 @@ int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const 
                          const int* channels, const float* const* weights, const float* const* biases, float* out,
                          int out_ctot, int out_c0, int precision, void* stream);
 
+/* Weights that do not change between calls (eval): build the tensor path's weight image (bf16 UMMA core matrices +
+ * fp32 biases) ONCE and hand it to the *_packed entry points -- the packing kernel costs as much as a small layer.
+ * dense = 0: fused SA scale (c1 ignored), 1: point-wise MLP (nsample / use_xyz ignored).  packed == NULL: only
+ * *packed_bytes is set.  TSMDET_ERR_INVALID: the second-generation tensor kernel does not take this shape (nsample
+ * not a power of two in 8..128, widths > 256): use the unpacked entry points. */
+int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers, const int* channels,
+                    const float* const* weights, const float* const* biases, void* packed, long long* packed_bytes,
+                    void* stream);
+int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
+                                 const float* new_xyz, const float* features, const int* idx, const int* idx_cnt,
+                                 int num_layers, const int* channels, const void* packed, float* out, int out_ctot,
+                                 int out_c0, void* stream);
+int tsmdet_pointwise_mlp_packed(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
+                                const int* channels, const void* packed, float* out, int out_ctot, int out_c0,
+                                void* stream);
+
 /* ---------------------------------------------------------------- centroid voxelisation ------
  * The tail of the layer-0 branch (pointnet2/pointnet2_batch/pointnet2_modules.py:1323-1355) in one call:
  * voxel indices ((xyz - range_min) / voxel_size truncated, pcdet/utils/voxel_aggregation_utils.py:48-83), the sorted

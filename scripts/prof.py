@@ -46,8 +46,9 @@ def main():
         g = layer.groupers[0]
         cnt, bidx = pu.ball_query(g.radius, g.nsample, src_xyz, new_xyz)
         fl = layer._folded_layers()[0]
+        img = layer._packed_layers(src_f.shape[1], True)[0]
         out = torch.empty((16, fl[-1][0].shape[0], new_xyz.shape[1]), device=dev)
-        fn = lambda: sa_mlp_maxpool(src_xyz, new_xyz, src_f, bidx, cnt, fl, out, 0, precision="bf16")  # noqa: E731
+        fn = lambda: sa_mlp_maxpool(src_xyz, new_xyz, src_f, bidx, cnt, fl, out, 0, precision="bf16", packed=img)  # noqa: E731
     elif a.op == "fp":
         import synth
         x = torch.from_numpy(synth.cloud_uniform(8, 65536, 7, synth.WAYMO_RANGE)).to(dev)

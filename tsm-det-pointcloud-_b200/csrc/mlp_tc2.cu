@@ -80,24 +80,32 @@ __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, c
     for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
 }
 
-// features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels
+// features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels.  One CTA moves a 64-point x Cp-channel tile
+// through shared memory: the reads run along N (coalesced 256-byte rows of one channel), the writes along Cp (the 64
+// output rows of the tile are ONE contiguous run of 64 * Cp bf16) -- the first version wrote 16-byte pieces 2*Cp bytes
+// apart and needed 14 us for the 8 MB of SA layer 3; HBM-bound it is ~2 us.
+constexpr int TR_PTS = 64;
 __global__ void __launch_bounds__(256) transpose2_bf16_kernel(int c, int cp, int n, const float* __restrict__ f,
                                                               __nv_bfloat16* __restrict__ out) {
+    extern __shared__ __nv_bfloat16 tr_tile[];  // [TR_PTS][cp + 2] (odd word stride: conflict-free column writes)
     const int b = blockIdx.y;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const float* src = f + (size_t)b * c * n + i;
-    __nv_bfloat16* dst = out + ((size_t)b * n + i) * cp;
-    for (int c0 = 0; c0 < cp; c0 += 8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ca = c0 + 2 * j, cb = ca + 1;
-            const float x = ca < c ? __ldg(src + (size_t)ca * n) : 0.f;
-            const float y = cb < c ? __ldg(src + (size_t)cb * n) : 0.f;
-            w[j] = pack_bf16(x, y);
-        }
-        *reinterpret_cast<uint4*>(dst + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    const int i0 = blockIdx.x * TR_PTS;
+    const int np = min(TR_PTS, n - i0);
+    const int ld = cp + 2;
+    const float* src = f + (size_t)b * c * n + i0;
+    for (int e = threadIdx.x; e < cp * TR_PTS; e += 256) {
+        const int ch = e / TR_PTS, p = e - ch * TR_PTS;
+        float v = 0.f;
+        if (ch < c && p < np) v = __ldg(src + (size_t)ch * n + p);
+        tr_tile[p * ld + ch] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+    // 4-byte (two-channel) stores, consecutive threads -> consecutive words of the contiguous output run
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((size_t)b * n + i0) * cp);
+    const int wpr = cp >> 1;  // words per output row
+    for (int e = threadIdx.x; e < np * wpr; e += 256) {
+        const int p = e / wpr, w = e - p * wpr;
+        dst[e] = *reinterpret_cast<const uint32_t*>(tr_tile + p * ld + 2 * w);
     }
 }
 
@@ -182,66 +190,84 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
     const int nchunk0 = pl.K[0] >> 3;
     const int tile0 = blockIdx.x * GROUPS + grp, tile_step = gridDim.x * GROUPS;
 
-    // SA mode: the neighbour index and the live flag of this thread's row, prefetched one tile ahead
-    int id_next = 0;
-    bool live_next = false;
+    // SA mode: the neighbour index and the hit count of this thread's row are LOADED one tile ahead and only looked at
+    // when the next gather is issued; the coordinates are loaded when the gather is issued and only looked at when it
+    // is finished -- no load is consumed where it is issued (the first version did, and stalled there for the full
+    // L2 latency: ncu source view, 9 % + 5 % of the samples).
+    int id_raw = 0, cnt_raw = 1;
     auto prefetch_row = [&](int tile) {
         if constexpr (!DENSE) {
-            id_next = 0;
-            live_next = false;
+            id_raw = 0;
+            cnt_raw = 0;  // rows past the end are masked
             if (tile < num_tiles) {
                 const long long g = (long long)tile * T2_ROWS + tid;
                 if (g < a.total_rows) {
-                    id_next = __ldg(a.idx + g);
-                    live_next = !(a.idx_cnt && __ldg(a.idx_cnt + (g >> log2s)) <= 0);  // empty ball -> zero input row
+                    id_raw = __ldg(a.idx + g);
+                    cnt_raw = a.idx_cnt ? __ldg(a.idx_cnt + (g >> log2s)) : 1;  // <= 0: empty ball -> zero input row
                 }
             }
         }
     };
-    // ---- SA mode: the layer-0 operand of a tile is gathered asynchronously, one tile ahead.
     // issue_gather(tile): cp.async of the row's feature chunks into the operand buffer (zero-fill when the row is masked
-    // or past the end) + the six coordinate loads; finish_gather(): the xyz chunk and the zero pad chunks from registers,
-    // then wait for the copies.  The operand buffer must be free: the caller issues it after the last MMA's commit.
-    float pend_dx = 0.f, pend_dy = 0.f, pend_dz = 0.f;
+    // or past the end) + the coordinate / narrow-feature loads; finish_gather(): the xyz chunk and the zero pad chunks
+    // from registers, then wait for the copies.  The operand buffer must be free: issued after the last MMA's commit.
+    float pend_p[3] = {0.f, 0.f, 0.f}, pend_q[3] = {0.f, 0.f, 0.f}, pend_f[4] = {0.f, 0.f, 0.f, 0.f};
+    bool pend_live = false;
     const uint32_t a_row_s = a_smem + (uint32_t)tid * 16u;
+    const bool planar = featT == nullptr && a.c_feat > 0;  // <= 4 feature channels: read straight from (B,C,N) fp32
     auto issue_gather = [&](int tile) {
         if constexpr (!DENSE) {
             const long long g = (long long)tile * T2_ROWS + tid;
-            const int id = id_next;
-            const bool live = live_next;
+            const int id = id_raw;
+            const bool live = cnt_raw > 0;
+            pend_live = live;
             const long long cpi = g < a.total_rows ? (g >> log2s) : 0;  // S is a power of two; B*M < 2^31 (launcher)
             const int b = (int)((unsigned)cpi / (unsigned)M);
             const size_t prow = (size_t)b * a.n + id;
-            pend_dx = pend_dy = pend_dz = 0.f;
             if (pl.xyz_chunk >= 0 && live) {
                 const float* p = a.xyz + prow * 3;
                 const float* q = a.new_xyz + (size_t)cpi * 3;
-                pend_dx = __fsub_rn(__ldg(p + 0), __ldg(q + 0));
-                pend_dy = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
-                pend_dz = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    pend_p[k] = __ldg(p + k);
+                    pend_q[k] = __ldg(q + k);
+                }
             }
-            const int fchunks = pl.cp >> 3;
-            const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
-            const int nbytes = live ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, nothing is read
-            for (int kc = 0; kc < fchunks; ++kc)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_row_s + (uint32_t)kc * (T2_ROWS * 16)),
-                             "l"(frow + kc), "r"(nbytes)
-                             : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (planar) {
+                if (live) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < a.c_feat) pend_f[k] = __ldg(a.features + ((size_t)b * a.c_feat + k) * a.n + id);
+                }
+            } else {
+                const int fchunks = pl.cp >> 3;
+                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
+                const int nbytes = live ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+                for (int kc = 0; kc < fchunks; ++kc)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_row_s + (uint32_t)kc * (T2_ROWS * 16)),
+                                 "l"(frow + kc), "r"(nbytes)
+                                 : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
         }
     };
     auto finish_gather = [&]() {
         if constexpr (!DENSE) {
-            const int fchunks = pl.cp >> 3;
-            for (int kc = fchunks; kc < nchunk0; ++kc) {
+            const int first = planar ? 0 : (pl.cp >> 3);
+            for (int kc = first; kc < nchunk0; ++kc) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (kc == pl.xyz_chunk) {
-                    v.x = pack_bf16(pend_dx, pend_dy);
-                    v.y = pack_bf16(pend_dz, 0.f);
+                if (pend_live) {
+                    if (kc == pl.xyz_chunk) {
+                        v.x = pack_bf16(__fsub_rn(pend_p[0], pend_q[0]), __fsub_rn(pend_p[1], pend_q[1]));
+                        v.y = pack_bf16(__fsub_rn(pend_p[2], pend_q[2]), 0.f);
+                    } else if (planar && kc == 0) {
+                        v.x = pack_bf16(pend_f[0], a.c_feat > 1 ? pend_f[1] : 0.f);
+                        v.y = pack_bf16(a.c_feat > 2 ? pend_f[2] : 0.f, a.c_feat > 3 ? pend_f[3] : 0.f);
+                    }
                 }
                 *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v;
             }
-            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (!planar) asm volatile("cp.async.wait_all;" ::: "memory");
         }
     };
     auto wait_mma = [&]() {
@@ -489,15 +515,15 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
 
 static int round_up2(int v, int m) { return (v + m - 1) / m * m; }
 
-// dense != 0: point-wise MLP over (B, c_feat + c1, n) (a.features / a.src1), a.m == a.n, a.s == 1, no idx.
-// Returns TSM_ERR_INVALID for shapes this kernel does not take (the caller falls back to sa_mlp_tc.cu / fp32).
-int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) {
+// Shapes this kernel takes and the shared-memory / TMEM plan for them.  TSM_ERR_INVALID otherwise (the caller falls
+// back to sa_mlp_tc.cu / the fp32 kernel).
+static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::Tc2Plan* out, int* groups_out) {
     using namespace tsm;
     const int S = a.s;
     if (a.num_layers < 1 || a.num_layers > T2_MAX_LAYERS) return TSM_ERR_INVALID;
     if (!dense) {
         if (S < 8 || S > T2_ROWS || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile, SC in {8,16,32}
-        if ((long long)b * a.m >= 0x7fffffffLL) return TSM_ERR_INVALID;            // 32-bit centre arithmetic
+        if (centres >= 0x7fffffffLL) return TSM_ERR_INVALID;                       // 32-bit centre arithmetic
     } else if (S != 1 || a.m != a.n) {
         return TSM_ERR_INVALID;
     }
@@ -547,16 +573,56 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) 
         groups = 2;
     pl.tmem_cols = pl.grp_cols * groups;
     pl.smem_bytes = smem_for(groups);
+    *out = pl;
+    *groups_out = groups;
+    return TSM_OK;
+}
 
+// The kernel's weight image (bf16 UMMA core matrices + fp32 biases) for an MLP: *bytes = its size; packed != nullptr:
+// build it there (device memory, >= *bytes).  Callers with constant weights build it ONCE and pass it to every call
+// (the packing kernel costs 5-8 us, comparable to a whole SA layer's tensor work).
+int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, long long* bytes, cudaStream_t stream) {
+    using namespace tsm;
+    Tc2Plan pl;
+    int groups = 1;
+    int rc = tc2_plan(a, 1, dense, &pl, &groups);
+    if (rc != TSM_OK) return rc;
+    if (bytes) *bytes = pl.packed_bytes;
+    if (packed) {
+        for (int l = 0; l < pl.nl; ++l)
+            if (!a.w[l] || !a.bias[l]) return TSM_ERR_INVALID;
+        dim3 pgrid(16, (unsigned)pl.nl);
+        pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(a, pl, dense, packed);
+        TSM_LAUNCH_CHECK();
+    }
+    return TSM_OK;
+}
+
+// dense != 0: point-wise MLP over (B, c_feat + c1, n) (a.features / a.src1), a.m == a.n, a.s == 1, no idx.
+// prepacked: the image built by tsm_mlp_tc2_pack for the same shapes (nullptr: packed here, per call).
+int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, const unsigned char* prepacked) {
+    using namespace tsm;
+    const int S = a.s;
+    Tc2Plan pl;
+    int groups = 1;
+    {
+        const int rc = tc2_plan(a, (long long)b * a.m, dense, &pl, &groups);
+        if (rc != TSM_OK) return rc;
+    }
+    // feature rows: <= 4 channels are read straight from the (B,C,N) fp32 planes by the gather; wider inputs go
+    // through a bf16 (B,N,Cp) transpose so that a gathered row is one contiguous run of 16-byte chunks
     __nv_bfloat16* featT = nullptr;
-    if (!dense && a.c_feat > 0) {
+    if (!dense && a.c_feat > 4) {
         void* p = nullptr;
         const size_t bytes = (size_t)b * a.n * pl.cp * sizeof(__nv_bfloat16);
         int rc = tsm_scratch_get(1, bytes, stream, &p);
         if (rc != TSM_OK) return rc;
         featT = (__nv_bfloat16*)p;
-        dim3 grid((unsigned)divup(a.n, 256), (unsigned)b);
-        transpose2_bf16_kernel<<<grid, 256, 0, stream>>>(a.c_feat, pl.cp, a.n, a.features, featT);
+        dim3 grid((unsigned)divup(a.n, TR_PTS), (unsigned)b);
+        const size_t tsm_bytes = (size_t)TR_PTS * (pl.cp + 2) * sizeof(__nv_bfloat16);
+        if (tsm_bytes > 48 * 1024)
+            TSM_CUDA_TRY(cudaFuncSetAttribute(transpose2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_bytes));
+        transpose2_bf16_kernel<<<grid, 256, tsm_bytes, stream>>>(a.c_feat, pl.cp, a.n, a.features, featT);
         TSM_LAUNCH_CHECK();
     }
     const long long tiles = (a.total_rows + T2_ROWS - 1) / T2_ROWS;
@@ -596,15 +662,15 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream) 
     if (grid * groups > tiles) grid = (tiles + groups - 1) / groups;
     SaMlpArgs args = a;
     args.status = tsm_status_word(stream);
-    unsigned char* packed = nullptr;
-    {
+    const unsigned char* packed = prepacked;
+    if (!packed) {
         void* p = nullptr;
         int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes, stream, &p);
         if (rc != TSM_OK) return rc;
-        packed = (unsigned char*)p;
         dim3 pgrid(16, (unsigned)pl.nl);
-        pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(args, pl, dense, packed);
+        pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(args, pl, dense, (unsigned char*)p);
         TSM_LAUNCH_CHECK();
+        packed = (const unsigned char*)p;
     }
     kern<<<(unsigned)grid, T2_THREADS * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
     TSM_LAUNCH_CHECK();

@@ -204,11 +204,12 @@ class SABackboneNMS(torch.nn.Module):
                 cnt, bidx = pointnet2_utils.ball_query(g.radius, g.nsample, src_xyz, new_xyz)
                 mark(f"query{src_xyz.shape[1]}", s_sa)
                 folded = layer._folded_layers()[0]
+                img = layer._packed_layers(cur_f.shape[1], True)[0]  # weight image built once, not per step
                 if li == len(layers) - 1:
                     out = out_features
                 else:
                     out = torch.empty((b, folded[-1][0].shape[0], new_xyz.shape[1]), dtype=torch.float32, device=dev)
-                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision)
+                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision, packed=img)
                 mark(f"mlp{src_xyz.shape[1]}", s_sa)
                 cur_f = out
         # stream C: NMS is independent of the backbone.  (Measured inside the captured graph: letting it run

@@ -71,10 +71,38 @@ def fold_conv_bn(seq: nn.Sequential):
     return out
 
 
+def pack_mlp(layers, *, dense: bool, nsample: int = 1, c_feat: int = 0, c1: int = 0, use_xyz: bool = True):
+    """The tensor path's weight image for folded ``layers`` (C ABI ``tsmdet_mlp_pack``): a uint8 CUDA tensor to pass as
+    ``packed=`` to ``sa_mlp_maxpool`` / ``pointwise_mlp``, or None when the second-generation tcgen05 kernel does not
+    take the shape (the unpacked calls then fall back to the first-generation / fp32 kernels).  Build it once per set
+    of weights: the packing kernel costs 5-8 us per call, as much as a small layer."""
+    from ._lib import TsmdetError
+
+    nl = len(layers)
+    cin0 = layers[0][0].shape[1]
+    chans = [cin0] + [w.shape[0] for w, _ in layers]
+    ch_arr = (ctypes.c_int * (nl + 1))(*chans)
+    w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
+    b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
+    size = ctypes.c_longlong(0)
+    dev = layers[0][0].device
+    args = (int(dense), int(nsample), int(c_feat), int(c1), int(use_xyz), nl, ch_arr, w_arr, b_arr)
+    try:
+        call("tsmdet_mlp_pack", *args, None, ctypes.byref(size), stream_ptr(dev))
+    except TsmdetError as e:
+        if e.code == 1000001:
+            return None
+        raise
+    packed = torch.empty((int(size.value),), dtype=torch.uint8, device=dev)
+    call("tsmdet_mlp_pack", *args, ptr(packed), ctypes.byref(size), stream_ptr(dev))
+    return packed
+
+
 def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: int, use_xyz: bool = True,
-                   precision: str = "fp32"):
-    """One fused set-abstraction scale (C ABI ``tsmdet_sa_mlp_maxpool``): writes
-    ``out[:, out_c0:out_c0+cout, :]`` (out is (B, Ctot, npoint) fp32 contiguous)."""
+                   precision: str = "fp32", packed: Optional[torch.Tensor] = None):
+    """One fused set-abstraction scale (C ABI ``tsmdet_sa_mlp_maxpool`` / ``_packed``): writes
+    ``out[:, out_c0:out_c0+cout, :]`` (out is (B, Ctot, npoint) fp32 contiguous).  ``packed`` = ``pack_mlp(layers,
+    dense=False, nsample=..., c_feat=..., use_xyz=...)`` skips the per-call weight packing (bf16 path only)."""
     b, n, _ = xyz.shape
     _, m, s = idx.shape
     c_feat = 0 if features is None else features.shape[1]
@@ -83,6 +111,10 @@ def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: in
     for l, (w, bias) in enumerate(layers):
         assert w.shape == (chans[l + 1], chans[l]) and w.is_contiguous() and bias.is_contiguous()
     ch_arr = (ctypes.c_int * (nl + 1))(*chans)
+    if packed is not None and precision == "bf16":
+        call("tsmdet_sa_mlp_maxpool_packed", b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features),
+             ptr(idx), ptr(idx_cnt), nl, ch_arr, ptr(packed), ptr(out), out.shape[1], out_c0, stream_ptr(xyz.device))
+        return out
     w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
     prec = {"fp32": 0, "bf16": 1}[precision]
@@ -92,7 +124,7 @@ def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: in
 
 
 def pointwise_mlp(src0: torch.Tensor, src1: Optional[torch.Tensor], layers, out: Optional[torch.Tensor] = None,
-                  out_c0: int = 0, precision: str = "fp32") -> torch.Tensor:
+                  out_c0: int = 0, precision: str = "fp32", packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Point-wise shared MLP, no pooling (C ABI ``tsmdet_pointwise_mlp``): ``out[:, out_c0:out_c0+cout, :] =
     MLP(cat([src0, src1], dim=1))`` for folded ``layers`` [(W (cout,cin), b (cout))]; src0 (B,c0,n), src1 (B,c1,n) |
     None.  The concatenation is never materialised.  ``precision='bf16'`` runs on tcgen05 tensor cores."""
@@ -108,6 +140,10 @@ def pointwise_mlp(src0: torch.Tensor, src1: Optional[torch.Tensor], layers, out:
         out = torch.empty((b, chans[-1], n), dtype=torch.float32, device=src0.device)
     assert out.is_contiguous() and out.shape[0] == b and out.shape[2] == n
     ch_arr = (ctypes.c_int * (nl + 1))(*chans)
+    if packed is not None and precision == "bf16":
+        call("tsmdet_pointwise_mlp_packed", b, n, c0, c1, ptr(src0), ptr(src1), nl, ch_arr, ptr(packed), ptr(out),
+             out.shape[1], out_c0, stream_ptr(src0.device))
+        return out
     w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
     prec = {"fp32": 0, "bf16": 1}[precision]
@@ -162,13 +198,14 @@ class PointnetFPModule(nn.Module):
         self.fused = fused
         self.precision = precision
         self._folded = None
+        self._packed = None
 
     def train(self, mode: bool = True):
         self._folded = None
         return super().train(mode)
 
     def _load_from_state_dict(self, *args, **kwargs):
-        self._folded = None  # weights changed under a cached fold
+        self._folded = None  # weights changed under a cached fold / packed image
         return super()._load_from_state_dict(*args, **kwargs)
 
     def forward(self, unknown, known, unknow_feats, known_feats):
@@ -183,11 +220,15 @@ class PointnetFPModule(nn.Module):
             interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
 
         if self.fused and not self.training:
+            c0 = interpolated_feats.shape[1]
+            c1 = 0 if unknow_feats is None else unknow_feats.shape[1]
             if self._folded is None:
                 self._folded = fold_conv_bn(self.mlp)
+                self._packed = (pack_mlp(self._folded, dense=True, c_feat=c0, c1=c1)
+                                if self.precision == "bf16" else None)
             return pointwise_mlp(interpolated_feats.contiguous(),
                                  None if unknow_feats is None else unknow_feats.contiguous(), self._folded,
-                                 precision=self.precision)
+                                 precision=self.precision, packed=self._packed)
         if unknow_feats is not None:
             new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
         else:
@@ -251,6 +292,8 @@ class PointnetSAModuleFSMSG(nn.Module):
         self.out_channels = out_channels
         self._folded = None  # cache of folded (W, b) per scale, built lazily in eval mode
         self._folded_agg = None
+        self._packed = None
+        self._packed_agg = None
 
     def _load_from_state_dict(self, *args, **kwargs):
         # a checkpoint loaded after a warm-up forward must not leave the fused path on stale folded weights
@@ -288,7 +331,18 @@ class PointnetSAModuleFSMSG(nn.Module):
     def _folded_layers(self):
         if self._folded is None:
             self._folded = [fold_conv_bn(m) for m in self.point_mlps]
+            self._packed = None
         return self._folded
+
+    def _packed_layers(self, c_feat: int, use_xyz: bool):
+        """Per scale: the tensor path's weight image of the folded MLP (None: shape not taken / fp32 mode), built once
+        per fold -- CUDA graphs captured afterwards hold its address, like the folded weights'."""
+        folded = self._folded_layers()
+        if self._packed is None or self._packed[0] != (c_feat, use_xyz, self.precision):
+            imgs = [pack_mlp(layers, dense=False, nsample=g.nsample, c_feat=c_feat, use_xyz=use_xyz)
+                    if self.precision == "bf16" else None for layers, g in zip(folded, self.groupers)]
+            self._packed = ((c_feat, use_xyz, self.precision), imgs)
+        return self._packed[1]
 
     def train(self, mode: bool = True):
         self._folded = None
@@ -316,14 +370,16 @@ class PointnetSAModuleFSMSG(nn.Module):
             extra = old_features.shape[1] if old_features is not None else 0
             new_features = torch.empty((b, sum(widths) + extra, npoint), dtype=torch.float32, device=xyz.device)
             c0 = 0
-            for grouper, layers, w in zip(self.groupers, folded, widths):
+            eff_xyz = self.use_xyz or features is None
+            packed = self._packed_layers(0 if features is None else features.shape[1], eff_xyz)
+            for grouper, layers, w, img in zip(self.groupers, folded, widths, packed):
                 if isinstance(grouper, pointnet2_utils.QueryAndGroupDilated):
                     idx_cnt, idx = pointnet2_utils.ball_query_dilated(
                         grouper.radius_in, grouper.radius_out, grouper.nsample, xyz, new_xyz)
                 else:
                     idx_cnt, idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
                 sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, new_features, c0,
-                               use_xyz=self.use_xyz or features is None, precision=self.precision)
+                               use_xyz=eff_xyz, precision=self.precision, packed=img)
                 c0 += w
             if old_features is not None:
                 new_features[:, c0:] = old_features
@@ -349,7 +405,10 @@ class PointnetSAModuleFSMSG(nn.Module):
             if use_fused:  # ref :1320-1321 as one kernel (BN folded; tensor cores in bf16 mode)
                 if self._folded_agg is None:
                     self._folded_agg = fold_conv_bn(self.aggregation_mlp)
-                new_features = pointwise_mlp(new_features.contiguous(), None, self._folded_agg, precision=self.precision)
+                    self._packed_agg = (pack_mlp(self._folded_agg, dense=True, c_feat=new_features.shape[1])
+                                        if self.precision == "bf16" else None)
+                new_features = pointwise_mlp(new_features.contiguous(), None, self._folded_agg, precision=self.precision,
+                                             packed=self._packed_agg)
             else:
                 new_features = self.aggregation_mlp(new_features)
         return new_xyz.contiguous(), new_features.contiguous(), sample_idx
