@@ -111,11 +111,19 @@ __global__ void __launch_bounds__(256) transpose2_bf16_kernel(int c, int cp, int
 
 // bias + ReLU + bf16 pack of NC accumulator columns of this thread's row -> NC/8 chunks of the next layer's A operand
 template <int NC>
-__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], const float* __restrict__ bias, unsigned char* dst) {
+__device__ __forceinline__ void load_bias(float4 (&bb)[NC / 4], const float* __restrict__ bias) {
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) bb[q] = *reinterpret_cast<const float4*>(bias + 4 * q);
+}
+
+// the biases arrive in registers: they are loaded BEFORE the tcgen05.wait::ld, so the shared-memory latency hides
+// behind the TMEM load instead of stalling every FADD2 (short-scoreboard stalls in the ncu source view)
+template <int NC>
+__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], const float4 (&bb)[NC / 4], unsigned char* dst) {
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * q);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + 8 * q + 4);
+        const float4 b0 = bb[2 * q];
+        const float4 b1 = bb[2 * q + 1];
         const float2 s0 = add2(make_float2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), make_float2(b0.x, b0.y));
         const float2 s1 = add2(make_float2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])), make_float2(b0.z, b0.w));
         const float2 s2 = add2(make_float2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), make_float2(b1.x, b1.y));
@@ -138,13 +146,18 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
 // GROUPS: tile pipelines per CTA.  SC = min(nsample, 32) in SA mode (8, 16 or 32).  DENSE: point-wise MLP over
 // (B,C,n) inputs (features = source 0, src1 = source 1, concatenated along channels), no pooling.
 template <int GROUPS, int SC, bool DENSE>
-__global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
+__global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // one group per CTA: 4 CTAs per SM (<= 128 regs)
     mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
                    const __nv_bfloat16* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_s;
+    // Per layer: the two operand descriptors of its first K step and what changes per step.  Built ONCE: assembling
+    // them per MMA (14-bit fields, 64-bit shifts) cost ~30 instructions per tcgen05.mma in the issuing thread -- about
+    // 2000 serial cycles per layer with the tensor pipe idle (SASS + ncu of the first version).
+    __shared__ __align__(8) uint64_t s_adesc[GROUPS][T2_MAX_LAYERS], s_wdesc[GROUPS][T2_MAX_LAYERS];
+    __shared__ uint32_t s_wstep[T2_MAX_LAYERS], s_idesc[T2_MAX_LAYERS];
 
     const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x >> 7);
     const int tid = threadIdx.x & 127, warp = tid >> 5;  // within the group
@@ -164,6 +177,18 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
         bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
+    }
+    if (tid == 0) {
+        const uint32_t act = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
+        for (int l = 0; l < nl; ++l) {
+            const uint32_t w_lbo = (uint32_t)pl.Npad[l] * 16;
+            s_adesc[grp][l] = smem_desc(act, T2_ROWS * 16, 128);                    // activations: LBO = 128 rows x 16 B
+            s_wdesc[grp][l] = smem_desc(smem_u32(smem + pl.w_off[l]), w_lbo, 128);  // weights: LBO = Npad rows x 16 B
+            if (grp == 0) {
+                s_wstep[l] = (2u * w_lbo) >> 4;  // start-address field (bytes >> 4) advance per K step of 16
+                s_idesc[l] = instr_desc_bf16_m128(l + 1 < nl ? pl.Npad[l] : T2_ROWS);
+            }
+        }
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -327,12 +352,15 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
             const int K = pl.K[l], Np = pl.Npad[l];
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
-                const uint32_t act_lbo = T2_ROWS * 16, w_lbo = (uint32_t)Np * 16;
-                const uint32_t idesc = instr_desc_bf16_m128(Np);  // act (A, M = 128 rows) x W_l (B, N = Np)
-                for (int kk = 0; kk < (K >> 4); ++kk)
-                    umma_bf16(d_tmem, smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128),
-                              smem_desc(w_smem + (uint32_t)kk * 2u * w_lbo, w_lbo, 128), idesc, kk > 0 ? 1u : 0u);
+                // act (A, M = 128 rows) x W_l (B, N = Np); per K step of 16 only the start-address fields advance
+                uint64_t ad = s_adesc[grp][l], wd = s_wdesc[grp][l];
+                const uint32_t idesc = s_idesc[l], wstep = s_wstep[l];
+                const int nk = K >> 4;
+                for (int kk = 0; kk < nk; ++kk) {
+                    umma_bf16(d_tmem, ad, wd, idesc, kk > 0 ? 1u : 0u);
+                    ad += (2u * T2_ROWS * 16u) >> 4;
+                    wd += wstep;
+                }
                 umma_commit(smem_u32(&mma_bar));
             }
             wait_mma();
@@ -341,23 +369,30 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
             int c0 = 0;
             for (; c0 + 64 <= Np; c0 += 64) {
                 uint32_t v0[32], v1[32];
+                float4 b0[8], b1[8];
                 tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
                 tmem_ld32_nowait(t_lane + (uint32_t)c0 + 32u, v1);
+                load_bias<32>(b0, bs + c0);
+                load_bias<32>(b1, bs + c0 + 32);
                 tmem_wait_ld();
-                epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-                epi_mid_store<32>(v1, bs + c0 + 32, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
+                epi_mid_store<32>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                epi_mid_store<32>(v1, b1, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
             }
             for (; c0 + 32 <= Np; c0 += 32) {
                 uint32_t v0[32];
+                float4 b0[8];
                 tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
+                load_bias<32>(b0, bs + c0);
                 tmem_wait_ld();
-                epi_mid_store<32>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                epi_mid_store<32>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
             }
             for (; c0 + 16 <= Np; c0 += 16) {
                 uint32_t v0[16];
+                float4 b0[4];
                 tmem_ld16_nowait(t_lane + (uint32_t)c0, v0);
+                load_bias<16>(b0, bs + c0);
                 tmem_wait_ld();
-                epi_mid_store<16>(v0, bs + c0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
+                epi_mid_store<16>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -370,14 +405,17 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, 1)
             const int K = pl.K[l], Np = pl.Npad[l];
             if (tid == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t w_smem = smem_u32(smem + pl.w_off[l]);
-                const uint32_t act_lbo = T2_ROWS * 16, w_lbo = (uint32_t)Np * 16;
-                const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS);  // W_last block (A, M = 128 channels) x act (B, N = 128 rows)
-                for (int mb = 0; mb < pl.mb; ++mb)
-                    for (int kk = 0; kk < (K >> 4); ++kk)
-                        umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS),
-                                  smem_desc(w_smem + (uint32_t)mb * (T2_ROWS * 16) + (uint32_t)kk * 2u * w_lbo, w_lbo, 128),
-                                  smem_desc(a_smem + (uint32_t)kk * 2u * act_lbo, act_lbo, 128), idesc, kk > 0 ? 1u : 0u);
+                // W_last block mb (A, M = 128 channels) x act (B, N = 128 rows)
+                const uint32_t idesc = s_idesc[l], wstep = s_wstep[l];
+                const int nk = K >> 4;
+                for (int mb = 0; mb < pl.mb; ++mb) {
+                    uint64_t ad = s_adesc[grp][l], wd = s_wdesc[grp][l] + (uint64_t)((mb * T2_ROWS * 16) >> 4);
+                    for (int kk = 0; kk < nk; ++kk) {
+                        umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS), wd, ad, idesc, kk > 0 ? 1u : 0u);
+                        ad += (2u * T2_ROWS * 16u) >> 4;
+                        wd += wstep;
+                    }
+                }
                 umma_commit(smem_u32(&mma_bar));
             }
             wait_mma();
