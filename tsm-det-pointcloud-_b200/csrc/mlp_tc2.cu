@@ -145,8 +145,11 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
 
 // GROUPS: tile pipelines per CTA.  SC = min(nsample, 32) in SA mode (8, 16 or 32).  DENSE: point-wise MLP over
 // (B,C,n) inputs (features = source 0, src1 = source 1, concatenated along channels), no pooling.
-template <int GROUPS, int SC, bool DENSE>
-__global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // one group per CTA: 4 CTAs per SM (<= 128 regs)
+// PF (SA mode): 16-byte feature chunks of a row that are prefetched INTO REGISTERS a whole tile ahead (4: <= 32
+// channels, 16: <= 128 channels); 0: rows of <= 4 channels read from the fp32 planes (a handful of registers, same
+// one-tile-ahead schedule), or -- wider than 128 channels -- cp.async into the operand buffer behind the last MMA.
+template <int GROUPS, int SC, bool DENSE, int PF>
+__global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) ? 4 : 1)  // <= 128 regs where 4 CTAs fit an SM
     mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
                    const __nv_bfloat16* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -199,12 +202,17 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        const uint32_t bar = smem_u32(&w_bar);
-        const long long t0 = clock64();
-        while (!mbar_try_wait_cta(bar, 0))
-            if (clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
-    }
+    bool weights_in = false;  // the weight image is awaited right before the first MMA: the first gather overlaps its copy
+    auto wait_weights = [&]() {
+        if (!weights_in) {
+            const uint32_t bar = smem_u32(&w_bar);
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (!mbar_try_wait_cta(bar, 0))
+                if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) watchdog_trip(a.status, TSM_ERR_WATCHDOG);
+            weights_in = true;
+        }
+    };
     const uint32_t d_tmem = tmem_base_s + (uint32_t)(grp * pl.grp_cols);
     const uint32_t t_lane = d_tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
     const uint32_t a_smem = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
@@ -233,14 +241,17 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
             }
         }
     };
-    // issue_gather(tile): cp.async of the row's feature chunks into the operand buffer (zero-fill when the row is masked
-    // or past the end) + the coordinate / narrow-feature loads; finish_gather(): the xyz chunk and the zero pad chunks
-    // from registers, then wait for the copies.  The operand buffer must be free: issued after the last MMA's commit.
+    // load_row(tile): every load of the row -- coordinates, and the features as PF register chunks / fp32 planes /
+    // cp.async -- is ISSUED; store_row(): what arrived in registers goes to the operand buffer.  With PF > 0 or planar
+    // rows, load_row(i+1) is issued right after store_row(i), so the loads have a whole tile of compute to land; the
+    // cp.async form needs the buffer itself and is issued behind tile i's last MMA (it overlaps the pooling epilogue).
     float pend_p[3] = {0.f, 0.f, 0.f}, pend_q[3] = {0.f, 0.f, 0.f}, pend_f[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 pf_row[PF > 0 ? PF : 1];
     bool pend_live = false;
     const uint32_t a_row_s = a_smem + (uint32_t)tid * 16u;
     const bool planar = featT == nullptr && a.c_feat > 0;  // <= 4 feature channels: read straight from (B,C,N) fp32
-    auto issue_gather = [&](int tile) {
+    constexpr bool kEarly = PF > 0;                         // (planar rows are early too: decided at run time)
+    auto load_row = [&](int tile) {
         if constexpr (!DENSE) {
             const long long g = (long long)tile * T2_ROWS + tid;
             const int id = id_raw;
@@ -264,6 +275,14 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
                     for (int k = 0; k < 4; ++k)
                         if (k < a.c_feat) pend_f[k] = __ldg(a.features + ((size_t)b * a.c_feat + k) * a.n + id);
                 }
+            } else if constexpr (PF > 0) {
+                const int fchunks = pl.cp >> 3;
+                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
+#pragma unroll
+                for (int kc = 0; kc < PF; ++kc) {
+                    pf_row[kc] = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && kc < fchunks) pf_row[kc] = __ldg(frow + kc);
+                }
             } else {
                 const int fchunks = pl.cp >> 3;
                 const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
@@ -276,10 +295,15 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
             }
         }
     };
-    auto finish_gather = [&]() {
+    auto store_row = [&]() {
         if constexpr (!DENSE) {
-            const int first = planar ? 0 : (pl.cp >> 3);
-            for (int kc = first; kc < nchunk0; ++kc) {
+            const int fchunks = (planar || featT == nullptr) ? 0 : (pl.cp >> 3);
+            if constexpr (PF > 0) {
+#pragma unroll
+                for (int kc = 0; kc < PF; ++kc)
+                    if (kc < fchunks) *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = pf_row[kc];
+            }
+            for (int kc = fchunks; kc < nchunk0; ++kc) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (pend_live) {
                     if (kc == pl.xyz_chunk) {
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
                 }
                 *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v;
             }
-            if (!planar) asm volatile("cp.async.wait_all;" ::: "memory");
+            if (PF == 0 && !planar) asm volatile("cp.async.wait_all;" ::: "memory");
         }
     };
     auto wait_mma = [&]() {
@@ -307,14 +331,19 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
+    const bool early = kEarly || planar;
     prefetch_row(tile0);
-    if (tile0 < num_tiles) issue_gather(tile0);
+    if (tile0 < num_tiles) load_row(tile0);
     prefetch_row(tile0 + tile_step);
 
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         // ------------------------------------------------------------------ layer-0 operand
         if constexpr (!DENSE) {
-            finish_gather();
+            store_row();
+            if (early) {  // the next tile's loads are in flight for this whole tile
+                if (tile + tile_step < num_tiles) load_row(tile + tile_step);
+                prefetch_row(tile + 2 * tile_step);
+            }
         } else {
             // dense: channel c of row g = src0[b, c, i] (c < c_feat) | src1[b, c - c_feat, i]; coalesced over threads
             const long long g = (long long)tile * T2_ROWS + tid;  // this thread's global row
@@ -345,6 +374,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
         // tile's tcgen05.ld's (every thread fenced them) before this tile's first MMA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        wait_weights();
         group_sync();
 
         // ------------------------------------------------------------------ layers 0 .. nl-2: D[row, cout] in TMEM
@@ -419,9 +449,10 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
                 umma_commit(smem_u32(&mma_bar));
             }
             wait_mma();
-            // the operand buffer is free again: start the next tile's gather now, it lands during the epilogue below
-            if (tile + tile_step < num_tiles) issue_gather(tile + tile_step);
-            prefetch_row(tile + 2 * tile_step);
+            if (!early) {  // cp.async rows: the operand buffer is free again, the copies land during the epilogue below
+                if (tile + tile_step < num_tiles) load_row(tile + tile_step);
+                prefetch_row(tile + 2 * tile_step);
+            }
             const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
 
             if constexpr (!DENSE) {
@@ -484,7 +515,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, GROUPS == 1 ? 4 : 1)  // 
                         }
                     }
                 }
-                // no barrier here: the next tile's MMA is issued after the barrier that follows finish_gather()
+                // no barrier here: the next tile's MMA is issued after the barrier that follows store_row()
             } else {
                 // dense: thread = output channel; 128 columns = 128 consecutive rows (points) of the tile
                 const long long g0 = (long long)tile * T2_ROWS;
@@ -668,13 +699,18 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, 
     using Kern = void (*)(const SaMlpArgs, const Tc2Plan, const __nv_bfloat16*, const unsigned char*, const int);
     Kern kern = nullptr;
     if (dense) {
-        kern = groups == 2 ? mlp_tc2_kernel<2, 32, true> : mlp_tc2_kernel<1, 32, true>;
+        kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0> : mlp_tc2_kernel<1, 32, true, 0>;
     } else {
         const int sc = S < 32 ? S : 32;
+        const int fchunks = featT ? (pl.cp >> 3) : 0;
+        const int pf = fchunks == 0 ? 0 : (fchunks <= 4 ? 4 : (fchunks <= 16 ? 16 : 0));
+#define TC2_PICK(G, P)                                                                                        \
+    (sc == 32 ? mlp_tc2_kernel<G, 32, false, P> : (sc == 16 ? mlp_tc2_kernel<G, 16, false, P> : mlp_tc2_kernel<G, 8, false, P>))
         if (groups == 2)
-            kern = sc == 32 ? mlp_tc2_kernel<2, 32, false> : (sc == 16 ? mlp_tc2_kernel<2, 16, false> : mlp_tc2_kernel<2, 8, false>);
+            kern = pf == 16 ? TC2_PICK(2, 16) : (pf == 4 ? TC2_PICK(2, 4) : TC2_PICK(2, 0));
         else
-            kern = sc == 32 ? mlp_tc2_kernel<1, 32, false> : (sc == 16 ? mlp_tc2_kernel<1, 16, false> : mlp_tc2_kernel<1, 8, false>);
+            kern = pf == 16 ? TC2_PICK(1, 16) : (pf == 4 ? TC2_PICK(1, 4) : TC2_PICK(1, 0));
+#undef TC2_PICK
     }
     TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     // resident CTAs per SM: what shared memory, registers (a grid of more CTAs than are resident runs a second,
