@@ -154,10 +154,13 @@ int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const 
 int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers, const int* channels,
                     const float* const* weights, const float* const* biases, void* packed, long long* packed_bytes,
                     void* stream);
+/* features_t (optional): the features as (B,N,round_up(c_feat,8)) bf16 rows (then features may be NULL and no
+ * transpose runs); out_t (optional second output): (B,M,round_up(cout,8)) bf16 rows = the next stacked layer's
+ * features_t; out may be NULL when out_t is given. */
 int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
-                                 const float* new_xyz, const float* features, const int* idx, const int* idx_cnt,
-                                 int num_layers, const int* channels, const void* packed, float* out, int out_ctot,
-                                 int out_c0, void* stream);
+                                 const float* new_xyz, const float* features, const void* features_t, const int* idx,
+                                 const int* idx_cnt, int num_layers, const int* channels, const void* packed, float* out,
+                                 void* out_t, int out_ctot, int out_c0, void* stream);
 int tsmdet_pointwise_mlp_packed(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
                                 const int* channels, const void* packed, float* out, int out_ctot, int out_c0,
                                 void* stream);

@@ -72,7 +72,7 @@ SIGNATURES = {
                              c_int, c_void_p],
     "tsmdet_mlp_pack": [c_int, c_int, c_int, c_int, c_int, c_int, _i, _pp, _pp, c_void_p, _ll, c_void_p],
     "tsmdet_sa_mlp_maxpool_packed": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_int, _i, c_void_p, c_void_p, c_int, c_int, c_void_p],
+                                     c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "tsmdet_pointwise_mlp_packed": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p],
     "tsmdet_voxel_centroids": [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

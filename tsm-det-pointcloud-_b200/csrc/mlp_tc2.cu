@@ -467,17 +467,24 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                     const float bias = bs[ch];
                     const bool ch_ok = ch < cout_last;
                     float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
+                    const int cpo = (cout_last + 7) & ~7;  // width of the bf16 row copy (zero padded)
+                    __nv_bfloat16* const tbase = reinterpret_cast<__nv_bfloat16*>(a.out_t) + (size_t)cbase * cpo + ch;
+                    const bool t_ok = a.out_t != nullptr && ch < cpo;
                     float run = 0.f;
                     auto emit = [&](int ci, float m) {
                         const unsigned cg = cbase + (unsigned)ci;
-                        if (ch_ok && cg < ctot) {
-                            const float y = fmaxf(__fadd_rn(m, bias), 0.f);
-                            if (pl.whole_tiles) {
-                                obase[ci] = y;
-                            } else {  // a tile may straddle two frames
-                                const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
-                                a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
+                        if (cg < ctot) {
+                            const float y = ch_ok ? fmaxf(__fadd_rn(m, bias), 0.f) : 0.f;
+                            if (ch_ok && a.out) {
+                                if (pl.whole_tiles) {
+                                    obase[ci] = y;
+                                } else {  // a tile may straddle two frames
+                                    const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
+                                    a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
+                                }
                             }
+                            // (B,M,cpo) bf16 rows for the next layer's gather: a warp writes 32 consecutive channels
+                            if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
                         }
                     };
 #pragma unroll 1
@@ -681,7 +688,9 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, 
     // feature rows: <= 4 channels are read straight from the (B,C,N) fp32 planes by the gather; wider inputs go
     // through a bf16 (B,N,Cp) transpose so that a gathered row is one contiguous run of 16-byte chunks
     __nv_bfloat16* featT = nullptr;
-    if (!dense && a.c_feat > 4) {
+    if (!dense && a.c_feat > 0 && a.feat_t) {
+        featT = (__nv_bfloat16*)a.feat_t;  // rows already in the gather's layout (a previous layer's out_t)
+    } else if (!dense && a.c_feat > 4) {
         void* p = nullptr;
         const size_t bytes = (size_t)b * a.n * pl.cp * sizeof(__nv_bfloat16);
         int rc = tsm_scratch_get(1, bytes, stream, &p);

@@ -126,16 +126,25 @@ extern "C" int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int u
     return tsm_mlp_tc2_pack(a, dense, static_cast<unsigned char*>(packed), packed_bytes, (cudaStream_t)stream);
 }
 
+// features_t (optional): the features as (B,N,round_up(c_feat,8)) bf16 rows -- then `features` may be NULL and no
+// transpose runs; out_t (optional): a second output, (B,M,round_up(cout,8)) bf16 rows, i.e. the next SA layer's
+// features_t (stacked layers chain through it); out may be NULL when out_t is given.
 extern "C" int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
-                                            const float* new_xyz, const float* features, const int* idx,
-                                            const int* idx_cnt, int num_layers, const int* channels, const void* packed,
-                                            float* out, int out_ctot, int out_c0, void* stream) {
+                                            const float* new_xyz, const float* features, const void* features_t,
+                                            const int* idx, const int* idx_cnt, int num_layers, const int* channels,
+                                            const void* packed, float* out, void* out_t, int out_ctot, int out_c0,
+                                            void* stream) {
     if (b <= 0 || m <= 0) return TSM_OK;
-    if (!packed) return TSM_ERR_INVALID;
+    if (!packed || (!out && !out_t)) return TSM_ERR_INVALID;
     tsm::SaMlpArgs a;
-    if (int rc = sa_args(a, b, n, m, nsample, c_feat, use_xyz, xyz, new_xyz, features, idx, idx_cnt, num_layers, channels,
-                         nullptr, nullptr, out, out_ctot, out_c0))
+    const float* f = features ? features : (const float*)features_t;  // sa_args only checks for non-null
+    if (int rc = sa_args(a, b, n, m, nsample, c_feat, use_xyz, xyz, new_xyz, f, idx, idx_cnt, num_layers, channels,
+                         nullptr, nullptr, out, out ? out_ctot : (1 << 30), out ? out_c0 : 0))
         return rc;
+    a.features = features;
+    a.feat_t = features_t;
+    a.out_t = out_t;
+    if (c_feat > 0 && !features && !features_t) return TSM_ERR_INVALID;
     return tsm_mlp_tc2(a, b, 0, (cudaStream_t)stream, static_cast<const unsigned char*>(packed));
 }
 

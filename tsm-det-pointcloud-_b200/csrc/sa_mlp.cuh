@@ -11,7 +11,9 @@ struct SaMlpArgs {
     const float* src1;      // dense mode only: source 1, (B,c1,n), concatenated after source 0 along channels; or null
     const int* idx;         // (B,M,S)
     const int* idx_cnt;     // (B,M) or null (no masking)
-    float* out;             // (B,out_ctot,M)
+    float* out;             // (B,out_ctot,M), or null when only out_t is wanted (tensor path)
+    const void* feat_t;     // optional: the features as (B,N,round_up(c_feat,8)) bf16 rows (a previous layer's out_t)
+    void* out_t;            // optional second output: (B,M,round_up(cout,8)) bf16 rows, zero padded -- the next layer's feat_t
     const float* w[4];
     const float* bias[4];
     int ch[5];  // ch[0] = input channels (3*use_xyz + C), ch[l+1] = outputs of layer l

@@ -197,21 +197,28 @@ class SABackboneNMS(torch.nn.Module):
             cur_xyz = new_xyz
         # stream B: query + fused MLP per layer, as soon as that layer's centres exist
         with torch.cuda.stream(s_sa):
-            cur_f = feats
+            cur_f, cur_t = feats, None  # fp32 (B,C,N) planes | bf16 (B,N,C) rows written by the previous layer
+            imgs = [l._packed_layers(l._folded_layers()[0][0][0].shape[1] - 3, True)[0] for l in layers]  # built once
             for li, (layer, (src_xyz, new_xyz), ev) in enumerate(zip(layers, centres, ready)):
                 s_sa.wait_event(ev)
                 g = layer.groupers[0]
                 cnt, bidx = pointnet2_utils.ball_query(g.radius, g.nsample, src_xyz, new_xyz)
                 mark(f"query{src_xyz.shape[1]}", s_sa)
                 folded = layer._folded_layers()[0]
-                img = layer._packed_layers(cur_f.shape[1], True)[0]  # weight image built once, not per step
-                if li == len(layers) - 1:
-                    out = out_features
-                else:
-                    out = torch.empty((b, folded[-1][0].shape[0], new_xyz.shape[1]), dtype=torch.float32, device=dev)
-                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision, packed=img)
+                img = imgs[li]
+                last = li == len(layers) - 1
+                cout = folded[-1][0].shape[0]
+                # Intermediate layers of the packed bf16 path hand their features on as bf16 ROWS -- exactly what the
+                # next layer's gather reads -- so no (B,C,M) fp32 tensor is written and no transpose kernel runs.
+                chain = img is not None and not last and imgs[li + 1] is not None
+                out = out_features if last else (None if chain else torch.empty((b, cout, new_xyz.shape[1]),
+                                                                              dtype=torch.float32, device=dev))
+                out_t = torch.empty((b, new_xyz.shape[1], (cout + 7) // 8 * 8), dtype=torch.bfloat16,
+                                    device=dev) if chain else None
+                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision, packed=img,
+                               feat_t=cur_t, out_t=out_t)
                 mark(f"mlp{src_xyz.shape[1]}", s_sa)
-                cur_f = out
+                cur_f, cur_t = out, out_t
         # stream C: NMS is independent of the backbone.  (Measured inside the captured graph: letting it run
         # beside the sampling chain is faster -- 4.98 vs 5.61 ms/step -- than holding it back until the chain
         # is done; TSMDET_NMS_AFTER_FPS=1 selects the latter for experiments.)

@@ -99,22 +99,36 @@ def pack_mlp(layers, *, dense: bool, nsample: int = 1, c_feat: int = 0, c1: int 
 
 
 def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: int, use_xyz: bool = True,
-                   precision: str = "fp32", packed: Optional[torch.Tensor] = None):
+                   precision: str = "fp32", packed: Optional[torch.Tensor] = None,
+                   feat_t: Optional[torch.Tensor] = None, out_t: Optional[torch.Tensor] = None):
     """One fused set-abstraction scale (C ABI ``tsmdet_sa_mlp_maxpool`` / ``_packed``): writes
     ``out[:, out_c0:out_c0+cout, :]`` (out is (B, Ctot, npoint) fp32 contiguous).  ``packed`` = ``pack_mlp(layers,
-    dense=False, nsample=..., c_feat=..., use_xyz=...)`` skips the per-call weight packing (bf16 path only)."""
+    dense=False, nsample=..., c_feat=..., use_xyz=...)`` skips the per-call weight packing (bf16 path only).
+    Stacked layers on the packed bf16 path can chain without transposes: ``out_t`` (B, npoint, round_up(cout, 8)) bf16
+    receives the pooled features as rows, and is the next layer's ``feat_t`` (then ``features`` may be None -- pass
+    ``c_feat`` through ``feat_t.shape[2]``-compatible layers -- and ``out`` may be None when only the rows are needed)."""
     b, n, _ = xyz.shape
     _, m, s = idx.shape
-    c_feat = 0 if features is None else features.shape[1]
+    if features is not None:
+        c_feat = features.shape[1]
+    elif feat_t is not None:
+        c_feat = layers[0][0].shape[1] - (3 if use_xyz else 0)
+        assert feat_t.dtype == torch.bfloat16 and feat_t.shape == (b, n, (c_feat + 7) // 8 * 8) and feat_t.is_contiguous()
+    else:
+        c_feat = 0
     nl = len(layers)
     chans = [(3 if use_xyz else 0) + c_feat] + [w.shape[0] for w, _ in layers]
     for l, (w, bias) in enumerate(layers):
         assert w.shape == (chans[l + 1], chans[l]) and w.is_contiguous() and bias.is_contiguous()
     ch_arr = (ctypes.c_int * (nl + 1))(*chans)
     if packed is not None and precision == "bf16":
+        if out_t is not None:
+            assert out_t.dtype == torch.bfloat16 and out_t.is_contiguous() and out_t.shape == (b, m, (chans[-1] + 7) // 8 * 8)
         call("tsmdet_sa_mlp_maxpool_packed", b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features),
-             ptr(idx), ptr(idx_cnt), nl, ch_arr, ptr(packed), ptr(out), out.shape[1], out_c0, stream_ptr(xyz.device))
+             ptr(feat_t), ptr(idx), ptr(idx_cnt), nl, ch_arr, ptr(packed), ptr(out), ptr(out_t),
+             out.shape[1] if out is not None else 0, out_c0, stream_ptr(xyz.device))
         return out
+    assert feat_t is None and out_t is None and out is not None, "row-chained layers need the packed bf16 path"
     w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
     prec = {"fp32": 0, "bf16": 1}[precision]
