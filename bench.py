@@ -591,7 +591,7 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
     t = _graph_timer(dev)
     kernels = []
     ctx = {}
-    cur_xyz, cur_f = xyz, feats
+    cur_xyz, cur_f, cur_t = xyz, feats, None
     tot = {"fps": [0.0, 0.0], "mlp": [0.0, 0.0, 0.0], "bq": [0.0, 0.0, 0.0]}  # ms, sm_ms, (flops | bytes)
     with torch.no_grad():
         for li, layer in enumerate(engine.backbone.layers):
@@ -607,9 +607,15 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
             ms_bq = t(lambda: pointnet2_utils.ball_query(g.radius, ns, cur_xyz, new_xyz))
             layers = layer._folded_layers()[0]
             img = layer._packed_layers(c, True)[0]
-            out = torch.empty((b, layers[-1][0].shape[0], m), device=dev)
-            ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, cur_f, bidx, cnt, layers, out, 0, precision=layer.precision,
-                                              packed=img))
+            cout = layers[-1][0].shape[0]
+            out = torch.empty((b, cout, m), device=dev)
+            # as in the pipelined step: layers hand their features on as bf16 rows (no fp32 tensor / transpose between)
+            chain_out = img is not None and li + 1 < len(engine.backbone.layers)
+            out_t = torch.empty((b, m, (cout + 7) // 8 * 8), dtype=torch.bfloat16, device=dev) if chain_out else None
+            f_in, t_in = (None, cur_t) if cur_t is not None else (cur_f, None)
+            ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, f_in, bidx, cnt, layers, out, 0, precision=layer.precision,
+                                              packed=img, feat_t=t_in, out_t=out_t))
+            next_t = out_t
             fps_bytes = b * (12 * n + 4 * m)
             bq_bytes = b * (12 * n + 12 * m + 4 * m * ns + 4 * m)
             chans = [3 + c] + [w.shape[0] for w, _ in layers]
@@ -633,7 +639,7 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
             tot["bq"][1] += ms_bq * sms * 0.6            # build: one CTA per cloud; query: every SM (ncu: 0.049 / 0.034 ms)
             tot["bq"][2] += bq_bytes
             ctx = {"xyz": cur_xyz, "f": cur_f, "idx": bidx}
-            cur_xyz, cur_f = new_xyz, out
+            cur_xyz, cur_f, cur_t = new_xyz, out, next_t
         # the API-level (materialising) grouping op on the last layer's shape: the HBM-bound kernel of the path
         lay = engine.backbone.layers[-1]
         g3 = lay.groupers[0]
