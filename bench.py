@@ -378,7 +378,7 @@ def main():
             res = eng.forward_device(*lane_inputs[0], gather=True)
             all_det, all_num = res["all_det"].clone(), res["all_num"].clone()
             torch.cuda.synchronize(dev)
-            gather_transport = ("peer-memory stores (tsmdet_peer_put: ring of 2 slots + credits), one kernel per step"
+            gather_transport = ("peer-memory stores (tsmdet_peer_put: ring of 4 slots + credits), one kernel per step"
                                 if eng._pg is not None else "nccl all_gather")
             f, k = res["det"].shape[0], res["det"].shape[1]
             ref_det, ref_num, _ = gather_packed(res["det_packed"], f, k)

@@ -108,7 +108,8 @@ class PeerGather:
     ``(s-1) % slots`` (their ack >= ``s - slots``), stores its packed records into row ``rank`` of that slot on every
     rank over NVLink, and publishes ``s`` into every rank's flag word.  An NCCL all_gather kernel holds SMs until all
     ranks have launched theirs (~15 % of the 8-GPU throughput at one collective per 0.6 ms step); here a rank only
-    ever waits when it is ``slots - 1`` whole steps ahead of the slowest peer, and then for exactly as long as the
+    ever waits when it is ``slots - 1`` whole steps ahead of the slowest peer (4 slots by default: with 2 the ranks were
+    coupled tightly enough to cost 7 % of the 8-GPU throughput), and then for exactly as long as the
     data it would overwrite is still unread -- records can never be torn or mixed across steps.
 
     Contract: the views of step ``s`` are valid from ``wait_stream()`` / ``wait()`` until this rank's NEXT ``put``
@@ -116,7 +117,7 @@ class PeerGather:
     rank constructs its PeerGather objects in the same order.  Construction is collective and agrees on failure:
     ``PeerGather.create`` returns None on EVERY rank if any rank could not set the transport up."""
 
-    def __init__(self, numel: int, device, group=None, slots: int = 2, timeout_s: float = 120.0):
+    def __init__(self, numel: int, device, group=None, slots: int = 4, timeout_s: float = 120.0):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 16:
@@ -181,7 +182,7 @@ class PeerGather:
         self._rows, self._flags, self._acks = rows, flags, acks
 
     @classmethod
-    def create(cls, numel: int, device, group=None, slots: int = 2, timeout_s: float = 120.0):
+    def create(cls, numel: int, device, group=None, slots: int = 4, timeout_s: float = 120.0):
         """Collective constructor: every rank gets a working PeerGather, or every rank gets None."""
 
         def agree(ok_local: bool) -> bool:
