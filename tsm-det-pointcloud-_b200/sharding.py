@@ -108,8 +108,8 @@ class PeerGather:
     ``(s-1) % slots`` (their ack >= ``s - slots``), stores its packed records into row ``rank`` of that slot on every
     rank over NVLink, and publishes ``s`` into every rank's flag word.  An NCCL all_gather kernel holds SMs until all
     ranks have launched theirs (~15 % of the 8-GPU throughput at one collective per 0.6 ms step); here a rank only
-    ever waits when it is ``slots - 1`` whole steps ahead of the slowest peer (4 slots by default: with 2 the ranks were
-    coupled tightly enough to cost 7 % of the 8-GPU throughput), and then for exactly as long as the
+    ever waits when it is ``slots - 1`` whole steps ahead of the slowest peer (4 slots by default: with 2 slots and a depth-8 pipeline the 8-GPU
+    device-resident throughput measured 0.91 of 8x one GPU), and then for exactly as long as the
     data it would overwrite is still unread -- records can never be torn or mixed across steps.
 
     Contract: the views of step ``s`` are valid from ``wait_stream()`` / ``wait()`` until this rank's NEXT ``put``
