@@ -13,9 +13,9 @@ for step in "$@"; do
     smoke)   timeout 600 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.txt 2>&1; tail -n 3 gpurun_out/${TAG}_smoke.txt ;;
     bench)   timeout 1500 python bench.py $rest > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -n 3 gpurun_out/${TAG}_bench.err; head -c 400 gpurun_out/${TAG}_bench.json; echo ;;
     prof)    timeout 300 python scripts/prof.py $rest --time --reps 5 2>&1 | grep -E "ms:|Error" | tee -a gpurun_out/${TAG}_prof.txt ;;
-    ncu)     op=${rest%%:*}; k=${rest#*:}
+    ncu)     op=${rest%%:*}; k=${rest#*:}; skip=${SKIP:-1}   # mlpN: the set-up runs the 3-layer backbone first -> SKIP=3
              timeout 300 python scripts/prof.py $op --time > gpurun_out/${TAG}_prof_$op.log 2>&1 && \
-             timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${TAG}_ncu_$op python scripts/prof.py $op > gpurun_out/${TAG}_ncu_$op.log 2>&1
+             timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/${TAG}_ncu_$op python scripts/prof.py $op > gpurun_out/${TAG}_ncu_$op.log 2>&1
              tail -n 2 gpurun_out/${TAG}_ncu_$op.log ;;
     dur)     timeout 300 python scripts/prof.py $rest > /dev/null 2>&1 && \
              timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_dur_$rest.csv python scripts/prof.py $rest > /dev/null 2>&1

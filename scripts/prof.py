@@ -80,12 +80,12 @@ def main():
         torch.cuda.synchronize()
         ts = []
         for _ in range(a.reps):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             fn()
-            e.record()
+            ev1.record()
             torch.cuda.synchronize()
-            ts.append(s.elapsed_time(e))
+            ts.append(ev0.elapsed_time(ev1))
     if a.time:
         print(a.op, "ms:", [round(t, 4) for t in ts])
     print("ok")
