@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-diag-suppress", "177",
-]
+] + os.environ.get("TSMDET_NVCC_EXTRA", "").split()  # e.g. -DMLP_PROF (phase clocks of the tcgen05 MLP kernel)
 
 
 def _deps_mtime() -> float:

@@ -107,6 +107,19 @@ __device__ __forceinline__ bool mbar_try_wait_cta(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 
+// non-blocking probe of a phase (test_wait returns at once; try_wait may suspend the thread)
+__device__ __forceinline__ bool mbar_test_wait_cta(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Remote (DSMEM) store that completes `bytes` on the destination CTA's mbarrier.
 __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c,
                                             uint32_t d) {
@@ -152,7 +165,7 @@ enum TsmKnob {
     KNOB_BQ_ALGO, KNOB_FPS_CLUSTER, KNOB_FPS_THREADS, KNOB_FPS_ALGO, KNOB_FPSB_T,
     KNOB_FPSB_P, KNOB_FPSB_K, KNOB_GROUP_SLAB_KB, KNOB_GROUP_WAVES, KNOB_GROUP_DIRECT,
     KNOB_NN_ALGO, KNOB_NMS_CTAS_PER_SM, KNOB_NMS_ALGO, KNOB_MLP_ONE_GROUP, KNOB_MLP_OCC,
-    KNOB_MLP_V1, KNOB_FPSC_K, KNOB_VOXEL_ALGO,
+    KNOB_MLP_V1, KNOB_FPSC_K, KNOB_VOXEL_ALGO, KNOB_MLP_NH,
     KNOB_COUNT
 };
 const char* tsm_knob(int id);

@@ -3,44 +3,68 @@
 // 1259-1268, 1297-1300) and the point-wise MLPs of the same file (PointnetFPModule.mlp :175-176, aggregation_mlp
 // :1320-1321: [1x1 conv + ReLU]* over a dense (B,C,n) tensor, no pooling) in one template.
 //
-// What changed against sa_mlp_tc.cu (kept for nsample < 8 and as the A/B reference, TSMDET_MLP_V1=1), and why -- ncu of round 1 showed
-// the tensor pipe 14 % active with each tile spending most of its time in the epilogues:
+// What changed against sa_mlp_tc.cu (kept for nsample < 8 and as the A/B reference, TSMDET_MLP_V1=1), and why:
 //
 //  * THE LAST LAYER IS COMPUTED TRANSPOSED.  Both operands are K-major core-matrix images in shared memory, so the
 //    roles can be swapped for free: D^T[channel, row] = W_last (A operand, M = 128 output channels per block) x
 //    activations (B operand, N = the tile's 128 rows).  In TMEM a lane is now an output CHANNEL and the columns are the
 //    tile's rows, i.e. the nsample rows of a centre are consecutive columns of ONE thread: the max-pool is an
-//    in-register FMNMX3 tree (16 instructions per 32 samples) instead of one REDUX.SYNC per channel per warp
-//    (256 warp collectives per tile at 256 channels), and bias + ReLU run once per centre AFTER the pool (both are
-//    monotone, so max(relu(x+b)) == relu(max(x)+b) bit for bit) instead of once per row.  The dense mode uses the
-//    same layout to write 512 contiguous bytes per thread.
-//  * epilogues keep several tcgen05.ld in flight per wait::ld (two 32-column loads instead of one 16-column load),
-//    add the bias with packed FADD2 and convert with F2FP.RELU (ReLU for free);
-//  * the gather of tile i+1 is issued as cp.async (LDGSTS, 16 bytes per feature chunk, zero-fill for masked rows)
-//    straight into the operand buffer as soon as tile i's last MMA has consumed it, and lands while tile i's pooling
-//    epilogue runs; the neighbour indices are prefetched one tile further ahead; one group barrier per layer
-//    (three per tile at three layers, five before);
+//    in-register FMNMX3 tree (16 instructions per 32 samples) instead of one REDUX.SYNC per channel per warp, and bias +
+//    ReLU run once per centre AFTER the pool (both are monotone, so max(relu(x+b)) == relu(max(x)+b) bit for bit).  The
+//    dense mode uses the same layout to write 256 contiguous bytes per thread.
+//  * THE BIAS OF EVERY OTHER LAYER IS ADDED BY THE TENSOR CORE: one extra K step multiplies a constant "ones" operand
+//    ([1, 1, 0, ...] per row, part of the weight image) with two weight rows holding bf16(b) and bf16(b - bf16(b)); the
+//    sum reproduces the fp32 bias to 2^-17 relative.  The mid-layer epilogue is then tcgen05.ld -> F2FP.RELU -> STS: no
+//    shared-memory bias loads and no adds (a third of its instructions in the round-2 ncu source view).
+//  * TWO THREADS PER TILE ROW (256-thread tile groups): ncu of the one-thread-per-row version showed 8 warps per SM at
+//    23 % issue slots, each warp a ~1800-instruction dependent chain per tile (28 % of the samples on the MMA barrier,
+//    the rest latency of its own chain).  Now thread (row, h) drains column half h in the epilogues and gathers the
+//    chunks of parity h: half the chain per warp, twice the warps.  Epilogue widths are compile-time (switch over the
+//    usual layer widths) and the pooling epilogue has a check-free path for whole tiles.
+//  * epilogues keep two 32-column tcgen05.ld in flight per wait::ld and convert with F2FP.RELU (ReLU for free);
+//  * rows are gathered a whole tile ahead into registers (or as cp.async, LDGSTS with zero-fill for masked rows, for
+//    rows wider than 128 channels); the neighbour indices are prefetched one tile further ahead; one group barrier per
+//    layer;
 //  * kernel parameters are __grid_constant__ (the per-layer plan arrays are indexed dynamically: without it the
-//    compiler copies them to local memory -- LDL on the critical path in the ncu source view of the first version).
+//    compiler copies them to local memory).
 //
-// One CTA = GROUPS x 128 threads; a group = one independent 128-row tile pipeline (own operand buffer, TMEM
+// One CTA = GROUPS x 256 threads; a group = one independent 128-row tile pipeline (own operand buffer, TMEM
 // columns, mbarrier, named barrier) over the CTA's resident weights, persistent over tiles.
+#include <cstdio>
+#include <type_traits>
+
 #include "sa_mlp.cuh"
 #include "umma.cuh"
+
+// -DMLP_PROF: lane 0 of warp 1 (a non-issuing warp) of group 0 of CTA 0 accumulates clock64() per phase of a tile and
+// prints the per-tile averages when the kernel ends (TSMDET_NVCC_EXTRA=-DMLP_PROF python .../build.py --force)
+#ifdef MLP_PROF
+#define MPROF(i)                                                        \
+    do {                                                                \
+        if (prof_on) {                                                  \
+            const long long t_ = clock64();                             \
+            prof_acc[i] += t_ - prof_t;                                 \
+            prof_t = t_;                                                \
+        }                                                               \
+    } while (0)
+#else
+#define MPROF(i)
+#endif
 
 namespace tsm {
 
 constexpr int T2_ROWS = 128;
-constexpr int T2_THREADS = 128;
 constexpr int T2_MAX_LAYERS = 4;
 
 struct Tc2Plan {
     int nl;
-    int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of 16)
+    int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of 16), without the bias step
     int Npad[T2_MAX_LAYERS];   // rows of layer l's weight image: cout padded to 16 (last layer: to 128)
-    int w_off[T2_MAX_LAYERS];  // byte offset of layer l's weights in dynamic smem
-    int b_off[T2_MAX_LAYERS];  // byte offset of layer l's bias (fp32)
+    int w_off[T2_MAX_LAYERS];  // byte offset of layer l's weights (non-last layers: K + 16 input rows, the last 16 = bias step)
+    int b_off;                 // byte offset of the LAST layer's bias (fp32; added after the pool)
+    int ones_off;              // the bias step's A operand: 2 chunk planes x 128 rows, [1, 1, 0, ...] | zeros
     int a_off, a_bytes;        // activation operand buffers (one per tile group)
+    int x_off;                 // nsample == 128: per-group exchange of the two halves' maxima (2 x 128 floats), else -1
     int smem_bytes, packed_bytes;
     int cp;                    // SA mode: feature channels padded to 8 (width of the bf16 transpose)
     int xyz_chunk;             // SA mode: 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
@@ -49,35 +73,52 @@ struct Tc2Plan {
     int whole_tiles;           // SA mode: M % (centres per tile) == 0 -> a tile's centres share the frame, consecutive p
 };
 
-// Weights (cout,cin) fp32 + bias -> the kernel's shared-memory image: per layer bf16 [K/8][Npad][8] (UMMA K-major core
-// matrices), then the fp32 biases.  SA mode: layer 0's input channels are permuted to the operand order
-// [features 0..C-1 | pad to cp | dx,dy,dz | pad] (reference order: [dx,dy,dz, features...], pointnet2_utils.py:523).
+// Weights (cout,cin) fp32 + bias -> the kernel's shared-memory image: per layer bf16 [K/8 (+2)][Npad][8] (UMMA K-major
+// core matrices; non-last layers end with the two planes of the bias step: input row K = bf16(b), row K+1 = bf16(b -
+// bf16(b)), rows K+2.. = 0), the last layer's fp32 bias, the ones operand.  SA mode: layer 0's input channels are
+// permuted to the operand order [features 0..C-1 | pad to cp | dx,dy,dz | pad] (reference order: [dx,dy,dz,
+// features...], pointnet2_utils.py:523).  blockIdx.y == nl builds the ones operand and the last bias.
 __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, const Tc2Plan pl, const int dense,
                                                             unsigned char* __restrict__ packed) {
     const int l = blockIdx.y;
+    if (l == pl.nl) {
+        __nv_bfloat16* ones = reinterpret_cast<__nv_bfloat16*>(packed + pl.ones_off);
+        for (int e = blockIdx.x * 256 + threadIdx.x; e < 2 * T2_ROWS * 8; e += gridDim.x * 256)
+            ones[e] = __float2bfloat16_rn((e < T2_ROWS * 8 && (e & 7) < 2) ? 1.f : 0.f);
+        const int Np = pl.Npad[pl.nl - 1], cout = a.ch[pl.nl];
+        float* bs = reinterpret_cast<float*>(packed + pl.b_off);
+        for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[pl.nl - 1] + e) : 0.f;
+        return;
+    }
     const int K = pl.K[l], Np = pl.Npad[l];
+    const int Kb = K + (l + 1 < pl.nl ? 16 : 0);  // + the bias step
     const int cin = a.ch[l], cout = a.ch[l + 1];
     __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(packed + pl.w_off[l]);
     const float* __restrict__ W = a.w[l];
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * K; e += gridDim.x * 256) {
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * Kb; e += gridDim.x * 256) {
         const int k = e / Np, n = e - k * Np;  // consecutive threads -> consecutive n: 16-byte-strided writes
-        float v = 0.f;
+        __nv_bfloat16 o = __float2bfloat16_rn(0.f);
         if (n < cout) {
-            int src = -1;
-            if (l == 0 && !dense) {
-                if (k < a.c_feat)
-                    src = (a.use_xyz ? 3 : 0) + k;
-                else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
-                    src = k - pl.xyz_chunk * 8;
-            } else if (k < cin) {
-                src = k;
+            if (k >= K) {
+                const float b = __ldg(a.bias[l] + n);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+                if (k == K) o = hi;
+                else if (k == K + 1) o = __float2bfloat16_rn(b - __bfloat162float(hi));
+            } else {
+                int src = -1;
+                if (l == 0 && !dense) {
+                    if (k < a.c_feat)
+                        src = (a.use_xyz ? 3 : 0) + k;
+                    else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
+                        src = k - pl.xyz_chunk * 8;
+                } else if (k < cin) {
+                    src = k;
+                }
+                if (src >= 0) o = __float2bfloat16_rn(__ldg(W + (size_t)n * cin + src));
             }
-            if (src >= 0) v = __ldg(W + (size_t)n * cin + src);
         }
-        ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = o;
     }
-    float* bs = reinterpret_cast<float*>(packed + pl.b_off[l]);
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[l] + e) : 0.f;
 }
 
 // features (B,C,N) fp32 -> (B,N,Cp) bf16, zero padded to Cp channels.  One CTA moves a 64-point x Cp-channel tile
@@ -109,28 +150,72 @@ __global__ void __launch_bounds__(256) transpose2_bf16_kernel(int c, int cp, int
     }
 }
 
-// bias + ReLU + bf16 pack of NC accumulator columns of this thread's row -> NC/8 chunks of the next layer's A operand
+// ReLU + bf16 pack of NC accumulator columns of this thread's row -> NC/8 chunks of the next layer's A operand.  (The
+// bias is already in the accumulator: every non-last layer ends with one extra K step against the constant "ones"
+// operand whose weight rows hold bias_hi + bias_lo, so the epilogue has no shared-memory bias loads and no adds.)
 template <int NC>
-__device__ __forceinline__ void load_bias(float4 (&bb)[NC / 4], const float* __restrict__ bias) {
-#pragma unroll
-    for (int q = 0; q < NC / 4; ++q) bb[q] = *reinterpret_cast<const float4*>(bias + 4 * q);
-}
-
-// the biases arrive in registers: they are loaded BEFORE the tcgen05.wait::ld, so the shared-memory latency hides
-// behind the TMEM load instead of stalling every FADD2 (short-scoreboard stalls in the ncu source view)
-template <int NC>
-__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], const float4 (&bb)[NC / 4], unsigned char* dst) {
+__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], unsigned char* dst) {
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
-        const float4 b0 = bb[2 * q];
-        const float4 b1 = bb[2 * q + 1];
-        const float2 s0 = add2(make_float2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), make_float2(b0.x, b0.y));
-        const float2 s1 = add2(make_float2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])), make_float2(b0.z, b0.w));
-        const float2 s2 = add2(make_float2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), make_float2(b1.x, b1.y));
-        const float2 s3 = add2(make_float2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])), make_float2(b1.z, b1.w));
-        *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) =
-            make_uint4(pack_bf16_relu(s0.x, s0.y), pack_bf16_relu(s1.x, s1.y), pack_bf16_relu(s2.x, s2.y), pack_bf16_relu(s3.x, s3.y));
+        *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = make_uint4(
+            pack_bf16_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+            pack_bf16_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+            pack_bf16_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+            pack_bf16_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
     }
+}
+
+// HW accumulator columns starting at TMEM address `taddr` (this thread's lane) -> HW/8 chunk planes starting at dst;
+// compile-time width: straight-line code, two 32-column loads in flight per wait where the width allows
+template <int HW, bool LEAN = false>
+__device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst) {
+    if constexpr (LEAN && HW >= 64) {  // 128-register kernels: one 32-column load in flight
+#pragma unroll
+        for (int i = 0; i < HW / 32; ++i) epi_mid<32>(taddr + 32u * i, dst + (size_t)(4 * i) * (T2_ROWS * 16));
+        return;
+    }
+    constexpr int N64 = HW / 64, R64 = HW % 64;
+#pragma unroll
+    for (int i = 0; i < N64; ++i) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32_nowait(taddr + 64u * i, v0);
+        tmem_ld32_nowait(taddr + 64u * i + 32u, v1);
+        tmem_wait_ld();
+        epi_mid_store<32>(v0, dst + (size_t)(8 * i) * (T2_ROWS * 16));
+        epi_mid_store<32>(v1, dst + (size_t)(8 * i + 4) * (T2_ROWS * 16));
+    }
+    constexpr int c1 = N64 * 64;
+    if constexpr (R64 >= 32) {
+        uint32_t v0[32];
+        tmem_ld32_nowait(taddr + c1, v0);
+        tmem_wait_ld();
+        epi_mid_store<32>(v0, dst + (size_t)(c1 / 8) * (T2_ROWS * 16));
+    }
+    constexpr int c2 = c1 + (R64 >= 32 ? 32 : 0);
+    if constexpr ((R64 % 32) >= 16) {
+        uint32_t v0[16];
+        tmem_ld16_nowait(taddr + c2, v0);
+        tmem_wait_ld();
+        epi_mid_store<16>(v0, dst + (size_t)(c2 / 8) * (T2_ROWS * 16));
+    }
+    constexpr int c3 = c2 + ((R64 % 32) >= 16 ? 16 : 0);
+    if constexpr ((R64 % 16) >= 8) {
+        uint32_t v0[8];
+        tmem_ld8_nowait(taddr + c3, v0);
+        tmem_wait_ld();
+        epi_mid_store<8>(v0, dst + (size_t)(c3 / 8) * (T2_ROWS * 16));
+    }
+}
+
+// any width that is a multiple of 8 (unusual channel counts)
+__device__ __forceinline__ void epi_mid_rt(int hw, uint32_t taddr, unsigned char* dst) {
+    int c = 0;
+    for (; c + 32 <= hw; c += 32) epi_mid<32>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
+    if (c + 16 <= hw) {
+        epi_mid<16>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
+        c += 16;
+    }
+    if (c + 8 <= hw) epi_mid<8>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
 }
 
 // max over W consecutive registers starting at v[O] (W = 8, 16 or 32), FMNMX3 tree
@@ -143,55 +228,49 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
     return m;
 }
 
-// GROUPS: tile pipelines per CTA.  SC = min(nsample, 32) in SA mode (8, 16 or 32).  DENSE: point-wise MLP over
-// (B,C,n) inputs (features = source 0, src1 = source 1, concatenated along channels), no pooling.
-// PF (SA mode): 16-byte feature chunks of a row that are prefetched INTO REGISTERS a whole tile ahead (4: <= 32
-// channels, 16: <= 128 channels); 0: rows of <= 4 channels read from the fp32 planes (a handful of registers, same
-// one-tile-ahead schedule), or -- wider than 128 channels -- cp.async into the operand buffer behind the last MMA.
-template <int GROUPS, int SC, bool DENSE, int PF>
-__global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) ? 4 : 1)  // <= 128 regs where 4 CTAs fit an SM
+// GROUPS: tile pipelines per CTA; a pipeline is 128 * NH threads = NH (1 or 2) per tile row: thread (row, h) drains
+// column part h of the row's TMEM lane in the mid-layer epilogues, gathers the 16-byte chunks kc = h (mod NH) of the
+// row, and in the transposed last layer owns output channel `row` for 128 / NH of the tile's rows.  NH = 2 halves
+// every warp's dependent chain per tile and doubles the warps, but duplicates the per-row bookkeeping (index load,
+// frame arithmetic) -- it pays where a row is wide (chosen per shape in the launcher, TSMDET_MLP_NH overrides).
+// SC = min(nsample, 32) in SA mode (8, 16 or 32).  DENSE: point-wise MLP over (B,C,n) inputs (features = source 0,
+// src1 = source 1, concatenated along channels), no pooling.
+// PF (SA mode): 16-byte feature chunks of a ROW that are prefetched INTO REGISTERS a whole tile ahead (4: <= 32
+// channels, 16: <= 128 channels; half of them per thread); 0: rows of <= 4 channels read from the fp32 planes (a handful
+// of registers, same one-tile-ahead schedule), or -- wider than 128 channels -- cp.async into the operand buffer behind
+// the last MMA.  MINB: CTAs per SM the register allocation must allow.
+template <int GROUPS, int SC, bool DENSE, int PF, int NH, int MINB>
+__global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
                    const __nv_bfloat16* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ uint32_t tmem_base_s;
-    // Per layer: the two operand descriptors of its first K step and what changes per step.  Built ONCE: assembling
-    // them per MMA (14-bit fields, 64-bit shifts) cost ~30 instructions per tcgen05.mma in the issuing thread -- about
-    // 2000 serial cycles per layer with the tensor pipe idle (SASS + ncu of the first version).
-    __shared__ __align__(8) uint64_t s_adesc[GROUPS][T2_MAX_LAYERS], s_wdesc[GROUPS][T2_MAX_LAYERS];
-    __shared__ uint32_t s_wstep[T2_MAX_LAYERS], s_idesc[T2_MAX_LAYERS];
 
-    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x >> 7);
-    const int tid = threadIdx.x & 127, warp = tid >> 5;  // within the group
+    constexpr int GT = 128 * NH;  // threads per tile group
+    constexpr bool LEAN = GT * GROUPS * MINB >= 512;  // <= 128 registers per thread: fewer TMEM loads in flight
+    constexpr int PFH = PF / NH;  // prefetch slots per thread
+    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x / GT);
+    const int gt = threadIdx.x & (GT - 1);
+    const int row = gt & 127;            // tile row (gather, mid-layer epilogues) / channel within a 128-block (last layer)
+    const int h = NH == 1 ? 0 : gt >> 7;  // column part / chunk residue; warps 4h..4h+3 of the group, TMEM lane quadrant = warp & 3
     uint64_t& mma_bar = mma_bars[grp];
     auto group_sync = [&]() {
         if (GROUPS == 1) __syncthreads();
-        else asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GT) : "memory");
     };
     const int S = a.s, M = a.m;
     const int log2s = 31 - __clz(S);
     const int nl = pl.nl;
 
-    // ---- one-time setup: packed weights + biases arrive with ONE bulk copy (TMA engine); barriers; TMEM
+    // ---- one-time setup: weights + bias rows + ones operand arrive with ONE bulk copy (TMA engine); barriers; TMEM
     if (threadIdx.x == 0) {
         for (int g = 0; g < GROUPS; ++g) mbar_init(smem_u32(&mma_bars[g]), 1);
         mbar_init(smem_u32(&w_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
         bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
-    }
-    if (tid == 0) {
-        const uint32_t act = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
-        for (int l = 0; l < nl; ++l) {
-            const uint32_t w_lbo = (uint32_t)pl.Npad[l] * 16;
-            s_adesc[grp][l] = smem_desc(act, T2_ROWS * 16, 128);                    // activations: LBO = 128 rows x 16 B
-            s_wdesc[grp][l] = smem_desc(smem_u32(smem + pl.w_off[l]), w_lbo, 128);  // weights: LBO = Npad rows x 16 B
-            if (grp == 0) {
-                s_wstep[l] = (2u * w_lbo) >> 4;  // start-address field (bytes >> 4) advance per K step of 16
-                s_idesc[l] = instr_desc_bf16_m128(l + 1 < nl ? pl.Npad[l] : T2_ROWS);
-            }
-        }
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -214,10 +293,20 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
         }
     };
     const uint32_t d_tmem = tmem_base_s + (uint32_t)(grp * pl.grp_cols);
-    const uint32_t t_lane = d_tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    // The MMAs are issued by one elected lane of the group's warp 0, from a warp-uniform branch with operands the
+    // compiler knows to be uniform: issued from a divergent `if (thread == 0)`, every tcgen05.mma was wrapped in an
+    // ELECT / 7 x R2UR waterfall loop (~19 instructions per MMA in the issuing thread, SASS).  The descriptors are
+    // assembled from the plan (constant bank) and the shared-memory base in the uniform datapath -- no shared-memory
+    // tables, no per-layer broadcasts (the path from the group barrier to the first MMA was ~100 instructions).
+    const bool mma_warp = __shfl_sync(FULL, gt >> 5, 0) == 0;
+    const uint32_t grp_u = __shfl_sync(FULL, (uint32_t)grp, 0);
+    const uint32_t d_tmem_u = __shfl_sync(FULL, d_tmem, 0);
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bit 46)
+    auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16); };
+    const uint32_t t_lane = d_tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
     const uint32_t a_smem = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
     unsigned char* const a_ptr = smem + pl.a_off + grp * pl.a_bytes;
-    unsigned char* const a_row = a_ptr + tid * 16;  // this thread's row inside every 16-byte chunk plane
+    unsigned char* const a_row = a_ptr + row * 16;  // this thread's row inside every 16-byte chunk plane
     uint32_t phase = 0;
     const int cout_last = a.ch[nl];
     const int nchunk0 = pl.K[0] >> 3;
@@ -225,15 +314,14 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
 
     // SA mode: the neighbour index and the hit count of this thread's row are LOADED one tile ahead and only looked at
     // when the next gather is issued; the coordinates are loaded when the gather is issued and only looked at when it
-    // is finished -- no load is consumed where it is issued (the first version did, and stalled there for the full
-    // L2 latency: ncu source view, 9 % + 5 % of the samples).
+    // is finished -- no load is consumed where it is issued.
     int id_raw = 0, cnt_raw = 1;
     auto prefetch_row = [&](int tile) {
         if constexpr (!DENSE) {
             id_raw = 0;
             cnt_raw = 0;  // rows past the end are masked
             if (tile < num_tiles) {
-                const long long g = (long long)tile * T2_ROWS + tid;
+                const long long g = (long long)tile * T2_ROWS + row;
                 if (g < a.total_rows) {
                     id_raw = __ldg(a.idx + g);
                     cnt_raw = a.idx_cnt ? __ldg(a.idx_cnt + (g >> log2s)) : 1;  // <= 0: empty ball -> zero input row
@@ -241,26 +329,27 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
             }
         }
     };
-    // load_row(tile): every load of the row -- coordinates, and the features as PF register chunks / fp32 planes /
-    // cp.async -- is ISSUED; store_row(): what arrived in registers goes to the operand buffer.  With PF > 0 or planar
-    // rows, load_row(i+1) is issued right after store_row(i), so the loads have a whole tile of compute to land; the
-    // cp.async form needs the buffer itself and is issued behind tile i's last MMA (it overlaps the pooling epilogue).
+    // load_row(tile): every load of this thread's chunks of the row (parity h) -- coordinates, and the features as PFH
+    // register chunks / fp32 planes / cp.async -- is ISSUED; store_row(): what arrived in registers goes to the operand
+    // buffer.  With PF > 0 or planar rows, load_row(i+1) is issued right after store_row(i), so the loads have a whole
+    // tile of compute to land; the cp.async form needs the buffer itself and is issued behind tile i's last MMA.
     float pend_p[3] = {0.f, 0.f, 0.f}, pend_q[3] = {0.f, 0.f, 0.f}, pend_f[4] = {0.f, 0.f, 0.f, 0.f};
-    uint4 pf_row[PF > 0 ? PF : 1];
+    uint4 pf_row[PFH > 0 ? PFH : 1];
     bool pend_live = false;
-    const uint32_t a_row_s = a_smem + (uint32_t)tid * 16u;
-    const bool planar = featT == nullptr && a.c_feat > 0;  // <= 4 feature channels: read straight from (B,C,N) fp32
-    constexpr bool kEarly = PF > 0;                         // (planar rows are early too: decided at run time)
+    const uint32_t a_row_s = a_smem + (uint32_t)row * 16u;
+    const bool planar = PF == 0 && featT == nullptr && a.c_feat > 0;  // <= 4 feature channels: read straight from (B,C,N) fp32
+    const bool own_xyz = pl.xyz_chunk >= 0 && (NH == 1 || (pl.xyz_chunk & 1) == h);
+    constexpr bool kEarly = PF > 0;  // (planar rows are early too: decided at run time)
     auto load_row = [&](int tile) {
         if constexpr (!DENSE) {
-            const long long g = (long long)tile * T2_ROWS + tid;
+            const long long g = (long long)tile * T2_ROWS + row;
             const int id = id_raw;
             const bool live = cnt_raw > 0;
             pend_live = live;
             const long long cpi = g < a.total_rows ? (g >> log2s) : 0;  // S is a power of two; B*M < 2^31 (launcher)
             const int b = (int)((unsigned)cpi / (unsigned)M);
             const size_t prow = (size_t)b * a.n + id;
-            if (pl.xyz_chunk >= 0 && live) {
+            if (own_xyz && live) {
                 const float* p = a.xyz + prow * 3;
                 const float* q = a.new_xyz + (size_t)cpi * 3;
 #pragma unroll
@@ -270,7 +359,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                 }
             }
             if (planar) {
-                if (live) {
+                if (live && h == 0) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if (k < a.c_feat) pend_f[k] = __ldg(a.features + ((size_t)b * a.c_feat + k) * a.n + id);
@@ -279,15 +368,15 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                 const int fchunks = pl.cp >> 3;
                 const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
 #pragma unroll
-                for (int kc = 0; kc < PF; ++kc) {
-                    pf_row[kc] = make_uint4(0u, 0u, 0u, 0u);
-                    if (live && kc < fchunks) pf_row[kc] = __ldg(frow + kc);
+                for (int j = 0; j < PFH; ++j) {
+                    pf_row[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && NH * j + h < fchunks) pf_row[j] = __ldg(frow + NH * j + h);
                 }
-            } else {
+            } else if (featT != nullptr) {
                 const int fchunks = pl.cp >> 3;
                 const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
                 const int nbytes = live ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, nothing is read
-                for (int kc = 0; kc < fchunks; ++kc)
+                for (int kc = h; kc < fchunks; kc += NH)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_row_s + (uint32_t)kc * (T2_ROWS * 16)),
                                  "l"(frow + kc), "r"(nbytes)
                                  : "memory");
@@ -300,10 +389,11 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
             const int fchunks = (planar || featT == nullptr) ? 0 : (pl.cp >> 3);
             if constexpr (PF > 0) {
 #pragma unroll
-                for (int kc = 0; kc < PF; ++kc)
-                    if (kc < fchunks) *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = pf_row[kc];
+                for (int j = 0; j < PFH; ++j)
+                    if (NH * j + h < fchunks) *reinterpret_cast<uint4*>(a_row + (size_t)(NH * j + h) * (T2_ROWS * 16)) = pf_row[j];
             }
-            for (int kc = fchunks; kc < nchunk0; ++kc) {
+            // this thread's chunks behind the features: coordinates, planar features, zero padding
+            for (int kc = fchunks + (NH == 2 ? ((fchunks ^ h) & 1) : 0); kc < nchunk0; kc += NH) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (pend_live) {
                     if (kc == pl.xyz_chunk) {
@@ -321,7 +411,12 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
     };
     auto wait_mma = [&]() {
         const uint32_t bar = smem_u32(&mma_bar);
-        if (!mbar_try_wait_cta(bar, phase)) {  // try_wait suspends the thread for a hardware time slice per call
+        // Probe with test_wait first: try_wait suspends the thread, and its wake-up added ~150 cycles to every layer of
+        // every tile (phase clocks, -DMLP_PROF; the three SA kernels ran 7 % faster).  A phase that has not completed
+        // after a few thousand probes goes to the suspending wait with the watchdog.
+        bool done = false;
+        for (int probes = 0; probes < 4096 && !(done = mbar_test_wait_cta(bar, phase)); ++probes) {}
+        if (!done && !mbar_try_wait_cta(bar, phase)) {
             const long long t0 = clock64();
             unsigned spins = 0;
             while (!mbar_try_wait_cta(bar, phase))
@@ -331,6 +426,11 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
+#ifdef MLP_PROF
+    const bool prof_on = blockIdx.x == 0 && grp == 0 && gt == 32;
+    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t = clock64(), prof_tiles = 0, prof_issue = 0;
+    const long long prof_t0 = prof_t;
+#endif
     const bool early = kEarly || planar;
     prefetch_row(tile0);
     if (tile0 < num_tiles) load_row(tile0);
@@ -340,20 +440,17 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
         // ------------------------------------------------------------------ layer-0 operand
         if constexpr (!DENSE) {
             store_row();
-            if (early) {  // the next tile's loads are in flight for this whole tile
-                if (tile + tile_step < num_tiles) load_row(tile + tile_step);
-                prefetch_row(tile + 2 * tile_step);
-            }
         } else {
-            // dense: channel c of row g = src0[b, c, i] (c < c_feat) | src1[b, c - c_feat, i]; coalesced over threads
-            const long long g = (long long)tile * T2_ROWS + tid;  // this thread's global row
+            // dense: channel c of row g = src0[b, c, i] (c < c_feat) | src1[b, c - c_feat, i]; coalesced over threads;
+            // thread (row, h) builds the 32-channel blocks h (mod NH)
+            const long long g = (long long)tile * T2_ROWS + row;  // this thread's global row
             const bool rv = g < a.total_rows;
             const int b = rv ? (int)(g / a.n) : 0;
             const int i = rv ? (int)(g - (long long)b * a.n) : 0;
             const float* s0 = a.features + (size_t)b * a.c_feat * a.n + i;
             const float* s1 = a.src1 ? a.src1 + (size_t)b * a.c1 * a.n + i : nullptr;
             const int ctot = a.c_feat + a.c1;
-            for (int kc0 = 0; kc0 < nchunk0; kc0 += 4) {
+            for (int kc0 = 4 * h; kc0 < nchunk0; kc0 += 4 * NH) {
                 float x[32];
 #pragma unroll
                 for (int u = 0; u < 32; ++u) {
@@ -372,174 +469,267 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
         }
         // generic-proxy writes of the operand -> visible to the tensor core (async proxy); also orders the previous
         // tile's tcgen05.ld's (every thread fenced them) before this tile's first MMA
+        MPROF(0);  // operand build
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         wait_weights();
         group_sync();
+        MPROF(1);  // fence + barrier
 
         // ------------------------------------------------------------------ layers 0 .. nl-2: D[row, cout] in TMEM
         for (int l = 0; l + 1 < nl; ++l) {
-            const int K = pl.K[l], Np = pl.Npad[l];
-            if (tid == 0) {
+            const int Np = pl.Npad[l];
+            if (mma_warp) {  // warp-uniform branch, uniform operands: the descriptors live in uniform registers
+#ifdef MLP_PROF
+                const long long ti0 = clock64();
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // act (A, M = 128 rows) x W_l (B, N = Np); per K step of 16 only the start-address fields advance
-                uint64_t ad = s_adesc[grp][l], wd = s_wdesc[grp][l];
-                const uint32_t idesc = s_idesc[l], wstep = s_wstep[l];
-                const int nk = K >> 4;
-                for (int kk = 0; kk < nk; ++kk) {
-                    umma_bf16(d_tmem, ad, wd, idesc, kk > 0 ? 1u : 0u);
-                    ad += (2u * T2_ROWS * 16u) >> 4;
-                    wd += wstep;
+                // act (A, M = 128 rows) x W_l (B, N = Np); per K step of 16 only the start-address fields advance;
+                // last step: ones (A) x [bias_hi, bias_lo] rows -- the bias lands in the accumulator
+                const uint32_t sbase = smem_u32(smem);
+                const uint32_t a_lo = desc_lo(sbase + (uint32_t)pl.a_off + grp_u * (uint32_t)pl.a_bytes, T2_ROWS * 16);  // LBO = 128 rows x 16 B
+                const uint32_t o_lo = desc_lo(sbase + (uint32_t)pl.ones_off, T2_ROWS * 16);
+                const uint32_t w_lo = desc_lo(sbase + (uint32_t)pl.w_off[l], (uint32_t)Np * 16);  // LBO = Npad rows x 16 B
+                const uint32_t idesc = instr_desc_bf16_m128(Np), wstep = (2u * (uint32_t)Np * 16u) >> 4;
+                constexpr uint32_t a_hi = DESC_HI, o_hi = DESC_HI, w_hi = DESC_HI;
+                const int nk = pl.K[l] >> 4;
+                if (elect_one()) {
+                    uint32_t ad = a_lo, wd = w_lo;
+                    for (int kk = 0; kk < nk; ++kk) {
+                        umma_bf16(d_tmem_u, desc64(ad, a_hi), desc64(wd, w_hi), idesc, kk > 0 ? 1u : 0u);
+                        ad += (2u * T2_ROWS * 16u) >> 4;
+                        wd += wstep;
+                    }
+                    umma_bf16(d_tmem_u, desc64(o_lo, o_hi), desc64(wd, w_hi), idesc, 1u);
+                    umma_commit(smem_u32(&mma_bar));
                 }
-                umma_commit(smem_u32(&mma_bar));
+                __syncwarp();
+#ifdef MLP_PROF
+                prof_issue += clock64() - ti0;
+#endif
             }
             wait_mma();
-            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
-            // bias + ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = row
-            int c0 = 0;
-            for (; c0 + 64 <= Np; c0 += 64) {
-                uint32_t v0[32], v1[32];
-                float4 b0[8], b1[8];
-                tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
-                tmem_ld32_nowait(t_lane + (uint32_t)c0 + 32u, v1);
-                load_bias<32>(b0, bs + c0);
-                load_bias<32>(b1, bs + c0 + 32);
-                tmem_wait_ld();
-                epi_mid_store<32>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-                epi_mid_store<32>(v1, b1, a_row + (size_t)((c0 + 32) >> 3) * (T2_ROWS * 16));
+            MPROF(2);  // mid-layer MMA issue + wait
+            // ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = (row, column part h)
+            const int hw = Np / NH;
+            const uint32_t ta = t_lane + (uint32_t)(h * hw);
+            unsigned char* const dst = a_row + (size_t)((h * hw) >> 3) * (T2_ROWS * 16);
+            switch (hw) {
+                case 8: epi_mid<8>(ta, dst); break;
+                case 16: epi_mid<16>(ta, dst); break;
+                case 32: epi_mid<32>(ta, dst); break;
+                case 64: epi_mid<64, LEAN>(ta, dst); break;
+                case 128: epi_mid<128, LEAN>(ta, dst); break;
+                case 256: epi_mid<256, LEAN>(ta, dst); break;
+                default: epi_mid_rt(hw, ta, dst); break;
             }
-            for (; c0 + 32 <= Np; c0 += 32) {
-                uint32_t v0[32];
-                float4 b0[8];
-                tmem_ld32_nowait(t_lane + (uint32_t)c0, v0);
-                load_bias<32>(b0, bs + c0);
-                tmem_wait_ld();
-                epi_mid_store<32>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-            }
-            for (; c0 + 16 <= Np; c0 += 16) {
-                uint32_t v0[16];
-                float4 b0[4];
-                tmem_ld16_nowait(t_lane + (uint32_t)c0, v0);
-                load_bias<16>(b0, bs + c0);
-                tmem_wait_ld();
-                epi_mid_store<16>(v0, b0, a_row + (size_t)(c0 >> 3) * (T2_ROWS * 16));
-            }
+            MPROF(3);  // mid-layer epilogue
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             group_sync();
+            MPROF(1);
         }
 
         // ------------------------------------------------------------------ last layer, transposed: D^T[cout, row]
         {
             const int l = nl - 1;
-            const int K = pl.K[l], Np = pl.Npad[l];
-            if (tid == 0) {
+            if (mma_warp) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // W_last block mb (A, M = 128 channels) x act (B, N = 128 rows)
-                const uint32_t idesc = s_idesc[l], wstep = s_wstep[l];
-                const int nk = K >> 4;
-                for (int mb = 0; mb < pl.mb; ++mb) {
-                    uint64_t ad = s_adesc[grp][l], wd = s_wdesc[grp][l] + (uint64_t)((mb * T2_ROWS * 16) >> 4);
-                    for (int kk = 0; kk < nk; ++kk) {
-                        umma_bf16(d_tmem + (uint32_t)(mb * T2_ROWS), wd, ad, idesc, kk > 0 ? 1u : 0u);
-                        ad += (2u * T2_ROWS * 16u) >> 4;
-                        wd += wstep;
+                const uint32_t sbase = smem_u32(smem);
+                const uint32_t a_lo = desc_lo(sbase + (uint32_t)pl.a_off + grp_u * (uint32_t)pl.a_bytes, T2_ROWS * 16);
+                const uint32_t w_lo = desc_lo(sbase + (uint32_t)pl.w_off[l], (uint32_t)pl.Npad[l] * 16);
+                const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS), wstep = (2u * (uint32_t)pl.Npad[l] * 16u) >> 4;
+                constexpr uint32_t a_hi = DESC_HI, w_hi = DESC_HI;
+                const int nk = pl.K[l] >> 4;
+                if (elect_one()) {
+                    for (int mb = 0; mb < pl.mb; ++mb) {
+                        uint32_t ad = a_lo, wd = w_lo + (uint32_t)((mb * T2_ROWS * 16) >> 4);
+                        for (int kk = 0; kk < nk; ++kk) {
+                            umma_bf16(d_tmem_u + (uint32_t)(mb * T2_ROWS), desc64(wd, w_hi), desc64(ad, a_hi), idesc, kk > 0 ? 1u : 0u);
+                            ad += (2u * T2_ROWS * 16u) >> 4;
+                            wd += wstep;
+                        }
                     }
+                    umma_commit(smem_u32(&mma_bar));
                 }
-                umma_commit(smem_u32(&mma_bar));
+                __syncwarp();
             }
+            // The next tile's row loads are issued here: they fly during the last MMA and the pooling epilogue and are
+            // consumed by the next store_row().  (Issued at the top of the tile, the prefetched registers were live across
+            // the mid-layer epilogues and ptxas spilled them right behind the loads -- STL stalls on the load, ncu.)
+            if (early) {
+                if (tile + tile_step < num_tiles) load_row(tile + tile_step);
+                prefetch_row(tile + 2 * tile_step);
+            }
+            MPROF(4);  // next tile's loads issued
             wait_mma();
+            MPROF(5);  // last MMA wait
             if (!early) {  // cp.async rows: the operand buffer is free again, the copies land during the epilogue below
                 if (tile + tile_step < num_tiles) load_row(tile + tile_step);
                 prefetch_row(tile + 2 * tile_step);
             }
-            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off[l]);
+            const float* bs = reinterpret_cast<const float*>(smem + pl.b_off);
+            constexpr int PW = T2_ROWS / NH;                      // tile rows (TMEM columns) per thread
+            const uint32_t t_part = t_lane + (uint32_t)(PW * h);  // this thread's columns of every channel block
 
             if constexpr (!DENSE) {
-                // thread = output channel; columns = the tile's rows: max over the S columns of a centre in registers,
-                // then bias + ReLU once per centre
+                // thread = (output channel, half of the tile's rows): max over the S columns of a centre in registers,
+                // then bias + ReLU once per centre (both monotone: max(relu(x+b)) == relu(max(x)+b) bit for bit)
                 const int cpt = T2_ROWS >> log2s;  // centres per tile
                 const unsigned cbase = (unsigned)tile * (unsigned)cpt;
                 const unsigned ctot = (unsigned)(a.total_rows >> log2s);
                 const unsigned b0 = cbase / (unsigned)M, p0 = cbase - b0 * (unsigned)M;
-                for (int mb = 0; mb < pl.mb; ++mb) {
-                    const int ch = mb * T2_ROWS + tid;
-                    const float bias = bs[ch];
-                    const bool ch_ok = ch < cout_last;
-                    float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
-                    const int cpo = (cout_last + 7) & ~7;  // width of the bf16 row copy (zero padded)
-                    __nv_bfloat16* const tbase = reinterpret_cast<__nv_bfloat16*>(a.out_t) + (size_t)cbase * cpo + ch;
-                    const bool t_ok = a.out_t != nullptr && ch < cpo;
-                    float run = 0.f;
-                    auto emit = [&](int ci, float m) {
-                        const unsigned cg = cbase + (unsigned)ci;
-                        if (cg < ctot) {
+                const int cpo = (cout_last + 7) & ~7;  // width of the bf16 row copy (zero padded)
+                const bool full = pl.whole_tiles && cbase + (unsigned)cpt <= ctot;  // every centre valid, one frame
+                float part0 = 0.f, part1 = 0.f;  // NH == 2, S == 128: this half's maximum per channel block
+                auto pool = [&](auto full_tag) {
+                    constexpr bool FULL = decltype(full_tag)::value;
+                    for (int mb = 0; mb < pl.mb; ++mb) {
+                        const int ch = mb * T2_ROWS + row;
+                        const float bias = bs[ch];
+                        const bool ch_ok = ch < cout_last;
+                        float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
+                        __nv_bfloat16* const tbase = reinterpret_cast<__nv_bfloat16*>(a.out_t) + (size_t)cbase * cpo + ch;
+                        const bool o_ok = a.out != nullptr && ch_ok;
+                        const bool t_ok = a.out_t != nullptr && ch < cpo;
+                        auto emit = [&](int ci, float m) {
                             const float y = ch_ok ? fmaxf(__fadd_rn(m, bias), 0.f) : 0.f;
-                            if (ch_ok && a.out) {
-                                if (pl.whole_tiles) {
-                                    obase[ci] = y;
-                                } else {  // a tile may straddle two frames
-                                    const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
-                                    a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
+                            if constexpr (FULL) {
+                                if (o_ok) obase[ci] = y;
+                                // (B,M,cpo) bf16 rows for the next layer's gather: a warp writes 32 consecutive channels
+                                if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
+                            } else {
+                                const unsigned cg = cbase + (unsigned)ci;
+                                if (cg < ctot) {
+                                    if (o_ok) {  // a tile may straddle two frames
+                                        const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
+                                        a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
+                                    }
+                                    if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
                                 }
                             }
-                            // (B,M,cpo) bf16 rows for the next layer's gather: a warp writes 32 consecutive channels
-                            if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
-                        }
-                    };
+                        };
+                        if (mb * T2_ROWS + (row & ~31) >= (cpo > cout_last ? cpo : cout_last)) continue;  // warp-uniform: padding channels
+                        float run = 0.f;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < T2_ROWS; c0 += 64) {
-                        uint32_t v0[32], v1[32];
-                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0), v0);
-                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0 + 32), v1);
-                        tmem_wait_ld();
-                        if constexpr (SC == 32) {
-                            // S = 32, 64 or 128: a 32-column chunk lies inside one centre
-                            const float m0 = max_run<0, 32>(v0), m1 = max_run<0, 32>(v1);
-                            if (S == 32) {
-                                emit(c0 >> 5, m0);
-                                emit((c0 >> 5) + 1, m1);
-                            } else if (S == 64) {
-                                emit(c0 >> 6, fmaxf(m0, m1));
-                            } else {  // S == 128
-                                run = c0 == 0 ? fmaxf(m0, m1) : max3(run, m0, m1);
-                                if (c0 == 64) emit(0, run);
+                        for (int cb = 0; cb < PW; cb += 64) {
+                            const int c0 = PW * h + cb;  // first tile row of this batch
+                            uint32_t v0[32], v1[32];
+                            tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb), v0);
+                            if constexpr (LEAN && SC < 32) {  // half the registers: the first 32 columns are emitted before the second load
+                                tmem_wait_ld();
+                                if constexpr (SC == 16) {
+                                    emit((c0 >> 4) + 0, max_run<0, 16>(v0));
+                                    emit((c0 >> 4) + 1, max_run<16, 16>(v0));
+                                } else {
+                                    emit((c0 >> 3) + 0, max_run<0, 8>(v0));
+                                    emit((c0 >> 3) + 1, max_run<8, 8>(v0));
+                                    emit((c0 >> 3) + 2, max_run<16, 8>(v0));
+                                    emit((c0 >> 3) + 3, max_run<24, 8>(v0));
+                                }
+                                tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb + 32), v0);
+                                tmem_wait_ld();
+                                if constexpr (SC == 16) {
+                                    emit((c0 >> 4) + 2, max_run<0, 16>(v0));
+                                    emit((c0 >> 4) + 3, max_run<16, 16>(v0));
+                                } else {
+                                    emit((c0 >> 3) + 4, max_run<0, 8>(v0));
+                                    emit((c0 >> 3) + 5, max_run<8, 8>(v0));
+                                    emit((c0 >> 3) + 6, max_run<16, 8>(v0));
+                                    emit((c0 >> 3) + 7, max_run<24, 8>(v0));
+                                }
+                                continue;
                             }
-                        } else if constexpr (SC == 16) {
-                            emit((c0 >> 4) + 0, max_run<0, 16>(v0));
-                            emit((c0 >> 4) + 1, max_run<16, 16>(v0));
-                            emit((c0 >> 4) + 2, max_run<0, 16>(v1));
-                            emit((c0 >> 4) + 3, max_run<16, 16>(v1));
-                        } else {  // SC == 8
-                            emit((c0 >> 3) + 0, max_run<0, 8>(v0));
-                            emit((c0 >> 3) + 1, max_run<8, 8>(v0));
-                            emit((c0 >> 3) + 2, max_run<16, 8>(v0));
-                            emit((c0 >> 3) + 3, max_run<24, 8>(v0));
-                            emit((c0 >> 3) + 4, max_run<0, 8>(v1));
-                            emit((c0 >> 3) + 5, max_run<8, 8>(v1));
-                            emit((c0 >> 3) + 6, max_run<16, 8>(v1));
-                            emit((c0 >> 3) + 7, max_run<24, 8>(v1));
+                            float m0 = 0.f, m1 = 0.f;
+                            if constexpr (LEAN && SC == 32) {  // one load in flight, the same registers twice
+                                tmem_wait_ld();
+                                m0 = max_run<0, 32>(v0);
+                                tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb + 32), v0);
+                                tmem_wait_ld();
+                                m1 = max_run<0, 32>(v0);
+                            } else {
+                                tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb + 32), v1);
+                                tmem_wait_ld();
+                                if constexpr (SC == 32) {
+                                    m0 = max_run<0, 32>(v0);
+                                    m1 = max_run<0, 32>(v1);
+                                }
+                            }
+                            if constexpr (SC == 32) {
+                                // S = 32, 64 or 128: a 32-column chunk lies inside one centre
+                                if (S == 32) {
+                                    emit(c0 >> 5, m0);
+                                    emit((c0 >> 5) + 1, m1);
+                                } else if (S == 64) {
+                                    emit(c0 >> 6, fmaxf(m0, m1));
+                                } else if (NH == 1) {  // S == 128, one thread per channel
+                                    run = cb == 0 ? fmaxf(m0, m1) : max3(run, m0, m1);
+                                    if (cb == 64) emit(0, run);
+                                } else {  // S == 128: the two halves of a channel meet in shared memory (below)
+                                    if (mb == 0) part0 = fmaxf(m0, m1);
+                                    else part1 = fmaxf(m0, m1);
+                                }
+                            } else if constexpr (SC == 16) {
+                                emit((c0 >> 4) + 0, max_run<0, 16>(v0));
+                                emit((c0 >> 4) + 1, max_run<16, 16>(v0));
+                                emit((c0 >> 4) + 2, max_run<0, 16>(v1));
+                                emit((c0 >> 4) + 3, max_run<16, 16>(v1));
+                            } else {  // SC == 8
+                                emit((c0 >> 3) + 0, max_run<0, 8>(v0));
+                                emit((c0 >> 3) + 1, max_run<8, 8>(v0));
+                                emit((c0 >> 3) + 2, max_run<16, 8>(v0));
+                                emit((c0 >> 3) + 3, max_run<24, 8>(v0));
+                                emit((c0 >> 3) + 4, max_run<0, 8>(v1));
+                                emit((c0 >> 3) + 5, max_run<8, 8>(v1));
+                                emit((c0 >> 3) + 6, max_run<16, 8>(v1));
+                                emit((c0 >> 3) + 7, max_run<24, 8>(v1));
+                            }
                         }
                     }
-                }
+                    if (NH == 2 && SC == 32 && S == 128) {  // uniform; the next write of xbuf lies behind the next tile's barriers
+                        float* const xbuf = reinterpret_cast<float*>(smem + pl.x_off) + grp * (2 * T2_ROWS);
+                        if (h == 1) {
+                            xbuf[row] = part0;
+                            xbuf[T2_ROWS + row] = part1;
+                        }
+                        group_sync();
+                        if (h == 0) {
+                            for (int mb = 0; mb < pl.mb; ++mb) {
+                                const int ch = mb * T2_ROWS + row;
+                                const bool ch_ok = ch < cout_last;
+                                const float m = fmaxf(mb == 0 ? part0 : part1, xbuf[mb * T2_ROWS + row]);
+                                const float y = ch_ok ? fmaxf(__fadd_rn(m, bs[ch]), 0.f) : 0.f;
+                                if (cbase < ctot) {  // one centre per tile
+                                    if (a.out != nullptr && ch_ok) a.out[((size_t)b0 * a.out_ctot + a.out_c0 + ch) * M + p0] = y;
+                                    if (a.out_t != nullptr && ch < cpo)
+                                        reinterpret_cast<__nv_bfloat16*>(a.out_t)[(size_t)cbase * cpo + ch] = __float2bfloat16_rn(y);
+                                }
+                            }
+                        }
+                    }
+                };
+                if (full) pool(std::true_type{});
+                else pool(std::false_type{});
                 // no barrier here: the next tile's MMA is issued after the barrier that follows store_row()
             } else {
-                // dense: thread = output channel; 128 columns = 128 consecutive rows (points) of the tile
+                // dense: thread = (output channel, half): 64 columns = 64 consecutive rows (points) of the tile
                 const long long g0 = (long long)tile * T2_ROWS;
                 const int b0 = (int)(g0 / a.n);
                 const int i0 = (int)(g0 - (long long)b0 * a.n);
                 const bool whole = (i0 + T2_ROWS <= a.n) && (g0 + T2_ROWS <= a.total_rows);  // one batch entry, full tile
                 for (int mb = 0; mb < pl.mb; ++mb) {
-                    const int ch = mb * T2_ROWS + tid;
+                    const int ch = mb * T2_ROWS + row;
                     const float bias = bs[ch];
                     const bool ch_ok = ch < cout_last;
-                    float* const orow = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * a.n + i0;
+                    if (mb * T2_ROWS + (row & ~31) >= cout_last) continue;  // warp-uniform: padding channels
+                    float* const orow = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * a.n + i0 + PW * h;
                     const bool vec = whole && ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0);
 #pragma unroll 1
-                    for (int c0 = 0; c0 < T2_ROWS; c0 += 64) {
+                    for (int cb = 0; cb < PW; cb += 64) {
                         uint32_t v0[32], v1[32];
-                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0), v0);
-                        tmem_ld32_nowait(t_lane + (uint32_t)(mb * T2_ROWS + c0 + 32), v1);
+                        tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb), v0);
+                        tmem_ld32_nowait(t_part + (uint32_t)(mb * T2_ROWS + cb + 32), v1);
                         tmem_wait_ld();
                         if (!ch_ok) continue;
                         if (vec) {
@@ -550,7 +740,7 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                                 o.y = fmaxf(__uint_as_float(v0[4 * q + 1]) + bias, 0.f);
                                 o.z = fmaxf(__uint_as_float(v0[4 * q + 2]) + bias, 0.f);
                                 o.w = fmaxf(__uint_as_float(v0[4 * q + 3]) + bias, 0.f);
-                                *reinterpret_cast<float4*>(orow + c0 + 4 * q) = o;
+                                *reinterpret_cast<float4*>(orow + cb + 4 * q) = o;
                             }
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
@@ -559,12 +749,12 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                                 o.y = fmaxf(__uint_as_float(v1[4 * q + 1]) + bias, 0.f);
                                 o.z = fmaxf(__uint_as_float(v1[4 * q + 2]) + bias, 0.f);
                                 o.w = fmaxf(__uint_as_float(v1[4 * q + 3]) + bias, 0.f);
-                                *reinterpret_cast<float4*>(orow + c0 + 32 + 4 * q) = o;
+                                *reinterpret_cast<float4*>(orow + cb + 32 + 4 * q) = o;
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 64; ++j) {
-                                const long long g2 = g0 + c0 + j;
+                                const long long g2 = g0 + PW * h + cb + j;
                                 if (g2 < a.total_rows) {
                                     const int b2 = (int)(g2 / a.n);
                                     const int i2 = (int)(g2 - (long long)b2 * a.n);
@@ -577,8 +767,23 @@ __global__ void __launch_bounds__(T2_THREADS * GROUPS, (GROUPS == 1 && PF <= 4) 
                 }
             }
         }
+#ifdef MLP_PROF
+        MPROF(6);  // pooling / output epilogue
+        ++prof_tiles;
+#endif
     }
 
+#ifdef MLP_PROF
+    if (blockIdx.x == 0 && grp == 0 && gt == 0 && tile0 < num_tiles)
+        printf("   issuing warp: barrier exit -> commit issued, mid layers, cycles per tile: %lld\n",
+               prof_issue / ((num_tiles - tile0 + tile_step - 1) / tile_step));
+    if (prof_on && prof_tiles > 0)
+        printf("mlp_tc2<G%d,SC%d,D%d,PF%d,NH%d> tiles/group %lld cycles/tile: total %lld | build %lld fence+bar %lld mid-mma-wait %lld mid-epi %lld "
+               "issue-loads %lld last-mma-wait %lld pool %lld\n",
+               GROUPS, SC, (int)DENSE, PF, NH, prof_tiles, (clock64() - prof_t0) / prof_tiles, prof_acc[0] / prof_tiles,
+               prof_acc[1] / prof_tiles, prof_acc[2] / prof_tiles, prof_acc[3] / prof_tiles, prof_acc[4] / prof_tiles,
+               prof_acc[5] / prof_tiles, prof_acc[6] / prof_tiles);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -623,20 +828,22 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
         kmax = pl.K[l] > kmax ? pl.K[l] : kmax;
         if (!last) nmid = pl.Npad[l] > nmid ? pl.Npad[l] : nmid;
         pl.w_off[l] = off;
-        off += pl.Npad[l] * pl.K[l] * 2;
+        off += pl.Npad[l] * (pl.K[l] + (last ? 0 : 16)) * 2;
     }
+    for (int l = pl.nl; l < T2_MAX_LAYERS; ++l) pl.K[l] = pl.Npad[l] = pl.w_off[l] = 0;
     if (kmax > 512) return TSM_ERR_INVALID;
     pl.mb = pl.Npad[pl.nl - 1] / T2_ROWS;
     pl.whole_tiles = (!dense && (a.m % (T2_ROWS / S)) == 0) ? 1 : 0;
-    for (int l = 0; l < pl.nl; ++l) {
-        pl.b_off[l] = off;
-        off += pl.Npad[l] * 4;
-    }
-    pl.packed_bytes = off;  // multiple of 64
+    pl.b_off = off;
+    off += pl.Npad[pl.nl - 1] * 4;
+    pl.ones_off = off;  // offsets so far are multiples of 32; descriptors address 16-byte units
+    off += 2 * T2_ROWS * 16;
+    pl.packed_bytes = off;  // multiple of 32
     off = round_up2(off, 128);
     pl.a_off = off;
     pl.a_bytes = round_up2(T2_ROWS * kmax * 2, 128);
-    auto smem_for = [&](int groups) { return off + groups * pl.a_bytes; };
+    const bool xch = !dense && S == T2_ROWS;
+    auto smem_for = [&](int groups) { return off + groups * pl.a_bytes + (xch ? groups * 2 * T2_ROWS * 4 : 0); };
     if (smem_for(1) > 227 * 1024 - 64) return TSM_ERR_INVALID;
     const int need_cols = nmid > pl.mb * T2_ROWS ? nmid : pl.mb * T2_ROWS;
     pl.grp_cols = 32;
@@ -648,15 +855,16 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
         !tsm_knob(KNOB_MLP_ONE_GROUP))
         groups = 2;
     pl.tmem_cols = pl.grp_cols * groups;
+    pl.x_off = xch ? off + groups * pl.a_bytes : -1;
     pl.smem_bytes = smem_for(groups);
     *out = pl;
     *groups_out = groups;
     return TSM_OK;
 }
 
-// The kernel's weight image (bf16 UMMA core matrices + fp32 biases) for an MLP: *bytes = its size; packed != nullptr:
-// build it there (device memory, >= *bytes).  Callers with constant weights build it ONCE and pass it to every call
-// (the packing kernel costs 5-8 us, comparable to a whole SA layer's tensor work).
+// The kernel's weight image (bf16 UMMA core matrices incl. the bias steps, the last fp32 bias, the ones operand) for an
+// MLP: *bytes = its size; packed != nullptr: build it there (device memory, >= *bytes).  Callers with constant weights
+// build it ONCE and pass it to every call (the packing kernel costs 5-8 us, comparable to a whole SA layer's tensor work).
 int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, long long* bytes, cudaStream_t stream) {
     using namespace tsm;
     Tc2Plan pl;
@@ -667,7 +875,7 @@ int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, 
     if (packed) {
         for (int l = 0; l < pl.nl; ++l)
             if (!a.w[l] || !a.bias[l]) return TSM_ERR_INVALID;
-        dim3 pgrid(16, (unsigned)pl.nl);
+        dim3 pgrid(16, (unsigned)pl.nl + 1);
         pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(a, pl, dense, packed);
         TSM_LAUNCH_CHECK();
     }
@@ -707,20 +915,33 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, 
     if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
     using Kern = void (*)(const SaMlpArgs, const Tc2Plan, const __nv_bfloat16*, const unsigned char*, const int);
     Kern kern = nullptr;
+    // threads per tile row (see the kernel's comment), TSMDET_MLP_NH=1|2 overrides
+    int nh = dense ? 2 : 1;  // measured (B200, config 2 / config 4): SA L1/L2/L3 48/36/50 us vs 74/48/60, FP MLP 285 vs 233 us
+    if (const char* e = tsm_knob(KNOB_MLP_NH)) nh = atoi(e) == 2 ? 2 : 1;
     if (dense) {
-        kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0> : mlp_tc2_kernel<1, 32, true, 0>;
+        if (nh == 2) kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1> : mlp_tc2_kernel<1, 32, true, 0, 2, 2>;
+        else kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 1, 1> : mlp_tc2_kernel<1, 32, true, 0, 1, 2>;
     } else {
         const int sc = S < 32 ? S : 32;
         const int fchunks = featT ? (pl.cp >> 3) : 0;
         const int pf = fchunks == 0 ? 0 : (fchunks <= 4 ? 4 : (fchunks <= 16 ? 16 : 0));
-#define TC2_PICK(G, P)                                                                                        \
-    (sc == 32 ? mlp_tc2_kernel<G, 32, false, P> : (sc == 16 ? mlp_tc2_kernel<G, 16, false, P> : mlp_tc2_kernel<G, 8, false, P>))
-        if (groups == 2)
-            kern = pf == 16 ? TC2_PICK(2, 16) : (pf == 4 ? TC2_PICK(2, 4) : TC2_PICK(2, 0));
-        else
-            kern = pf == 16 ? TC2_PICK(1, 16) : (pf == 4 ? TC2_PICK(1, 4) : TC2_PICK(1, 0));
+        // MINB: one-group CTAs of 128 threads with narrow rows fit 4 per SM in <= 128 registers; 256-thread ones 2
+#define TC2_PICK(G, P, H, B)                                                                                    \
+    (sc == 32 ? mlp_tc2_kernel<G, 32, false, P, H, B> : (sc == 16 ? mlp_tc2_kernel<G, 16, false, P, H, B> : mlp_tc2_kernel<G, 8, false, P, H, B>))
+        if (nh == 2) {
+            if (groups == 2)
+                kern = pf == 16 ? TC2_PICK(2, 16, 2, 1) : (pf == 4 ? TC2_PICK(2, 4, 2, 1) : TC2_PICK(2, 0, 2, 1));
+            else
+                kern = pf == 16 ? TC2_PICK(1, 16, 2, 2) : (pf == 4 ? TC2_PICK(1, 4, 2, 2) : TC2_PICK(1, 0, 2, 2));
+        } else {
+            if (groups == 2)
+                kern = pf == 16 ? TC2_PICK(2, 16, 1, 1) : (pf == 4 ? TC2_PICK(2, 4, 1, 1) : TC2_PICK(2, 0, 1, 1));
+            else
+                kern = pf == 16 ? TC2_PICK(1, 16, 1, 1) : (pf == 4 ? TC2_PICK(1, 4, 1, 4) : TC2_PICK(1, 0, 1, 4));
+        }
 #undef TC2_PICK
     }
+    const int gthreads = 128 * nh;
     TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     // resident CTAs per SM: what shared memory, registers (a grid of more CTAs than are resident runs a second,
     // partial wave) and the 512 TMEM columns allow
@@ -729,7 +950,7 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, 
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kern);
         if (e == cudaSuccess && fa.numRegs > 0) {
-            const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * T2_THREADS * groups;
+            const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * gthreads * groups;
             const int occ_regs = 65536 / regs_cta;
             if (occ > occ_regs) occ = occ_regs;
         } else {
@@ -750,12 +971,12 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, 
         void* p = nullptr;
         int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes, stream, &p);
         if (rc != TSM_OK) return rc;
-        dim3 pgrid(16, (unsigned)pl.nl);
+        dim3 pgrid(16, (unsigned)pl.nl + 1);
         pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(args, pl, dense, (unsigned char*)p);
         TSM_LAUNCH_CHECK();
         packed = (const unsigned char*)p;
     }
-    kern<<<(unsigned)grid, T2_THREADS * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    kern<<<(unsigned)grid, gthreads * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }
