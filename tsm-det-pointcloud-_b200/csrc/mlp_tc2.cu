@@ -411,12 +411,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     };
     auto wait_mma = [&]() {
         const uint32_t bar = smem_u32(&mma_bar);
-        // Probe with test_wait first: try_wait suspends the thread, and its wake-up added ~150 cycles to every layer of
-        // every tile (phase clocks, -DMLP_PROF; the three SA kernels ran 7 % faster).  A phase that has not completed
-        // after a few thousand probes goes to the suspending wait with the watchdog.
-        bool done = false;
-        for (int probes = 0; probes < 4096 && !(done = mbar_test_wait_cta(bar, phase)); ++probes) {}
-        if (!done && !mbar_try_wait_cta(bar, phase)) {
+        if (!mbar_try_wait_cta(bar, phase)) {  // try_wait suspends the thread for a hardware time slice per call
             const long long t0 = clock64();
             unsigned spins = 0;
             while (!mbar_try_wait_cta(bar, phase))
