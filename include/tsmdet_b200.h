@@ -131,7 +131,9 @@ int tsmdet_three_interpolate_grad(int b, int c, int n, int m, const float* grad_
  *   w[l]  (cout_l, cin_l) f32 row-major folded weights, bias[l] (cout_l) f32 folded bias
  *   out (B, out_stride_c... ) : written at out[b, out_c0 + co, p] with channel stride M and batch
  *   stride out_ctot*M, so several scales can write into one concatenated tensor.
- * precision: 0 = fp32 FMA (1e-5 parity mode), 1 = bf16 tensor cores (tcgen05), fp32 accumulate. */
+ * precision: 0 = fp32 FMA (1e-5 parity mode), 1 = bf16 tensor cores (tcgen05 kind::f16), 2 = tf32 tensor cores
+ * (tcgen05 kind::tf32: operands rounded to 10 mantissa bits, ~1e-3 relative), fp32 accumulate.  TSMDET_ERR_INVALID
+ * in tf32 mode: the MLP's weights do not fit shared memory as 4-byte operands (e.g. [131,128,128,256]). */
 int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
                           const float* new_xyz, const float* features, const int* idx, const int* idx_cnt,
                           int num_layers, const int* channels, const float* const* weights,
@@ -164,6 +166,18 @@ int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, i
 int tsmdet_pointwise_mlp_packed(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
                                 const int* channels, const void* packed, float* out, int out_ctot, int out_c0,
                                 void* stream);
+/* The same three with the tensor precision spelled out (1 = bf16, 2 = tf32; the un-suffixed forms are precision 1).
+ * In tf32 mode the weight image holds tf32 operands and features_t / out_t are fp32 rows of round_up(c, 4) channels. */
+int tsmdet_mlp_pack_p(int precision, int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers,
+                      const int* channels, const float* const* weights, const float* const* biases, void* packed,
+                      long long* packed_bytes, void* stream);
+int tsmdet_sa_mlp_maxpool_packed_p(int precision, int b, int n, int m, int nsample, int c_feat, int use_xyz,
+                                   const float* xyz, const float* new_xyz, const float* features, const void* features_t,
+                                   const int* idx, const int* idx_cnt, int num_layers, const int* channels,
+                                   const void* packed, float* out, void* out_t, int out_ctot, int out_c0, void* stream);
+int tsmdet_pointwise_mlp_packed_p(int precision, int b, int n, int c0, int c1, const float* src0, const float* src1,
+                                  int num_layers, const int* channels, const void* packed, float* out, int out_ctot,
+                                  int out_c0, void* stream);
 
 /* ---------------------------------------------------------------- centroid voxelisation ------
  * The tail of the layer-0 branch (pointnet2/pointnet2_batch/pointnet2_modules.py:1323-1355) in one call:

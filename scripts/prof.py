@@ -26,11 +26,12 @@ def main():
     ap.add_argument("op")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     xyz_np, feats_np, boxes_np, scores_np = bench.make_inputs(16, 0)
     xyz, feats = torch.from_numpy(xyz_np).to(dev), torch.from_numpy(feats_np).to(dev)
-    eng = SABackboneNMS(precision="bf16", use_graph=False).to(dev)
+    eng = SABackboneNMS(precision=a.precision, use_graph=False).to(dev)
     _lib.call("tsmdet_fps_configure", 2)
     levels = [(xyz, feats)]
     with torch.no_grad():
@@ -48,14 +49,15 @@ def main():
         fl = layer._folded_layers()[0]
         img = layer._packed_layers(src_f.shape[1], True)[0]
         out = torch.empty((16, fl[-1][0].shape[0], new_xyz.shape[1]), device=dev)
-        fn = lambda: sa_mlp_maxpool(src_xyz, new_xyz, src_f, bidx, cnt, fl, out, 0, precision="bf16", packed=img)  # noqa: E731
+        assert img is not None, "the tensor kernel does not take this layer at this precision"
+        fn = lambda: sa_mlp_maxpool(src_xyz, new_xyz, src_f, bidx, cnt, fl, out, 0, precision=a.precision, packed=img)  # noqa: E731
     elif a.op == "fp":
         import synth
         x = torch.from_numpy(synth.cloud_uniform(8, 65536, 7, synth.WAYMO_RANGE)).to(dev)
         nx = gather_xyz(x, pu.farthest_point_sample(x, 16384))
         f2, kf = torch.rand((8, 2, 65536), device=dev), torch.rand((8, 128, 16384), device=dev)
         torch.manual_seed(0)
-        fp = PointnetFPModule(mlp=[130, 128, 128], precision="bf16").to(dev).eval()
+        fp = PointnetFPModule(mlp=[130, 128, 128], precision=a.precision).to(dev).eval()
         fn = lambda: fp(x, nx, f2, kf)  # noqa: E731
     elif a.op == "fps":
         fn = lambda: pu.farthest_point_sample(xyz, 4096)  # noqa: E731

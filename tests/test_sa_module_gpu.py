@@ -73,10 +73,11 @@ CFGS["ns8_two_scales"] = dict(npoint_list=[300], sample_range_list=[[0, None]], 
 
 
 @pytest.mark.parametrize("name", list(CFGS))
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_v1"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_v1", "tf32"])
 def test_fused_sa_matches_eager(name, precision, monkeypatch):
-    """fp32 FMA kernel, second-generation tcgen05 kernel (mlp_tc2.cu, where the shape qualifies) and first-generation
-    tcgen05 kernel (TSMDET_MLP_V1=1) against the eager Conv2d/BatchNorm2d/ReLU/max_pool2d stack; bars in parity.py."""
+    """fp32 FMA kernel, second-generation tcgen05 kernel (mlp_tc2.cu, where the shape qualifies; bf16 and tf32 operands)
+    and first-generation tcgen05 kernel (TSMDET_MLP_V1=1) against the eager Conv2d/BatchNorm2d/ReLU/max_pool2d stack;
+    bars in parity.py.  tf32: MLPs whose 4-byte weights do not fit shared memory (kitti_l3) run in the fp32 kernel."""
     import parity
     from tsmdet_b200 import _lib
 
@@ -105,6 +106,10 @@ def test_fused_sa_matches_eager(name, precision, monkeypatch):
     m = parity.err_metrics(got, want)
     print(name, precision, m)
     parity.check_metrics(m, precision, f"{name}")
+    if precision == "tf32":  # the tensor kernel really ran where the plan says it fits
+        imgs = layer._packed_layers(c_in, True)
+        fits = {"kitti_l1": 1, "kitti_l2": 1, "kitti_l3": 0, "ref_layer0": 3, "odd": 0, "ns64": 1, "ns128_wide": 1, "ns8_two_scales": 2}
+        assert sum(i is not None for i in imgs) == fits[name], [None if i is None else i.numel() for i in imgs]
 
 
 def test_empty_ball_outputs_relu_bias_chain():
@@ -147,7 +152,7 @@ def test_fp_module_matches_eager():
     assert float((got - want).abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "tf32"])
 @pytest.mark.parametrize("shape", ["small_odd", "config4"])
 def test_fp_module_fused_mlp_matches_eager(precision, shape):
     """PointnetFPModule with its MLP (and the concatenation feeding it) in ONE kernel -- fp32 FMA or bf16 tcgen05,

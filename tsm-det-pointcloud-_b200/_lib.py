@@ -75,6 +75,11 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "tsmdet_pointwise_mlp_packed": [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p],
+    "tsmdet_mlp_pack_p": [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _i, _pp, _pp, c_void_p, _ll, c_void_p],
+    "tsmdet_sa_mlp_maxpool_packed_p": [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "tsmdet_pointwise_mlp_packed_p": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, _i, c_void_p, c_void_p,
+                                      c_int, c_int, c_void_p],
     "tsmdet_voxel_centroids": [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "tsmdet_centroid_per_voxel": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -136,7 +141,8 @@ KERNELS_PER_CALL = {
     "tsmdet_boxes_overlap_bev": 3, "tsmdet_boxes_iou_bev": 3, "tsmdet_boxes_iou_bev_cpu": 0,
     "tsmdet_fps_plan": 0, "tsmdet_fps_configure": 0, "tsmdet_enable_peer_access": 0, "tsmdet_read_status": 0,
     "tsmdet_reload_options": 0, "tsmdet_scratch_stats": 0, "tsmdet_scratch_trim": 0, "tsmdet_ball_query": 3, "tsmdet_ball_query_dilated": 3, "tsmdet_sa_mlp_maxpool": 3, "tsmdet_pointwise_mlp": 2, "tsmdet_sa_mlp_maxpool_packed": 2,
-    "tsmdet_pointwise_mlp_packed": 1, "tsmdet_mlp_pack": 1, "tsmdet_voxel_centroids": 2, "tsmdet_centroid_per_voxel": 2, "tsmdet_voxel2pinds": 2,
+    "tsmdet_pointwise_mlp_packed": 1, "tsmdet_mlp_pack": 1, "tsmdet_sa_mlp_maxpool_packed_p": 2, "tsmdet_pointwise_mlp_packed_p": 1,
+    "tsmdet_mlp_pack_p": 1, "tsmdet_voxel_centroids": 2, "tsmdet_centroid_per_voxel": 2, "tsmdet_voxel2pinds": 2,
 }
 launch_count = 0
 

@@ -58,7 +58,8 @@ constexpr int T2_MAX_LAYERS = 4;
 
 struct Tc2Plan {
     int nl;
-    int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of 16), without the bias step
+    int eb;                    // bytes per operand element: 2 = bf16 (kind::f16), 4 = tf32 (kind::tf32)
+    int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of a K step: 16 bf16 / 8 tf32), without the bias step
     int Npad[T2_MAX_LAYERS];   // rows of layer l's weight image: cout padded to 16 (last layer: to 128)
     int w_off[T2_MAX_LAYERS];  // byte offset of layer l's weights (non-last layers: K + 16 input rows, the last 16 = bias step)
     int b_off;                 // byte offset of the LAST layer's bias (fp32; added after the pool)
@@ -81,43 +82,46 @@ struct Tc2Plan {
 __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, const Tc2Plan pl, const int dense,
                                                             unsigned char* __restrict__ packed) {
     const int l = blockIdx.y;
+    const int epc = 16 / pl.eb, ks = 2 * epc;  // elements per 16-byte chunk, per K step
+    auto put = [&](unsigned char* base, size_t e, float v) {
+        if (pl.eb == 2) reinterpret_cast<__nv_bfloat16*>(base)[e] = __float2bfloat16_rn(v);
+        else reinterpret_cast<uint32_t*>(base)[e] = to_tf32(v);
+    };
+    auto rnd = [&](float v) { return pl.eb == 2 ? __bfloat162float(__float2bfloat16_rn(v)) : __uint_as_float(to_tf32(v)); };
     if (l == pl.nl) {
-        __nv_bfloat16* ones = reinterpret_cast<__nv_bfloat16*>(packed + pl.ones_off);
-        for (int e = blockIdx.x * 256 + threadIdx.x; e < 2 * T2_ROWS * 8; e += gridDim.x * 256)
-            ones[e] = __float2bfloat16_rn((e < T2_ROWS * 8 && (e & 7) < 2) ? 1.f : 0.f);
+        for (int e = blockIdx.x * 256 + threadIdx.x; e < 2 * T2_ROWS * epc; e += gridDim.x * 256)
+            put(packed + pl.ones_off, e, (e < T2_ROWS * epc && (e % epc) < 2) ? 1.f : 0.f);
         const int Np = pl.Npad[pl.nl - 1], cout = a.ch[pl.nl];
         float* bs = reinterpret_cast<float*>(packed + pl.b_off);
         for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[pl.nl - 1] + e) : 0.f;
         return;
     }
     const int K = pl.K[l], Np = pl.Npad[l];
-    const int Kb = K + (l + 1 < pl.nl ? 16 : 0);  // + the bias step
+    const int Kb = K + (l + 1 < pl.nl ? ks : 0);  // + the bias step
     const int cin = a.ch[l], cout = a.ch[l + 1];
-    __nv_bfloat16* ws = reinterpret_cast<__nv_bfloat16*>(packed + pl.w_off[l]);
     const float* __restrict__ W = a.w[l];
     for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * Kb; e += gridDim.x * 256) {
         const int k = e / Np, n = e - k * Np;  // consecutive threads -> consecutive n: 16-byte-strided writes
-        __nv_bfloat16 o = __float2bfloat16_rn(0.f);
+        float o = 0.f;
         if (n < cout) {
             if (k >= K) {
                 const float b = __ldg(a.bias[l] + n);
-                const __nv_bfloat16 hi = __float2bfloat16_rn(b);
-                if (k == K) o = hi;
-                else if (k == K + 1) o = __float2bfloat16_rn(b - __bfloat162float(hi));
+                if (k == K) o = rnd(b);
+                else if (k == K + 1) o = b - rnd(b);
             } else {
                 int src = -1;
                 if (l == 0 && !dense) {
                     if (k < a.c_feat)
                         src = (a.use_xyz ? 3 : 0) + k;
-                    else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * 8 && k < pl.xyz_chunk * 8 + 3)
-                        src = k - pl.xyz_chunk * 8;
+                    else if (pl.xyz_chunk >= 0 && k >= pl.xyz_chunk * epc && k < pl.xyz_chunk * epc + 3)
+                        src = k - pl.xyz_chunk * epc;
                 } else if (k < cin) {
                     src = k;
                 }
-                if (src >= 0) o = __float2bfloat16_rn(__ldg(W + (size_t)n * cin + src));
+                if (src >= 0) o = __ldg(W + (size_t)n * cin + src);
             }
         }
-        ws[(size_t)(k >> 3) * (Np * 8) + n * 8 + (k & 7)] = o;
+        put(packed + pl.w_off[l], (size_t)(k / epc) * (Np * epc) + n * epc + (k % epc), o);
     }
 }
 
@@ -126,52 +130,66 @@ __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, c
 // output rows of the tile are ONE contiguous run of 64 * Cp bf16) -- the first version wrote 16-byte pieces 2*Cp bytes
 // apart and needed 14 us for the 8 MB of SA layer 3; HBM-bound it is ~2 us.
 constexpr int TR_PTS = 64;
-__global__ void __launch_bounds__(256) transpose2_bf16_kernel(int c, int cp, int n, const float* __restrict__ f,
-                                                              __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __nv_bfloat16 tr_tile[];  // [TR_PTS][cp + 2] (odd word stride: conflict-free column writes)
+template <typename OutT>  // __nv_bfloat16, or float holding tf32-rounded values
+__global__ void __launch_bounds__(256) transpose2_kernel(int c, int cp, int n, const float* __restrict__ f, OutT* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char tr_raw[];
+    OutT* const tr_tile = reinterpret_cast<OutT*>(tr_raw);  // [TR_PTS][ld] (odd word stride: conflict-free column writes)
     const int b = blockIdx.y;
     const int i0 = blockIdx.x * TR_PTS;
     const int np = min(TR_PTS, n - i0);
-    const int ld = cp + 2;
+    const int ld = cp + (sizeof(OutT) == 2 ? 2 : 1);
     const float* src = f + (size_t)b * c * n + i0;
     for (int e = threadIdx.x; e < cp * TR_PTS; e += 256) {
         const int ch = e / TR_PTS, p = e - ch * TR_PTS;
         float v = 0.f;
         if (ch < c && p < np) v = __ldg(src + (size_t)ch * n + p);
-        tr_tile[p * ld + ch] = __float2bfloat16_rn(v);
+        if constexpr (sizeof(OutT) == 2) tr_tile[p * ld + ch] = __float2bfloat16_rn(v);
+        else tr_tile[p * ld + ch] = __uint_as_float(to_tf32(v));
     }
     __syncthreads();
-    // 4-byte (two-channel) stores, consecutive threads -> consecutive words of the contiguous output run
+    // 4-byte stores, consecutive threads -> consecutive words of the contiguous output run
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((size_t)b * n + i0) * cp);
-    const int wpr = cp >> 1;  // words per output row
+    constexpr int EPW = 4 / (int)sizeof(OutT);  // elements per word
+    const int wpr = cp / EPW;                   // words per output row
     for (int e = threadIdx.x; e < np * wpr; e += 256) {
         const int p = e / wpr, w = e - p * wpr;
-        dst[e] = *reinterpret_cast<const uint32_t*>(tr_tile + p * ld + 2 * w);
+        dst[e] = *reinterpret_cast<const uint32_t*>(tr_tile + p * ld + EPW * w);
     }
 }
 
-// ReLU + bf16 pack of NC accumulator columns of this thread's row -> NC/8 chunks of the next layer's A operand.  (The
-// bias is already in the accumulator: every non-last layer ends with one extra K step against the constant "ones"
-// operand whose weight rows hold bias_hi + bias_lo, so the epilogue has no shared-memory bias loads and no adds.)
-template <int NC>
+// ReLU + operand-type pack of NC accumulator columns of this thread's row -> 16-byte chunks of the next layer's A
+// operand (8 bf16 or 4 tf32 per chunk).  (The bias is already in the accumulator: every non-last layer ends with one
+// extra K step against the constant "ones" operand whose weight rows hold bias_hi + bias_lo, so the epilogue has no
+// shared-memory bias loads and no adds.)
+template <int NC, int EB>
 __device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], unsigned char* dst) {
+    if constexpr (EB == 2) {
 #pragma unroll
-    for (int q = 0; q < NC / 8; ++q) {
-        *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = make_uint4(
-            pack_bf16_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
-            pack_bf16_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-            pack_bf16_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-            pack_bf16_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+        for (int q = 0; q < NC / 8; ++q) {
+            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = make_uint4(
+                pack_bf16_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+                pack_bf16_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                pack_bf16_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                pack_bf16_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NC / 4; ++q) {
+            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) =
+                make_uint4(to_tf32(fmaxf(__uint_as_float(v[4 * q + 0]), 0.f)), to_tf32(fmaxf(__uint_as_float(v[4 * q + 1]), 0.f)),
+                           to_tf32(fmaxf(__uint_as_float(v[4 * q + 2]), 0.f)), to_tf32(fmaxf(__uint_as_float(v[4 * q + 3]), 0.f)));
+        }
     }
 }
 
-// HW accumulator columns starting at TMEM address `taddr` (this thread's lane) -> HW/8 chunk planes starting at dst;
+// HW accumulator columns starting at TMEM address `taddr` (this thread's lane) -> chunk planes starting at dst;
 // compile-time width: straight-line code, two 32-column loads in flight per wait where the width allows
-template <int HW, bool LEAN = false>
+template <int HW, bool LEAN, int EB>
 __device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst) {
+    constexpr int EPC = 16 / EB;  // columns per chunk plane
     if constexpr (LEAN && HW >= 64) {  // 128-register kernels: one 32-column load in flight
 #pragma unroll
-        for (int i = 0; i < HW / 32; ++i) epi_mid<32>(taddr + 32u * i, dst + (size_t)(4 * i) * (T2_ROWS * 16));
+        for (int i = 0; i < HW / 32; ++i) epi_mid<32, false, EB>(taddr + 32u * i, dst + (size_t)(32 * i / EPC) * (T2_ROWS * 16));
         return;
     }
     constexpr int N64 = HW / 64, R64 = HW % 64;
@@ -181,41 +199,43 @@ __device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst) {
         tmem_ld32_nowait(taddr + 64u * i, v0);
         tmem_ld32_nowait(taddr + 64u * i + 32u, v1);
         tmem_wait_ld();
-        epi_mid_store<32>(v0, dst + (size_t)(8 * i) * (T2_ROWS * 16));
-        epi_mid_store<32>(v1, dst + (size_t)(8 * i + 4) * (T2_ROWS * 16));
+        epi_mid_store<32, EB>(v0, dst + (size_t)(64 * i / EPC) * (T2_ROWS * 16));
+        epi_mid_store<32, EB>(v1, dst + (size_t)((64 * i + 32) / EPC) * (T2_ROWS * 16));
     }
     constexpr int c1 = N64 * 64;
     if constexpr (R64 >= 32) {
         uint32_t v0[32];
         tmem_ld32_nowait(taddr + c1, v0);
         tmem_wait_ld();
-        epi_mid_store<32>(v0, dst + (size_t)(c1 / 8) * (T2_ROWS * 16));
+        epi_mid_store<32, EB>(v0, dst + (size_t)(c1 / EPC) * (T2_ROWS * 16));
     }
     constexpr int c2 = c1 + (R64 >= 32 ? 32 : 0);
     if constexpr ((R64 % 32) >= 16) {
         uint32_t v0[16];
         tmem_ld16_nowait(taddr + c2, v0);
         tmem_wait_ld();
-        epi_mid_store<16>(v0, dst + (size_t)(c2 / 8) * (T2_ROWS * 16));
+        epi_mid_store<16, EB>(v0, dst + (size_t)(c2 / EPC) * (T2_ROWS * 16));
     }
     constexpr int c3 = c2 + ((R64 % 32) >= 16 ? 16 : 0);
     if constexpr ((R64 % 16) >= 8) {
         uint32_t v0[8];
         tmem_ld8_nowait(taddr + c3, v0);
         tmem_wait_ld();
-        epi_mid_store<8>(v0, dst + (size_t)(c3 / 8) * (T2_ROWS * 16));
+        epi_mid_store<8, EB>(v0, dst + (size_t)(c3 / EPC) * (T2_ROWS * 16));
     }
 }
 
 // any width that is a multiple of 8 (unusual channel counts)
+template <int EB>
 __device__ __forceinline__ void epi_mid_rt(int hw, uint32_t taddr, unsigned char* dst) {
+    constexpr int EPC = 16 / EB;
     int c = 0;
-    for (; c + 32 <= hw; c += 32) epi_mid<32>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
+    for (; c + 32 <= hw; c += 32) epi_mid<32, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
     if (c + 16 <= hw) {
-        epi_mid<16>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
+        epi_mid<16, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
         c += 16;
     }
-    if (c + 8 <= hw) epi_mid<8>(taddr + (uint32_t)c, dst + (size_t)(c >> 3) * (T2_ROWS * 16));
+    if (c + 8 <= hw) epi_mid<8, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
 }
 
 // max over W consecutive registers starting at v[O] (W = 8, 16 or 32), FMNMX3 tree
@@ -239,10 +259,13 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
 // channels, 16: <= 128 channels; half of them per thread); 0: rows of <= 4 channels read from the fp32 planes (a handful
 // of registers, same one-tile-ahead schedule), or -- wider than 128 channels -- cp.async into the operand buffer behind
 // the last MMA.  MINB: CTAs per SM the register allocation must allow.
-template <int GROUPS, int SC, bool DENSE, int PF, int NH, int MINB>
+// EB: bytes per operand element -- 2: bf16 operands (kind::f16), 4: tf32 operands (kind::tf32, fp32 bit patterns rounded
+// to 10 mantissa bits; twice the shared memory and half the tensor rate, ~8x tighter than bf16).
+template <int GROUPS, int SC, bool DENSE, int PF, int NH, int MINB, int EB>
 __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
-                   const __nv_bfloat16* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
+                   const unsigned char* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
+    constexpr int EPC = 16 / EB;  // operand elements per 16-byte chunk
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
@@ -303,13 +326,17 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     const uint32_t d_tmem_u = __shfl_sync(FULL, d_tmem, 0);
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1 (bit 46)
     auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16); };
+    auto umma = [](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+        if constexpr (EB == 2) umma_bf16(d, ad, bd, idesc, acc);
+        else umma_tf32(d, ad, bd, idesc, acc);
+    };
     const uint32_t t_lane = d_tmem + ((uint32_t)(row & ~31) << 16);  // this warp's 32 TMEM lanes
     const uint32_t a_smem = smem_u32(smem + pl.a_off + grp * pl.a_bytes);
     unsigned char* const a_ptr = smem + pl.a_off + grp * pl.a_bytes;
     unsigned char* const a_row = a_ptr + row * 16;  // this thread's row inside every 16-byte chunk plane
     uint32_t phase = 0;
     const int cout_last = a.ch[nl];
-    const int nchunk0 = pl.K[0] >> 3;
+    const int nchunk0 = pl.K[0] / EPC;
     const int tile0 = blockIdx.x * GROUPS + grp, tile_step = gridDim.x * GROUPS;
 
     // SA mode: the neighbour index and the hit count of this thread's row are LOADED one tile ahead and only looked at
@@ -365,16 +392,16 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                         if (k < a.c_feat) pend_f[k] = __ldg(a.features + ((size_t)b * a.c_feat + k) * a.n + id);
                 }
             } else if constexpr (PF > 0) {
-                const int fchunks = pl.cp >> 3;
-                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
+                const int fchunks = pl.cp / EPC;
+                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp * EB);
 #pragma unroll
                 for (int j = 0; j < PFH; ++j) {
                     pf_row[j] = make_uint4(0u, 0u, 0u, 0u);
                     if (live && NH * j + h < fchunks) pf_row[j] = __ldg(frow + NH * j + h);
                 }
             } else if (featT != nullptr) {
-                const int fchunks = pl.cp >> 3;
-                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp);
+                const int fchunks = pl.cp / EPC;
+                const uint4* frow = reinterpret_cast<const uint4*>(featT + prow * pl.cp * EB);
                 const int nbytes = live ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled, nothing is read
                 for (int kc = h; kc < fchunks; kc += NH)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_row_s + (uint32_t)kc * (T2_ROWS * 16)),
@@ -386,7 +413,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     };
     auto store_row = [&]() {
         if constexpr (!DENSE) {
-            const int fchunks = (planar || featT == nullptr) ? 0 : (pl.cp >> 3);
+            const int fchunks = (planar || featT == nullptr) ? 0 : (pl.cp / EPC);
             if constexpr (PF > 0) {
 #pragma unroll
                 for (int j = 0; j < PFH; ++j)
@@ -397,11 +424,21 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (pend_live) {
                     if (kc == pl.xyz_chunk) {
-                        v.x = pack_bf16(__fsub_rn(pend_p[0], pend_q[0]), __fsub_rn(pend_p[1], pend_q[1]));
-                        v.y = pack_bf16(__fsub_rn(pend_p[2], pend_q[2]), 0.f);
+                        const float dx = __fsub_rn(pend_p[0], pend_q[0]), dy = __fsub_rn(pend_p[1], pend_q[1]), dz = __fsub_rn(pend_p[2], pend_q[2]);
+                        if constexpr (EB == 2) {
+                            v.x = pack_bf16(dx, dy);
+                            v.y = pack_bf16(dz, 0.f);
+                        } else {
+                            v = make_uint4(to_tf32(dx), to_tf32(dy), to_tf32(dz), 0u);
+                        }
                     } else if (planar && kc == 0) {
-                        v.x = pack_bf16(pend_f[0], a.c_feat > 1 ? pend_f[1] : 0.f);
-                        v.y = pack_bf16(a.c_feat > 2 ? pend_f[2] : 0.f, a.c_feat > 3 ? pend_f[3] : 0.f);
+                        const float f1 = a.c_feat > 1 ? pend_f[1] : 0.f, f2 = a.c_feat > 2 ? pend_f[2] : 0.f, f3 = a.c_feat > 3 ? pend_f[3] : 0.f;
+                        if constexpr (EB == 2) {
+                            v.x = pack_bf16(pend_f[0], f1);
+                            v.y = pack_bf16(f2, f3);
+                        } else {
+                            v = make_uint4(to_tf32(pend_f[0]), to_tf32(f1), to_tf32(f2), to_tf32(f3));
+                        }
                     }
                 }
                 *reinterpret_cast<uint4*>(a_row + (size_t)kc * (T2_ROWS * 16)) = v;
@@ -445,25 +482,29 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             const float* s0 = a.features + (size_t)b * a.c_feat * a.n + i;
             const float* s1 = a.src1 ? a.src1 + (size_t)b * a.c1 * a.n + i : nullptr;
             const int ctot = a.c_feat + a.c1;
-            for (int kc0 = 4 * h; kc0 < nchunk0; kc0 += 4 * NH) {
+            constexpr int CPI = 32 / EPC;  // chunks per 32-channel block
+            for (int kc0 = CPI * h; kc0 < nchunk0; kc0 += CPI * NH) {
                 float x[32];
 #pragma unroll
                 for (int u = 0; u < 32; ++u) {
-                    const int c = kc0 * 8 + u;
+                    const int c = kc0 * EPC + u;
                     x[u] = 0.f;
                     if (rv && c < ctot) x[u] = c < a.c_feat ? __ldg(s0 + (size_t)c * a.n) : __ldg(s1 + (size_t)(c - a.c_feat) * a.n);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (kc0 + u < nchunk0)
-                        *reinterpret_cast<uint4*>(a_row + (size_t)(kc0 + u) * (T2_ROWS * 16)) =
-                            make_uint4(pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
-                                       pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
+                for (int u = 0; u < CPI; ++u) {
+                    if (kc0 + u < nchunk0) {
+                        uint4 v;
+                        if constexpr (EB == 2)
+                            v = make_uint4(pack_bf16(x[8 * u], x[8 * u + 1]), pack_bf16(x[8 * u + 2], x[8 * u + 3]),
+                                           pack_bf16(x[8 * u + 4], x[8 * u + 5]), pack_bf16(x[8 * u + 6], x[8 * u + 7]));
+                        else
+                            v = make_uint4(to_tf32(x[4 * u]), to_tf32(x[4 * u + 1]), to_tf32(x[4 * u + 2]), to_tf32(x[4 * u + 3]));
+                        *reinterpret_cast<uint4*>(a_row + (size_t)(kc0 + u) * (T2_ROWS * 16)) = v;
+                    }
                 }
             }
         }
-        // generic-proxy writes of the operand -> visible to the tensor core (async proxy); also orders the previous
-        // tile's tcgen05.ld's (every thread fenced them) before this tile's first MMA
         MPROF(0);  // operand build
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -485,17 +526,17 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                 const uint32_t a_lo = desc_lo(sbase + (uint32_t)pl.a_off + grp_u * (uint32_t)pl.a_bytes, T2_ROWS * 16);  // LBO = 128 rows x 16 B
                 const uint32_t o_lo = desc_lo(sbase + (uint32_t)pl.ones_off, T2_ROWS * 16);
                 const uint32_t w_lo = desc_lo(sbase + (uint32_t)pl.w_off[l], (uint32_t)Np * 16);  // LBO = Npad rows x 16 B
-                const uint32_t idesc = instr_desc_bf16_m128(Np), wstep = (2u * (uint32_t)Np * 16u) >> 4;
+                const uint32_t idesc = EB == 2 ? instr_desc_bf16_m128(Np) : instr_desc_tf32_m128(Np), wstep = (2u * (uint32_t)Np * 16u) >> 4;
                 constexpr uint32_t a_hi = DESC_HI, o_hi = DESC_HI, w_hi = DESC_HI;
-                const int nk = pl.K[l] >> 4;
+                const int nk = pl.K[l] / (2 * EPC);
                 if (elect_one()) {
                     uint32_t ad = a_lo, wd = w_lo;
                     for (int kk = 0; kk < nk; ++kk) {
-                        umma_bf16(d_tmem_u, desc64(ad, a_hi), desc64(wd, w_hi), idesc, kk > 0 ? 1u : 0u);
+                        umma(d_tmem_u, desc64(ad, a_hi), desc64(wd, w_hi), idesc, kk > 0 ? 1u : 0u);
                         ad += (2u * T2_ROWS * 16u) >> 4;
                         wd += wstep;
                     }
-                    umma_bf16(d_tmem_u, desc64(o_lo, o_hi), desc64(wd, w_hi), idesc, 1u);
+                    umma(d_tmem_u, desc64(o_lo, o_hi), desc64(wd, w_hi), idesc, 1u);
                     umma_commit(smem_u32(&mma_bar));
                 }
                 __syncwarp();
@@ -508,15 +549,15 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             // ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = (row, column part h)
             const int hw = Np / NH;
             const uint32_t ta = t_lane + (uint32_t)(h * hw);
-            unsigned char* const dst = a_row + (size_t)((h * hw) >> 3) * (T2_ROWS * 16);
+            unsigned char* const dst = a_row + (size_t)((h * hw) / EPC) * (T2_ROWS * 16);
             switch (hw) {
-                case 8: epi_mid<8>(ta, dst); break;
-                case 16: epi_mid<16>(ta, dst); break;
-                case 32: epi_mid<32>(ta, dst); break;
-                case 64: epi_mid<64, LEAN>(ta, dst); break;
-                case 128: epi_mid<128, LEAN>(ta, dst); break;
-                case 256: epi_mid<256, LEAN>(ta, dst); break;
-                default: epi_mid_rt(hw, ta, dst); break;
+                case 8: epi_mid<8, false, EB>(ta, dst); break;
+                case 16: epi_mid<16, false, EB>(ta, dst); break;
+                case 32: epi_mid<32, false, EB>(ta, dst); break;
+                case 64: epi_mid<64, LEAN, EB>(ta, dst); break;
+                case 128: epi_mid<128, LEAN, EB>(ta, dst); break;
+                case 256: epi_mid<256, LEAN, EB>(ta, dst); break;
+                default: epi_mid_rt<EB>(hw, ta, dst); break;
             }
             MPROF(3);  // mid-layer epilogue
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -534,14 +575,14 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                 const uint32_t sbase = smem_u32(smem);
                 const uint32_t a_lo = desc_lo(sbase + (uint32_t)pl.a_off + grp_u * (uint32_t)pl.a_bytes, T2_ROWS * 16);
                 const uint32_t w_lo = desc_lo(sbase + (uint32_t)pl.w_off[l], (uint32_t)pl.Npad[l] * 16);
-                const uint32_t idesc = instr_desc_bf16_m128(T2_ROWS), wstep = (2u * (uint32_t)pl.Npad[l] * 16u) >> 4;
+                const uint32_t idesc = EB == 2 ? instr_desc_bf16_m128(T2_ROWS) : instr_desc_tf32_m128(T2_ROWS), wstep = (2u * (uint32_t)pl.Npad[l] * 16u) >> 4;
                 constexpr uint32_t a_hi = DESC_HI, w_hi = DESC_HI;
-                const int nk = pl.K[l] >> 4;
+                const int nk = pl.K[l] / (2 * EPC);
                 if (elect_one()) {
                     for (int mb = 0; mb < pl.mb; ++mb) {
                         uint32_t ad = a_lo, wd = w_lo + (uint32_t)((mb * T2_ROWS * 16) >> 4);
                         for (int kk = 0; kk < nk; ++kk) {
-                            umma_bf16(d_tmem_u + (uint32_t)(mb * T2_ROWS), desc64(wd, w_hi), desc64(ad, a_hi), idesc, kk > 0 ? 1u : 0u);
+                            umma(d_tmem_u + (uint32_t)(mb * T2_ROWS), desc64(wd, w_hi), desc64(ad, a_hi), idesc, kk > 0 ? 1u : 0u);
                             ad += (2u * T2_ROWS * 16u) >> 4;
                             wd += wstep;
                         }
@@ -575,7 +616,12 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                 const unsigned cbase = (unsigned)tile * (unsigned)cpt;
                 const unsigned ctot = (unsigned)(a.total_rows >> log2s);
                 const unsigned b0 = cbase / (unsigned)M, p0 = cbase - b0 * (unsigned)M;
-                const int cpo = (cout_last + 7) & ~7;  // width of the bf16 row copy (zero padded)
+                const int cpo = (cout_last + EPC - 1) / EPC * EPC;  // width of the operand-type row copy (zero padded)
+                using RowT = std::conditional_t<EB == 2, __nv_bfloat16, float>;
+                auto to_row = [](float y) -> RowT {
+                    if constexpr (EB == 2) return __float2bfloat16_rn(y);
+                    else return __uint_as_float(to_tf32(y));
+                };
                 const bool full = pl.whole_tiles && cbase + (unsigned)cpt <= ctot;  // every centre valid, one frame
                 float part0 = 0.f, part1 = 0.f;  // NH == 2, S == 128: this half's maximum per channel block
                 auto pool = [&](auto full_tag) {
@@ -585,7 +631,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                         const float bias = bs[ch];
                         const bool ch_ok = ch < cout_last;
                         float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
-                        __nv_bfloat16* const tbase = reinterpret_cast<__nv_bfloat16*>(a.out_t) + (size_t)cbase * cpo + ch;
+                        RowT* const tbase = reinterpret_cast<RowT*>(a.out_t) + (size_t)cbase * cpo + ch;
                         const bool o_ok = a.out != nullptr && ch_ok;
                         const bool t_ok = a.out_t != nullptr && ch < cpo;
                         auto emit = [&](int ci, float m) {
@@ -593,7 +639,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                             if constexpr (FULL) {
                                 if (o_ok) obase[ci] = y;
                                 // (B,M,cpo) bf16 rows for the next layer's gather: a warp writes 32 consecutive channels
-                                if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
+                                if (t_ok) tbase[(size_t)ci * cpo] = to_row(y);
                             } else {
                                 const unsigned cg = cbase + (unsigned)ci;
                                 if (cg < ctot) {
@@ -601,7 +647,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                                         const unsigned b2 = cg / (unsigned)M, p2 = cg - b2 * (unsigned)M;
                                         a.out[((size_t)b2 * a.out_ctot + a.out_c0 + ch) * M + p2] = y;
                                     }
-                                    if (t_ok) tbase[(size_t)ci * cpo] = __float2bfloat16_rn(y);
+                                    if (t_ok) tbase[(size_t)ci * cpo] = to_row(y);
                                 }
                             }
                         };
@@ -698,7 +744,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                                 if (cbase < ctot) {  // one centre per tile
                                     if (a.out != nullptr && ch_ok) a.out[((size_t)b0 * a.out_ctot + a.out_c0 + ch) * M + p0] = y;
                                     if (a.out_t != nullptr && ch < cpo)
-                                        reinterpret_cast<__nv_bfloat16*>(a.out_t)[(size_t)cbase * cpo + ch] = __float2bfloat16_rn(y);
+                                        reinterpret_cast<RowT*>(a.out_t)[(size_t)cbase * cpo + ch] = to_row(y);
                                 }
                             }
                         }
@@ -793,9 +839,11 @@ static int round_up2(int v, int m) { return (v + m - 1) / m * m; }
 
 // Shapes this kernel takes and the shared-memory / TMEM plan for them.  TSM_ERR_INVALID otherwise (the caller falls
 // back to sa_mlp_tc.cu / the fp32 kernel).
-static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::Tc2Plan* out, int* groups_out) {
+static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int eb, tsm::Tc2Plan* out, int* groups_out) {
     using namespace tsm;
     const int S = a.s;
+    if (eb != 2 && eb != 4) return TSM_ERR_INVALID;
+    const int epc = 16 / eb, ks = 2 * epc;  // operand elements per 16-byte chunk / per K step
     if (a.num_layers < 1 || a.num_layers > T2_MAX_LAYERS) return TSM_ERR_INVALID;
     if (!dense) {
         if (S < 8 || S > T2_ROWS || (S & (S - 1)) != 0) return TSM_ERR_INVALID;  // whole centres per tile, SC in {8,16,32}
@@ -805,14 +853,15 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
     }
     Tc2Plan pl;
     pl.nl = a.num_layers;
+    pl.eb = eb;
     if (!dense) {
-        pl.cp = round_up2(a.c_feat, 8);
-        pl.xyz_chunk = a.use_xyz ? (pl.cp >> 3) : -1;
-        pl.K[0] = round_up2(pl.cp + (a.use_xyz ? 8 : 0), 16);
+        pl.cp = round_up2(a.c_feat, epc);
+        pl.xyz_chunk = a.use_xyz ? (pl.cp / epc) : -1;
+        pl.K[0] = round_up2(pl.cp + (a.use_xyz ? epc : 0), ks);
     } else {
         pl.cp = 0;
         pl.xyz_chunk = -1;
-        pl.K[0] = round_up2(a.c_feat + a.c1, 16);
+        pl.K[0] = round_up2(a.c_feat + a.c1, ks);
     }
     int off = 0, kmax = pl.K[0], nmid = 0;
     for (int l = 0; l < pl.nl; ++l) {
@@ -823,7 +872,7 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
         kmax = pl.K[l] > kmax ? pl.K[l] : kmax;
         if (!last) nmid = pl.Npad[l] > nmid ? pl.Npad[l] : nmid;
         pl.w_off[l] = off;
-        off += pl.Npad[l] * (pl.K[l] + (last ? 0 : 16)) * 2;
+        off += pl.Npad[l] * (pl.K[l] + (last ? 0 : ks)) * eb;
     }
     for (int l = pl.nl; l < T2_MAX_LAYERS; ++l) pl.K[l] = pl.Npad[l] = pl.w_off[l] = 0;
     if (kmax > 512) return TSM_ERR_INVALID;
@@ -836,7 +885,7 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
     pl.packed_bytes = off;  // multiple of 32
     off = round_up2(off, 128);
     pl.a_off = off;
-    pl.a_bytes = round_up2(T2_ROWS * kmax * 2, 128);
+    pl.a_bytes = round_up2(T2_ROWS * kmax * eb, 128);
     const bool xch = !dense && S == T2_ROWS;
     auto smem_for = [&](int groups) { return off + groups * pl.a_bytes + (xch ? groups * 2 * T2_ROWS * 4 : 0); };
     if (smem_for(1) > 227 * 1024 - 64) return TSM_ERR_INVALID;
@@ -860,11 +909,11 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, tsm::
 // The kernel's weight image (bf16 UMMA core matrices incl. the bias steps, the last fp32 bias, the ones operand) for an
 // MLP: *bytes = its size; packed != nullptr: build it there (device memory, >= *bytes).  Callers with constant weights
 // build it ONCE and pass it to every call (the packing kernel costs 5-8 us, comparable to a whole SA layer's tensor work).
-int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, long long* bytes, cudaStream_t stream) {
+int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, int eb, unsigned char* packed, long long* bytes, cudaStream_t stream) {
     using namespace tsm;
     Tc2Plan pl;
     int groups = 1;
-    int rc = tc2_plan(a, 1, dense, &pl, &groups);
+    int rc = tc2_plan(a, 1, dense, eb, &pl, &groups);
     if (rc != TSM_OK) return rc;
     if (bytes) *bytes = pl.packed_bytes;
     if (packed) {
@@ -879,63 +928,71 @@ int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, 
 
 // dense != 0: point-wise MLP over (B, c_feat + c1, n) (a.features / a.src1), a.m == a.n, a.s == 1, no idx.
 // prepacked: the image built by tsm_mlp_tc2_pack for the same shapes (nullptr: packed here, per call).
-int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, const unsigned char* prepacked) {
+// eb: 2 = bf16 operands, 4 = tf32 operands (a.feat_t / a.out_t rows and the weight image are of that type).
+int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, int eb, cudaStream_t stream, const unsigned char* prepacked) {
     using namespace tsm;
     const int S = a.s;
     Tc2Plan pl;
     int groups = 1;
     {
-        const int rc = tc2_plan(a, (long long)b * a.m, dense, &pl, &groups);
+        const int rc = tc2_plan(a, (long long)b * a.m, dense, eb, &pl, &groups);
         if (rc != TSM_OK) return rc;
     }
+    const int epc = 16 / eb;
     // feature rows: <= 4 channels are read straight from the (B,C,N) fp32 planes by the gather; wider inputs go
     // through a bf16 (B,N,Cp) transpose so that a gathered row is one contiguous run of 16-byte chunks
-    __nv_bfloat16* featT = nullptr;
+    const unsigned char* featT = nullptr;
     if (!dense && a.c_feat > 0 && a.feat_t) {
-        featT = (__nv_bfloat16*)a.feat_t;  // rows already in the gather's layout (a previous layer's out_t)
+        featT = (const unsigned char*)a.feat_t;  // rows already in the gather's layout (a previous layer's out_t)
     } else if (!dense && a.c_feat > 4) {
         void* p = nullptr;
-        const size_t bytes = (size_t)b * a.n * pl.cp * sizeof(__nv_bfloat16);
+        const size_t bytes = (size_t)b * a.n * pl.cp * eb;
         int rc = tsm_scratch_get(1, bytes, stream, &p);
         if (rc != TSM_OK) return rc;
-        featT = (__nv_bfloat16*)p;
+        featT = (const unsigned char*)p;
         dim3 grid((unsigned)divup(a.n, TR_PTS), (unsigned)b);
-        const size_t tsm_bytes = (size_t)TR_PTS * (pl.cp + 2) * sizeof(__nv_bfloat16);
-        if (tsm_bytes > 48 * 1024)
-            TSM_CUDA_TRY(cudaFuncSetAttribute(transpose2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_bytes));
-        transpose2_bf16_kernel<<<grid, 256, tsm_bytes, stream>>>(a.c_feat, pl.cp, a.n, a.features, featT);
+        const size_t tsm_bytes = (size_t)TR_PTS * (pl.cp + (eb == 2 ? 2 : 1)) * eb;
+        if (eb == 2) {
+            if (tsm_bytes > 48 * 1024)
+                TSM_CUDA_TRY(cudaFuncSetAttribute(transpose2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_bytes));
+            transpose2_kernel<__nv_bfloat16><<<grid, 256, tsm_bytes, stream>>>(a.c_feat, pl.cp, a.n, a.features, (__nv_bfloat16*)p);
+        } else {
+            if (tsm_bytes > 48 * 1024)
+                TSM_CUDA_TRY(cudaFuncSetAttribute(transpose2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm_bytes));
+            transpose2_kernel<float><<<grid, 256, tsm_bytes, stream>>>(a.c_feat, pl.cp, a.n, a.features, (float*)p);
+        }
         TSM_LAUNCH_CHECK();
     }
     const long long tiles = (a.total_rows + T2_ROWS - 1) / T2_ROWS;
     if (tiles > 0x7fffffffLL) return TSM_ERR_INVALID;
-    using Kern = void (*)(const SaMlpArgs, const Tc2Plan, const __nv_bfloat16*, const unsigned char*, const int);
+    using Kern = void (*)(const SaMlpArgs, const Tc2Plan, const unsigned char*, const unsigned char*, const int);
     Kern kern = nullptr;
-    // threads per tile row (see the kernel's comment), TSMDET_MLP_NH=1|2 overrides
+    // threads per tile row (see the kernel's comment), TSMDET_MLP_NH=1|2 overrides (bf16 SA scales only)
     int nh = dense ? 2 : 1;  // measured (B200, config 2 / config 4): SA L1/L2/L3 48/36/50 us vs 74/48/60, FP MLP 285 vs 233 us
-    if (const char* e = tsm_knob(KNOB_MLP_NH)) nh = atoi(e) == 2 ? 2 : 1;
-    if (dense) {
-        if (nh == 2) kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1> : mlp_tc2_kernel<1, 32, true, 0, 2, 2>;
-        else kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 1, 1> : mlp_tc2_kernel<1, 32, true, 0, 1, 2>;
-    } else {
-        const int sc = S < 32 ? S : 32;
-        const int fchunks = featT ? (pl.cp >> 3) : 0;
-        const int pf = fchunks == 0 ? 0 : (fchunks <= 4 ? 4 : (fchunks <= 16 ? 16 : 0));
-        // MINB: one-group CTAs of 128 threads with narrow rows fit 4 per SM in <= 128 registers; 256-thread ones 2
-#define TC2_PICK(G, P, H, B)                                                                                    \
-    (sc == 32 ? mlp_tc2_kernel<G, 32, false, P, H, B> : (sc == 16 ? mlp_tc2_kernel<G, 16, false, P, H, B> : mlp_tc2_kernel<G, 8, false, P, H, B>))
-        if (nh == 2) {
-            if (groups == 2)
-                kern = pf == 16 ? TC2_PICK(2, 16, 2, 1) : (pf == 4 ? TC2_PICK(2, 4, 2, 1) : TC2_PICK(2, 0, 2, 1));
-            else
-                kern = pf == 16 ? TC2_PICK(1, 16, 2, 2) : (pf == 4 ? TC2_PICK(1, 4, 2, 2) : TC2_PICK(1, 0, 2, 2));
+    if (const char* e = tsm_knob(KNOB_MLP_NH)) nh = (atoi(e) == 2 && (eb == 2 || dense)) ? 2 : (dense && eb == 4 ? 2 : 1);
+    const int sc = S < 32 ? S : 32;
+    const int fchunks = (!dense && featT) ? (pl.cp / epc) : 0;
+    const int pf = fchunks == 0 ? 0 : (fchunks <= 4 ? 4 : (fchunks <= 16 ? 16 : 0));
+    // MINB: one-group CTAs of 128 threads with narrow rows fit 4 per SM in <= 128 registers; 256-thread ones 2
+#define TC2_PICK(G, P, H, B, E)                                                                                       \
+    (sc == 32 ? mlp_tc2_kernel<G, 32, false, P, H, B, E>                                                              \
+              : (sc == 16 ? mlp_tc2_kernel<G, 16, false, P, H, B, E> : mlp_tc2_kernel<G, 8, false, P, H, B, E>))
+#define TC2_PICK_PF(G, H, B16, B4, E) (pf == 16 ? TC2_PICK(G, 16, H, B16, E) : (pf == 4 ? TC2_PICK(G, 4, H, B4, E) : TC2_PICK(G, 0, H, B4, E)))
+    if (eb == 2) {
+        if (dense) {
+            if (nh == 2) kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1, 2> : mlp_tc2_kernel<1, 32, true, 0, 2, 2, 2>;
+            else kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 1, 1, 2> : mlp_tc2_kernel<1, 32, true, 0, 1, 2, 2>;
+        } else if (nh == 2) {
+            kern = groups == 2 ? TC2_PICK_PF(2, 2, 1, 1, 2) : TC2_PICK_PF(1, 2, 2, 2, 2);
         } else {
-            if (groups == 2)
-                kern = pf == 16 ? TC2_PICK(2, 16, 1, 1) : (pf == 4 ? TC2_PICK(2, 4, 1, 1) : TC2_PICK(2, 0, 1, 1));
-            else
-                kern = pf == 16 ? TC2_PICK(1, 16, 1, 1) : (pf == 4 ? TC2_PICK(1, 4, 1, 4) : TC2_PICK(1, 0, 1, 4));
+            kern = groups == 2 ? TC2_PICK_PF(2, 1, 1, 1, 2) : TC2_PICK_PF(1, 1, 1, 4, 2);
         }
-#undef TC2_PICK
+    } else {  // tf32: one thread per row for SA scales, two for dense MLPs
+        if (dense) kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1, 4> : mlp_tc2_kernel<1, 32, true, 0, 2, 2, 4>;
+        else kern = groups == 2 ? TC2_PICK_PF(2, 1, 1, 1, 4) : TC2_PICK_PF(1, 1, 1, 4, 4);
     }
+#undef TC2_PICK_PF
+#undef TC2_PICK
     const int gthreads = 128 * nh;
     TSM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes));
     // resident CTAs per SM: what shared memory, registers (a grid of more CTAs than are resident runs a second,

@@ -82,11 +82,12 @@ extern "C" int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_fea
         // second-generation kernel (transposed last layer, in-register pooling) where it applies; TSMDET_MLP_V1=1
         // keeps every shape on the first-generation kernel (A/B measurements, tests of both)
         if (!tsm_knob(KNOB_MLP_V1)) {
-            const int rc = tsm_mlp_tc2(a, b, 0, (cudaStream_t)stream);
+            const int rc = tsm_mlp_tc2(a, b, 0, 2, (cudaStream_t)stream);
             if (rc != TSM_ERR_INVALID) return rc;
         }
         return tsm_sa_mlp_tc(a, b, (cudaStream_t)stream);
     }
+    if (precision == 2) return tsm_mlp_tc2(a, b, 0, 4, (cudaStream_t)stream);  // tf32 operands; no other tf32 kernel
     return TSM_ERR_INVALID;
 }
 
@@ -94,7 +95,7 @@ extern "C" int tsmdet_sa_mlp_maxpool(int b, int n, int m, int nsample, int c_fea
 // [1x1 conv (BN folded) + bias + ReLU] x num_layers -- PointnetFPModule.mlp (pointnet2_modules.py:175-176, on the
 // concatenation of the interpolated and the skip features, :171) and aggregation_mlp (:1320-1321).
 //   src0 (B,c0,n), src1 (B,c1,n) | NULL; channels[0] == c0 + c1; out (B,out_ctot,n).
-// precision 0 = fp32 FMA, 1 = bf16 tensor cores (tcgen05, fp32 accumulate).
+// precision 0 = fp32 FMA, 1 = bf16 / 2 = tf32 tensor cores (tcgen05, fp32 accumulate).
 extern "C" int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* src0, const float* src1, int num_layers,
                                     const int* channels, const float* const* weights, const float* const* biases,
                                     float* out, int out_ctot, int out_c0, int precision, void* stream) {
@@ -103,7 +104,7 @@ extern "C" int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* s
     tsm::SaMlpArgs a;
     if (int rc = dense_args(a, b, n, c0, c1, src0, src1, num_layers, channels, weights, biases, out, out_ctot, out_c0)) return rc;
     if (precision == 0) return tsm_sa_mlp_fp32_dense(a, b, (cudaStream_t)stream);
-    if (precision == 1) return tsm_mlp_tc2(a, b, 1, (cudaStream_t)stream);
+    if (precision == 1 || precision == 2) return tsm_mlp_tc2(a, b, 1, precision == 1 ? 2 : 4, (cudaStream_t)stream);
     return TSM_ERR_INVALID;
 }
 
@@ -111,9 +112,10 @@ extern "C" int tsmdet_pointwise_mlp(int b, int n, int c0, int c1, const float* s
 // pass it to the *_packed entry points.  dense = 0: fused SA scale (c1 ignored), 1: point-wise MLP (nsample /
 // use_xyz ignored).  packed == NULL: only *packed_bytes is set.  TSMDET_ERR_INVALID: the tensor path does not take
 // this shape -- use the unpacked entry points (they fall back to the first-generation / fp32 kernels).
-extern "C" int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers, const int* channels,
-                               const float* const* weights, const float* const* biases, void* packed,
-                               long long* packed_bytes, void* stream) {
+extern "C" int tsmdet_mlp_pack_p(int precision, int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers,
+                                 const int* channels, const float* const* weights, const float* const* biases, void* packed,
+                                 long long* packed_bytes, void* stream) {
+    if (precision != 1 && precision != 2) return TSM_ERR_INVALID;
     tsm::SaMlpArgs a;
     int rc;
     if (dense)
@@ -123,17 +125,24 @@ extern "C" int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int u
                      nullptr, nullptr, num_layers, channels, weights, biases, nullptr, 1 << 30, 0);
     if (rc) return rc;
     if (packed && (!weights || !biases)) return TSM_ERR_INVALID;
-    return tsm_mlp_tc2_pack(a, dense, static_cast<unsigned char*>(packed), packed_bytes, (cudaStream_t)stream);
+    return tsm_mlp_tc2_pack(a, dense, precision == 1 ? 2 : 4, static_cast<unsigned char*>(packed), packed_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int tsmdet_mlp_pack(int dense, int nsample, int c_feat, int c1, int use_xyz, int num_layers, const int* channels,
+                               const float* const* weights, const float* const* biases, void* packed,
+                               long long* packed_bytes, void* stream) {
+    return tsmdet_mlp_pack_p(1, dense, nsample, c_feat, c1, use_xyz, num_layers, channels, weights, biases, packed, packed_bytes, stream);
 }
 
 // features_t (optional): the features as (B,N,round_up(c_feat,8)) bf16 rows -- then `features` may be NULL and no
 // transpose runs; out_t (optional): a second output, (B,M,round_up(cout,8)) bf16 rows, i.e. the next SA layer's
 // features_t (stacked layers chain through it); out may be NULL when out_t is given.
-extern "C" int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
-                                            const float* new_xyz, const float* features, const void* features_t,
-                                            const int* idx, const int* idx_cnt, int num_layers, const int* channels,
-                                            const void* packed, float* out, void* out_t, int out_ctot, int out_c0,
-                                            void* stream) {
+extern "C" int tsmdet_sa_mlp_maxpool_packed_p(int precision, int b, int n, int m, int nsample, int c_feat, int use_xyz,
+                                              const float* xyz, const float* new_xyz, const float* features,
+                                              const void* features_t, const int* idx, const int* idx_cnt, int num_layers,
+                                              const int* channels, const void* packed, float* out, void* out_t, int out_ctot,
+                                              int out_c0, void* stream) {
+    if (precision != 1 && precision != 2) return TSM_ERR_INVALID;
     if (b <= 0 || m <= 0) return TSM_OK;
     if (!packed || (!out && !out_t)) return TSM_ERR_INVALID;
     tsm::SaMlpArgs a;
@@ -145,15 +154,31 @@ extern "C" int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, in
     a.feat_t = features_t;
     a.out_t = out_t;
     if (c_feat > 0 && !features && !features_t) return TSM_ERR_INVALID;
-    return tsm_mlp_tc2(a, b, 0, (cudaStream_t)stream, static_cast<const unsigned char*>(packed));
+    return tsm_mlp_tc2(a, b, 0, precision == 1 ? 2 : 4, (cudaStream_t)stream, static_cast<const unsigned char*>(packed));
+}
+
+extern "C" int tsmdet_sa_mlp_maxpool_packed(int b, int n, int m, int nsample, int c_feat, int use_xyz, const float* xyz,
+                                            const float* new_xyz, const float* features, const void* features_t,
+                                            const int* idx, const int* idx_cnt, int num_layers, const int* channels,
+                                            const void* packed, float* out, void* out_t, int out_ctot, int out_c0,
+                                            void* stream) {
+    return tsmdet_sa_mlp_maxpool_packed_p(1, b, n, m, nsample, c_feat, use_xyz, xyz, new_xyz, features, features_t, idx, idx_cnt,
+                                          num_layers, channels, packed, out, out_t, out_ctot, out_c0, stream);
+}
+
+extern "C" int tsmdet_pointwise_mlp_packed_p(int precision, int b, int n, int c0, int c1, const float* src0, const float* src1,
+                                             int num_layers, const int* channels, const void* packed, float* out,
+                                             int out_ctot, int out_c0, void* stream) {
+    if (precision != 1 && precision != 2) return TSM_ERR_INVALID;
+    if (b <= 0 || n <= 0) return TSM_OK;
+    if (!src0 || (c1 > 0 && !src1) || !out || !packed) return TSM_ERR_INVALID;
+    tsm::SaMlpArgs a;
+    if (int rc = dense_args(a, b, n, c0, c1, src0, src1, num_layers, channels, nullptr, nullptr, out, out_ctot, out_c0)) return rc;
+    return tsm_mlp_tc2(a, b, 1, precision == 1 ? 2 : 4, (cudaStream_t)stream, static_cast<const unsigned char*>(packed));
 }
 
 extern "C" int tsmdet_pointwise_mlp_packed(int b, int n, int c0, int c1, const float* src0, const float* src1,
                                            int num_layers, const int* channels, const void* packed, float* out,
                                            int out_ctot, int out_c0, void* stream) {
-    if (b <= 0 || n <= 0) return TSM_OK;
-    if (!src0 || (c1 > 0 && !src1) || !out || !packed) return TSM_ERR_INVALID;
-    tsm::SaMlpArgs a;
-    if (int rc = dense_args(a, b, n, c0, c1, src0, src1, num_layers, channels, nullptr, nullptr, out, out_ctot, out_c0)) return rc;
-    return tsm_mlp_tc2(a, b, 1, (cudaStream_t)stream, static_cast<const unsigned char*>(packed));
+    return tsmdet_pointwise_mlp_packed_p(1, b, n, c0, c1, src0, src1, num_layers, channels, packed, out, out_ctot, out_c0, stream);
 }

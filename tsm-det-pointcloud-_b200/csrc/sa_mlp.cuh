@@ -31,7 +31,8 @@ struct SaMlpArgs {
 int tsm_sa_mlp_fp32(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);
 int tsm_sa_mlp_fp32_dense(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);
 int tsm_sa_mlp_tc(const tsm::SaMlpArgs& a, int b, cudaStream_t stream);  // TSM_ERR_INVALID if the shape is unsupported
-// second-generation tcgen05 kernel (mlp_tc2.cu): SA scales with >= 64 output channels and nsample >= 8 (dense == 0),
-// point-wise MLPs over dense (B,C,n) inputs (dense != 0).  TSM_ERR_INVALID if the shape is unsupported.
-int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, cudaStream_t stream, const unsigned char* prepacked = nullptr);
-int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, unsigned char* packed, long long* bytes, cudaStream_t stream);
+// second-generation tcgen05 kernel (mlp_tc2.cu): SA scales with nsample a power of two in 8..128 (dense == 0),
+// point-wise MLPs over dense (B,C,n) inputs (dense != 0); eb = bytes per operand element, 2 = bf16, 4 = tf32.
+// TSM_ERR_INVALID if the shape is unsupported (incl. weights that do not fit shared memory in tf32).
+int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, int eb, cudaStream_t stream, const unsigned char* prepacked = nullptr);
+int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, int eb, unsigned char* packed, long long* bytes, cudaStream_t stream);

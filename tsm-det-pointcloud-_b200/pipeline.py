@@ -35,7 +35,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib, iou3d_nms_utils, pointnet2_utils
-from .pointnet2_modules import gather_xyz, kitti_sa_stack, sa_mlp_maxpool, stage_points
+from .pointnet2_modules import _effective_precision, gather_xyz, kitti_sa_stack, sa_mlp_maxpool, stage_points
 from .sharding import PeerGather, gather_detections, gather_packed, pack_detections
 
 
@@ -213,10 +213,11 @@ class SABackboneNMS(torch.nn.Module):
                 chain = img is not None and not last and imgs[li + 1] is not None
                 out = out_features if last else (None if chain else torch.empty((b, cout, new_xyz.shape[1]),
                                                                               dtype=torch.float32, device=dev))
-                out_t = torch.empty((b, new_xyz.shape[1], (cout + 7) // 8 * 8), dtype=torch.bfloat16,
+                row_dt, row_q = (torch.bfloat16, 8) if layer.precision == "bf16" else (torch.float32, 4)  # tf32: fp32 rows
+                out_t = torch.empty((b, new_xyz.shape[1], (cout + row_q - 1) // row_q * row_q), dtype=row_dt,
                                     device=dev) if chain else None
-                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0, precision=layer.precision, packed=img,
-                               feat_t=cur_t, out_t=out_t)
+                sa_mlp_maxpool(src_xyz, new_xyz, cur_f, bidx, cnt, folded, out, 0,
+                               precision=_effective_precision(layer.precision, img), packed=img, feat_t=cur_t, out_t=out_t)
                 mark(f"mlp{src_xyz.shape[1]}", s_sa)
                 cur_f, cur_t = out, out_t
         # stream C: NMS is independent of the backbone.  (Measured inside the captured graph: letting it run

@@ -19,7 +19,8 @@ Two execution modes give the same numbers within the stated tolerances:
                    Conv2d/BatchNorm2d/ReLU/max_pool2d) -- kept as the behavioural reference;
   ``fused=True``   (eval mode only) BatchNorm folded into the 1x1 convs, one fused kernel per scale
                    (gather + MLP + max-pool, nothing materialised).  ``precision='fp32'`` is the
-                   1e-5 parity mode, ``precision='bf16'`` runs the contraction on tcgen05 tensor cores.
+                   1e-5 parity mode, ``precision='bf16'`` / ``'tf32'`` run the contraction on tcgen05 tensor cores
+                   (kind::f16 / kind::tf32).
 """
 from __future__ import annotations
 
@@ -71,8 +72,13 @@ def fold_conv_bn(seq: nn.Sequential):
     return out
 
 
-def pack_mlp(layers, *, dense: bool, nsample: int = 1, c_feat: int = 0, c1: int = 0, use_xyz: bool = True):
-    """The tensor path's weight image for folded ``layers`` (C ABI ``tsmdet_mlp_pack``): a uint8 CUDA tensor to pass as
+PRECISIONS = {"fp32": 0, "bf16": 1, "tf32": 2}  # C ABI codes; bf16 / tf32 = tcgen05 tensor cores
+
+
+def pack_mlp(layers, *, dense: bool, nsample: int = 1, c_feat: int = 0, c1: int = 0, use_xyz: bool = True,
+             precision: str = "bf16"):
+    """The tensor path's weight image for folded ``layers`` (C ABI ``tsmdet_mlp_pack_p``; ``precision`` 'bf16' or 'tf32' --
+    an image only fits calls of the same precision): a uint8 CUDA tensor to pass as
     ``packed=`` to ``sa_mlp_maxpool`` / ``pointwise_mlp``, or None when the second-generation tcgen05 kernel does not
     take the shape (the unpacked calls then fall back to the first-generation / fp32 kernels).  Build it once per set
     of weights: the packing kernel costs 5-8 us per call, as much as a small layer."""
@@ -86,16 +92,23 @@ def pack_mlp(layers, *, dense: bool, nsample: int = 1, c_feat: int = 0, c1: int 
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
     size = ctypes.c_longlong(0)
     dev = layers[0][0].device
-    args = (int(dense), int(nsample), int(c_feat), int(c1), int(use_xyz), nl, ch_arr, w_arr, b_arr)
+    args = (PRECISIONS[precision], int(dense), int(nsample), int(c_feat), int(c1), int(use_xyz), nl, ch_arr, w_arr, b_arr)
     try:
-        call("tsmdet_mlp_pack", *args, None, ctypes.byref(size), stream_ptr(dev))
+        call("tsmdet_mlp_pack_p", *args, None, ctypes.byref(size), stream_ptr(dev))
     except TsmdetError as e:
         if e.code == 1000001:
             return None
         raise
     packed = torch.empty((int(size.value),), dtype=torch.uint8, device=dev)
-    call("tsmdet_mlp_pack", *args, ptr(packed), ctypes.byref(size), stream_ptr(dev))
+    call("tsmdet_mlp_pack_p", *args, ptr(packed), ctypes.byref(size), stream_ptr(dev))
     return packed
+
+
+def _effective_precision(precision: str, packed) -> str:
+    """tf32 operands take twice the shared memory of bf16: an MLP whose weights do not fit (pack_mlp -> None, e.g.
+    [131,128,128,256]) runs in the fp32 FMA kernel instead -- tighter, slower, never looser than asked for.  (bf16
+    without an image goes to the unpacked call, which falls back to the first-generation tcgen05 kernel.)"""
+    return "fp32" if precision == "tf32" and packed is None else precision
 
 
 def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: int, use_xyz: bool = True,
@@ -113,7 +126,8 @@ def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: in
         c_feat = features.shape[1]
     elif feat_t is not None:
         c_feat = layers[0][0].shape[1] - (3 if use_xyz else 0)
-        assert feat_t.dtype == torch.bfloat16 and feat_t.shape == (b, n, (c_feat + 7) // 8 * 8) and feat_t.is_contiguous()
+        row_dt, row_q = (torch.bfloat16, 8) if precision == "bf16" else (torch.float32, 4)
+        assert feat_t.dtype == row_dt and feat_t.shape == (b, n, (c_feat + row_q - 1) // row_q * row_q) and feat_t.is_contiguous()
     else:
         c_feat = 0
     nl = len(layers)
@@ -121,17 +135,18 @@ def sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, out, out_c0: in
     for l, (w, bias) in enumerate(layers):
         assert w.shape == (chans[l + 1], chans[l]) and w.is_contiguous() and bias.is_contiguous()
     ch_arr = (ctypes.c_int * (nl + 1))(*chans)
-    if packed is not None and precision == "bf16":
+    if packed is not None and precision in ("bf16", "tf32"):
         if out_t is not None:
-            assert out_t.dtype == torch.bfloat16 and out_t.is_contiguous() and out_t.shape == (b, m, (chans[-1] + 7) // 8 * 8)
-        call("tsmdet_sa_mlp_maxpool_packed", b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features),
+            row_dt, row_q = (torch.bfloat16, 8) if precision == "bf16" else (torch.float32, 4)
+            assert out_t.dtype == row_dt and out_t.is_contiguous() and out_t.shape == (b, m, (chans[-1] + row_q - 1) // row_q * row_q)
+        call("tsmdet_sa_mlp_maxpool_packed_p", PRECISIONS[precision], b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features),
              ptr(feat_t), ptr(idx), ptr(idx_cnt), nl, ch_arr, ptr(packed), ptr(out), ptr(out_t),
              out.shape[1] if out is not None else 0, out_c0, stream_ptr(xyz.device))
         return out
-    assert feat_t is None and out_t is None and out is not None, "row-chained layers need the packed bf16 path"
+    assert feat_t is None and out_t is None and out is not None, "row-chained layers need the packed tensor path"
     w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
-    prec = {"fp32": 0, "bf16": 1}[precision]
+    prec = PRECISIONS[precision]
     call("tsmdet_sa_mlp_maxpool", b, n, m, s, c_feat, int(use_xyz), ptr(xyz), ptr(new_xyz), ptr(features), ptr(idx),
          ptr(idx_cnt), nl, ch_arr, w_arr, b_arr, ptr(out), out.shape[1], out_c0, prec, stream_ptr(xyz.device))
     return out
@@ -154,13 +169,13 @@ def pointwise_mlp(src0: torch.Tensor, src1: Optional[torch.Tensor], layers, out:
         out = torch.empty((b, chans[-1], n), dtype=torch.float32, device=src0.device)
     assert out.is_contiguous() and out.shape[0] == b and out.shape[2] == n
     ch_arr = (ctypes.c_int * (nl + 1))(*chans)
-    if packed is not None and precision == "bf16":
-        call("tsmdet_pointwise_mlp_packed", b, n, c0, c1, ptr(src0), ptr(src1), nl, ch_arr, ptr(packed), ptr(out),
+    if packed is not None and precision in ("bf16", "tf32"):
+        call("tsmdet_pointwise_mlp_packed_p", PRECISIONS[precision], b, n, c0, c1, ptr(src0), ptr(src1), nl, ch_arr, ptr(packed), ptr(out),
              out.shape[1], out_c0, stream_ptr(src0.device))
         return out
     w_arr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w, _ in layers])
     b_arr = (ctypes.c_void_p * nl)(*[bb.data_ptr() for _, bb in layers])
-    prec = {"fp32": 0, "bf16": 1}[precision]
+    prec = PRECISIONS[precision]
     call("tsmdet_pointwise_mlp", b, n, c0, c1, ptr(src0), ptr(src1), nl, ch_arr, w_arr, b_arr, ptr(out), out.shape[1],
          out_c0, prec, stream_ptr(src0.device))
     return out
@@ -238,11 +253,11 @@ class PointnetFPModule(nn.Module):
             c1 = 0 if unknow_feats is None else unknow_feats.shape[1]
             if self._folded is None:
                 self._folded = fold_conv_bn(self.mlp)
-                self._packed = (pack_mlp(self._folded, dense=True, c_feat=c0, c1=c1)
-                                if self.precision == "bf16" else None)
+                self._packed = (pack_mlp(self._folded, dense=True, c_feat=c0, c1=c1, precision=self.precision)
+                                if self.precision in ("bf16", "tf32") else None)
             return pointwise_mlp(interpolated_feats.contiguous(),
                                  None if unknow_feats is None else unknow_feats.contiguous(), self._folded,
-                                 precision=self.precision, packed=self._packed)
+                                 precision=_effective_precision(self.precision, self._packed), packed=self._packed)
         if unknow_feats is not None:
             new_features = torch.cat([interpolated_feats, unknow_feats], dim=1)
         else:
@@ -353,8 +368,8 @@ class PointnetSAModuleFSMSG(nn.Module):
         per fold -- CUDA graphs captured afterwards hold its address, like the folded weights'."""
         folded = self._folded_layers()
         if self._packed is None or self._packed[0] != (c_feat, use_xyz, self.precision):
-            imgs = [pack_mlp(layers, dense=False, nsample=g.nsample, c_feat=c_feat, use_xyz=use_xyz)
-                    if self.precision == "bf16" else None for layers, g in zip(folded, self.groupers)]
+            imgs = [pack_mlp(layers, dense=False, nsample=g.nsample, c_feat=c_feat, use_xyz=use_xyz, precision=self.precision)
+                    if self.precision in ("bf16", "tf32") else None for layers, g in zip(folded, self.groupers)]
             self._packed = ((c_feat, use_xyz, self.precision), imgs)
         return self._packed[1]
 
@@ -393,7 +408,7 @@ class PointnetSAModuleFSMSG(nn.Module):
                 else:
                     idx_cnt, idx = pointnet2_utils.ball_query(grouper.radius, grouper.nsample, xyz, new_xyz)
                 sa_mlp_maxpool(xyz, new_xyz, features, idx, idx_cnt, layers, new_features, c0,
-                               use_xyz=eff_xyz, precision=self.precision, packed=img)
+                               use_xyz=eff_xyz, precision=_effective_precision(self.precision, img), packed=img)
                 c0 += w
             if old_features is not None:
                 new_features[:, c0:] = old_features
@@ -419,9 +434,11 @@ class PointnetSAModuleFSMSG(nn.Module):
             if use_fused:  # ref :1320-1321 as one kernel (BN folded; tensor cores in bf16 mode)
                 if self._folded_agg is None:
                     self._folded_agg = fold_conv_bn(self.aggregation_mlp)
-                    self._packed_agg = (pack_mlp(self._folded_agg, dense=True, c_feat=new_features.shape[1])
-                                        if self.precision == "bf16" else None)
-                new_features = pointwise_mlp(new_features.contiguous(), None, self._folded_agg, precision=self.precision,
+                    self._packed_agg = (pack_mlp(self._folded_agg, dense=True, c_feat=new_features.shape[1],
+                                                 precision=self.precision)
+                                        if self.precision in ("bf16", "tf32") else None)
+                new_features = pointwise_mlp(new_features.contiguous(), None, self._folded_agg,
+                                             precision=_effective_precision(self.precision, self._packed_agg),
                                              packed=self._packed_agg)
             else:
                 new_features = self.aggregation_mlp(new_features)
