@@ -59,14 +59,15 @@ constexpr int T2_MAX_LAYERS = 4;
 struct Tc2Plan {
     int nl;
     int eb;                    // bytes per operand element: 2 = bf16 (kind::f16), 4 = tf32 (kind::tf32)
+    int cl;                    // CTAs per tile: 1, or 2 = a cluster pair, each CTA holding HALF of every layer's output channels
     int K[T2_MAX_LAYERS];      // padded input channels of layer l (multiple of a K step: 16 bf16 / 8 tf32), without the bias step
-    int Npad[T2_MAX_LAYERS];   // rows of layer l's weight image: cout padded to 16 (last layer: to 128)
+    int Npad[T2_MAX_LAYERS];   // rows of layer l's weight image IN ONE CTA: cout padded to 16 (last layer: to 128), / cl
     int w_off[T2_MAX_LAYERS];  // byte offset of layer l's weights (non-last layers: K + 16 input rows, the last 16 = bias step)
     int b_off;                 // byte offset of the LAST layer's bias (fp32; added after the pool)
     int ones_off;              // the bias step's A operand: 2 chunk planes x 128 rows, [1, 1, 0, ...] | zeros
     int a_off, a_bytes;        // activation operand buffers (one per tile group)
     int x_off;                 // nsample == 128: per-group exchange of the two halves' maxima (2 x 128 floats), else -1
-    int smem_bytes, packed_bytes;
+    int smem_bytes, packed_bytes;  // packed_bytes: one CTA's image (the whole image is cl of them, rank-major)
     int cp;                    // SA mode: feature channels padded to 8 (width of the bf16 transpose)
     int xyz_chunk;             // SA mode: 16-byte chunk index of [dx,dy,dz,0...] in layer-0 rows, -1 if unused
     int grp_cols, tmem_cols;   // TMEM columns of one tile group / of the CTA (power of two >= 32)
@@ -82,6 +83,8 @@ struct Tc2Plan {
 __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, const Tc2Plan pl, const int dense,
                                                             unsigned char* __restrict__ packed) {
     const int l = blockIdx.y;
+    const int rank = blockIdx.z;  // cluster pair: CTA `rank` holds output channels [rank * Npad, (rank + 1) * Npad) of every layer
+    packed += (size_t)rank * pl.packed_bytes;
     const int epc = 16 / pl.eb, ks = 2 * epc;  // elements per 16-byte chunk, per K step
     auto put = [&](unsigned char* base, size_t e, float v) {
         if (pl.eb == 2) reinterpret_cast<__nv_bfloat16*>(base)[e] = __float2bfloat16_rn(v);
@@ -93,7 +96,8 @@ __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, c
             put(packed + pl.ones_off, e, (e < T2_ROWS * epc && (e % epc) < 2) ? 1.f : 0.f);
         const int Np = pl.Npad[pl.nl - 1], cout = a.ch[pl.nl];
         float* bs = reinterpret_cast<float*>(packed + pl.b_off);
-        for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256) bs[e] = e < cout ? __ldg(a.bias[pl.nl - 1] + e) : 0.f;
+        for (int e = blockIdx.x * 256 + threadIdx.x; e < Np; e += gridDim.x * 256)
+            bs[e] = rank * Np + e < cout ? __ldg(a.bias[pl.nl - 1] + rank * Np + e) : 0.f;
         return;
     }
     const int K = pl.K[l], Np = pl.Npad[l];
@@ -102,10 +106,11 @@ __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, c
     const float* __restrict__ W = a.w[l];
     for (int e = blockIdx.x * 256 + threadIdx.x; e < Np * Kb; e += gridDim.x * 256) {
         const int k = e / Np, n = e - k * Np;  // consecutive threads -> consecutive n: 16-byte-strided writes
+        const int ng = rank * Np + n;          // the output channel
         float o = 0.f;
-        if (n < cout) {
+        if (ng < cout) {
             if (k >= K) {
-                const float b = __ldg(a.bias[l] + n);
+                const float b = __ldg(a.bias[l] + ng);
                 if (k == K) o = rnd(b);
                 else if (k == K + 1) o = b - rnd(b);
             } else {
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(256) pack_weights2_kernel(const SaMlpArgs a, c
                 } else if (k < cin) {
                     src = k;
                 }
-                if (src >= 0) o = __ldg(W + (size_t)n * cin + src);
+                if (src >= 0) o = __ldg(W + (size_t)ng * cin + src);
             }
         }
         put(packed + pl.w_off[l], (size_t)(k / epc) * (Np * epc) + n * epc + (k % epc), o);
@@ -161,35 +166,46 @@ __global__ void __launch_bounds__(256) transpose2_kernel(int c, int cp, int n, c
 // operand (8 bf16 or 4 tf32 per chunk).  (The bias is already in the accumulator: every non-last layer ends with one
 // extra K step against the constant "ones" operand whose weight rows hold bias_hi + bias_lo, so the epilogue has no
 // shared-memory bias loads and no adds.)
-template <int NC, int EB>
-__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], unsigned char* dst) {
+// REMOTE: the chunk also goes to the same place in the peer CTA's operand buffer (rdst = its shared::cluster address).
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, const uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NC, int EB, bool REMOTE>
+__device__ __forceinline__ void epi_mid_store(const uint32_t (&v)[NC], unsigned char* dst, uint32_t rdst) {
     if constexpr (EB == 2) {
 #pragma unroll
         for (int q = 0; q < NC / 8; ++q) {
-            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = make_uint4(
+            const uint4 o = make_uint4(
                 pack_bf16_relu(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
                 pack_bf16_relu(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
                 pack_bf16_relu(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
                 pack_bf16_relu(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = o;
+            if constexpr (REMOTE) st_cluster_v4(rdst + (uint32_t)q * (T2_ROWS * 16), o);
         }
     } else {
 #pragma unroll
         for (int q = 0; q < NC / 4; ++q) {
-            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) =
+            const uint4 o =
                 make_uint4(to_tf32(fmaxf(__uint_as_float(v[4 * q + 0]), 0.f)), to_tf32(fmaxf(__uint_as_float(v[4 * q + 1]), 0.f)),
                            to_tf32(fmaxf(__uint_as_float(v[4 * q + 2]), 0.f)), to_tf32(fmaxf(__uint_as_float(v[4 * q + 3]), 0.f)));
+            *reinterpret_cast<uint4*>(dst + (size_t)q * (T2_ROWS * 16)) = o;
+            if constexpr (REMOTE) st_cluster_v4(rdst + (uint32_t)q * (T2_ROWS * 16), o);
         }
     }
 }
 
 // HW accumulator columns starting at TMEM address `taddr` (this thread's lane) -> chunk planes starting at dst;
 // compile-time width: straight-line code, two 32-column loads in flight per wait where the width allows
-template <int HW, bool LEAN, int EB>
-__device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst) {
+template <int HW, bool LEAN, int EB, bool REMOTE>
+__device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst, uint32_t rdst) {
     constexpr int EPC = 16 / EB;  // columns per chunk plane
+    constexpr uint32_t PL = T2_ROWS * 16;
     if constexpr (LEAN && HW >= 64) {  // 128-register kernels: one 32-column load in flight
 #pragma unroll
-        for (int i = 0; i < HW / 32; ++i) epi_mid<32, false, EB>(taddr + 32u * i, dst + (size_t)(32 * i / EPC) * (T2_ROWS * 16));
+        for (int i = 0; i < HW / 32; ++i)
+            epi_mid<32, false, EB, REMOTE>(taddr + 32u * i, dst + (size_t)(32 * i / EPC) * PL, rdst + (uint32_t)(32 * i / EPC) * PL);
         return;
     }
     constexpr int N64 = HW / 64, R64 = HW % 64;
@@ -199,43 +215,45 @@ __device__ __forceinline__ void epi_mid(uint32_t taddr, unsigned char* dst) {
         tmem_ld32_nowait(taddr + 64u * i, v0);
         tmem_ld32_nowait(taddr + 64u * i + 32u, v1);
         tmem_wait_ld();
-        epi_mid_store<32, EB>(v0, dst + (size_t)(64 * i / EPC) * (T2_ROWS * 16));
-        epi_mid_store<32, EB>(v1, dst + (size_t)((64 * i + 32) / EPC) * (T2_ROWS * 16));
+        epi_mid_store<32, EB, REMOTE>(v0, dst + (size_t)(64 * i / EPC) * PL, rdst + (uint32_t)(64 * i / EPC) * PL);
+        epi_mid_store<32, EB, REMOTE>(v1, dst + (size_t)((64 * i + 32) / EPC) * PL, rdst + (uint32_t)((64 * i + 32) / EPC) * PL);
     }
     constexpr int c1 = N64 * 64;
     if constexpr (R64 >= 32) {
         uint32_t v0[32];
         tmem_ld32_nowait(taddr + c1, v0);
         tmem_wait_ld();
-        epi_mid_store<32, EB>(v0, dst + (size_t)(c1 / EPC) * (T2_ROWS * 16));
+        epi_mid_store<32, EB, REMOTE>(v0, dst + (size_t)(c1 / EPC) * PL, rdst + (uint32_t)(c1 / EPC) * PL);
     }
     constexpr int c2 = c1 + (R64 >= 32 ? 32 : 0);
     if constexpr ((R64 % 32) >= 16) {
         uint32_t v0[16];
         tmem_ld16_nowait(taddr + c2, v0);
         tmem_wait_ld();
-        epi_mid_store<16, EB>(v0, dst + (size_t)(c2 / EPC) * (T2_ROWS * 16));
+        epi_mid_store<16, EB, REMOTE>(v0, dst + (size_t)(c2 / EPC) * PL, rdst + (uint32_t)(c2 / EPC) * PL);
     }
     constexpr int c3 = c2 + ((R64 % 32) >= 16 ? 16 : 0);
     if constexpr ((R64 % 16) >= 8) {
         uint32_t v0[8];
         tmem_ld8_nowait(taddr + c3, v0);
         tmem_wait_ld();
-        epi_mid_store<8, EB>(v0, dst + (size_t)(c3 / EPC) * (T2_ROWS * 16));
+        epi_mid_store<8, EB, REMOTE>(v0, dst + (size_t)(c3 / EPC) * PL, rdst + (uint32_t)(c3 / EPC) * PL);
     }
 }
 
 // any width that is a multiple of 8 (unusual channel counts)
-template <int EB>
-__device__ __forceinline__ void epi_mid_rt(int hw, uint32_t taddr, unsigned char* dst) {
+template <int EB, bool REMOTE>
+__device__ __forceinline__ void epi_mid_rt(int hw, uint32_t taddr, unsigned char* dst, uint32_t rdst) {
     constexpr int EPC = 16 / EB;
+    constexpr uint32_t PL = T2_ROWS * 16;
     int c = 0;
-    for (; c + 32 <= hw; c += 32) epi_mid<32, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
+    for (; c + 32 <= hw; c += 32)
+        epi_mid<32, false, EB, REMOTE>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * PL, rdst + (uint32_t)(c / EPC) * PL);
     if (c + 16 <= hw) {
-        epi_mid<16, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
+        epi_mid<16, false, EB, REMOTE>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * PL, rdst + (uint32_t)(c / EPC) * PL);
         c += 16;
     }
-    if (c + 8 <= hw) epi_mid<8, false, EB>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * (T2_ROWS * 16));
+    if (c + 8 <= hw) epi_mid<8, false, EB, REMOTE>(taddr + (uint32_t)c, dst + (size_t)(c / EPC) * PL, rdst + (uint32_t)(c / EPC) * PL);
 }
 
 // max over W consecutive registers starting at v[O] (W = 8, 16 or 32), FMNMX3 tree
@@ -261,11 +279,18 @@ __device__ __forceinline__ float max_run(const uint32_t (&v)[32]) {
 // the last MMA.  MINB: CTAs per SM the register allocation must allow.
 // EB: bytes per operand element -- 2: bf16 operands (kind::f16), 4: tf32 operands (kind::tf32, fp32 bit patterns rounded
 // to 10 mantissa bits; twice the shared memory and half the tensor rate, ~8x tighter than bf16).
-template <int GROUPS, int SC, bool DENSE, int PF, int NH, int MINB, int EB>
+// CL = 2: a tile is computed by a CLUSTER PAIR.  Each CTA holds half of every layer's output channels (half of the
+// weights: a [131,128,128,256] MLP in tf32 is 278 KB of operands), both gather the tile's rows, each computes its half of a
+// mid layer's activations and stores them into BOTH operand buffers (st.shared::cluster), and the transposed last layer
+// splits by output-channel block.  Two cluster barriers per mid layer: "both MMAs have read the buffers" before the
+// epilogues overwrite them, "both halves are written" before the next MMA.
+template <int GROUPS, int SC, bool DENSE, int PF, int NH, int MINB, int EB, int CL = 1>
 __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     mlp_tc2_kernel(const __grid_constant__ SaMlpArgs a, const __grid_constant__ Tc2Plan pl,
                    const unsigned char* __restrict__ featT, const unsigned char* __restrict__ packed, const int num_tiles) {
     constexpr int EPC = 16 / EB;  // operand elements per 16-byte chunk
+    static_assert(CL == 1 || (GROUPS == 1 && NH == 1 && !DENSE), "cluster pairs: one tile pipeline of 128 threads per CTA");
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mma_bars[GROUPS];
     __shared__ __align__(8) uint64_t w_bar;
@@ -293,7 +318,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
         mbar_init(smem_u32(&w_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_arrive_expect_tx(smem_u32(&w_bar), (uint32_t)pl.packed_bytes);
-        bulk_g2s(smem_u32(smem), packed, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
+        bulk_g2s(smem_u32(smem), packed + (size_t)crank * pl.packed_bytes, (uint32_t)pl.packed_bytes, smem_u32(&w_bar));
     }
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -304,6 +329,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if constexpr (CL == 2) cluster_sync_all();  // the peer CTA is resident before anything is stored into it
     bool weights_in = false;  // the weight image is awaited right before the first MMA: the first gather overlaps its copy
     auto wait_weights = [&]() {
         if (!weights_in) {
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     uint32_t phase = 0;
     const int cout_last = a.ch[nl];
     const int nchunk0 = pl.K[0] / EPC;
-    const int tile0 = blockIdx.x * GROUPS + grp, tile_step = gridDim.x * GROUPS;
+    const int tile0 = (blockIdx.x / CL) * GROUPS + grp, tile_step = (gridDim.x / CL) * GROUPS;  // both CTAs of a pair: the same tiles
 
     // SA mode: the neighbour index and the hit count of this thread's row are LOADED one tile ahead and only looked at
     // when the next gather is issued; the coordinates are loaded when the gather is issued and only looked at when it
@@ -519,6 +545,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
 #ifdef MLP_PROF
                 const long long ti0 = clock64();
 #endif
+                if constexpr (CL == 2) asm volatile("fence.proxy.async;" ::: "memory");  // the peer's stores -> async proxy
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // act (A, M = 128 rows) x W_l (B, N = Np); per K step of 16 only the start-address fields advance;
                 // last step: ones (A) x [bias_hi, bias_lo] rows -- the bias lands in the accumulator
@@ -546,23 +573,33 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             }
             wait_mma();
             MPROF(2);  // mid-layer MMA issue + wait
-            // ReLU -> bf16 -> next layer's A operand (written over the consumed one); thread = (row, column part h)
+            if constexpr (CL == 2) cluster_sync_all();  // both CTAs' MMAs have read their operand buffers
+            // ReLU -> bf16 / tf32 -> next layer's A operand (written over the consumed one); thread = (row, column part h);
+            // in a pair this CTA's columns are activation channels [crank * Np, (crank + 1) * Np)
             const int hw = Np / NH;
             const uint32_t ta = t_lane + (uint32_t)(h * hw);
-            unsigned char* const dst = a_row + (size_t)((h * hw) / EPC) * (T2_ROWS * 16);
+            const uint32_t poff = (uint32_t)(((int)crank * Np + h * hw) / EPC) * (T2_ROWS * 16);
+            unsigned char* const dst = a_row + poff;
+            const uint32_t rdst = CL == 2 ? mapa_u32(a_row_s + poff, crank ^ 1u) : 0u;
+            constexpr bool RM = CL == 2;
             switch (hw) {
-                case 8: epi_mid<8, false, EB>(ta, dst); break;
-                case 16: epi_mid<16, false, EB>(ta, dst); break;
-                case 32: epi_mid<32, false, EB>(ta, dst); break;
-                case 64: epi_mid<64, LEAN, EB>(ta, dst); break;
-                case 128: epi_mid<128, LEAN, EB>(ta, dst); break;
-                case 256: epi_mid<256, LEAN, EB>(ta, dst); break;
-                default: epi_mid_rt<EB>(hw, ta, dst); break;
+                case 8: epi_mid<8, false, EB, RM>(ta, dst, rdst); break;
+                case 16: epi_mid<16, false, EB, RM>(ta, dst, rdst); break;
+                case 32: epi_mid<32, false, EB, RM>(ta, dst, rdst); break;
+                case 64: epi_mid<64, LEAN, EB, RM>(ta, dst, rdst); break;
+                case 128: epi_mid<128, LEAN, EB, RM>(ta, dst, rdst); break;
+                case 256: epi_mid<256, LEAN, EB, RM>(ta, dst, rdst); break;
+                default: epi_mid_rt<EB, RM>(hw, ta, dst, rdst); break;
             }
             MPROF(3);  // mid-layer epilogue
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            group_sync();
+            if constexpr (CL == 2) {
+                asm volatile("fence.proxy.async;" ::: "memory");  // local and remote stores
+                cluster_sync_all();                                // both halves of the activations are in both buffers
+            } else {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                group_sync();
+            }
             MPROF(1);
         }
 
@@ -570,6 +607,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
         {
             const int l = nl - 1;
             if (mma_warp) {
+                if constexpr (CL == 2) asm volatile("fence.proxy.async;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // W_last block mb (A, M = 128 channels) x act (B, N = 128 rows)
                 const uint32_t sbase = smem_u32(smem);
@@ -627,8 +665,8 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                 auto pool = [&](auto full_tag) {
                     constexpr bool FULL = decltype(full_tag)::value;
                     for (int mb = 0; mb < pl.mb; ++mb) {
-                        const int ch = mb * T2_ROWS + row;
-                        const float bias = bs[ch];
+                        const int ch = (mb + (int)crank) * T2_ROWS + row;  // (a pair: CTA `crank` owns channel block `crank`)
+                        const float bias = bs[mb * T2_ROWS + row];
                         const bool ch_ok = ch < cout_last;
                         float* const obase = a.out + ((size_t)b0 * a.out_ctot + a.out_c0 + (ch_ok ? ch : 0)) * M + p0;
                         RowT* const tbase = reinterpret_cast<RowT*>(a.out_t) + (size_t)cbase * cpo + ch;
@@ -651,7 +689,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                                 }
                             }
                         };
-                        if (mb * T2_ROWS + (row & ~31) >= (cpo > cout_last ? cpo : cout_last)) continue;  // warp-uniform: padding channels
+                        if ((mb + (int)crank) * T2_ROWS + (row & ~31) >= (cpo > cout_last ? cpo : cout_last)) continue;  // warp-uniform: padding channels
                         float run = 0.f;
 #pragma unroll 1
                         for (int cb = 0; cb < PW; cb += 64) {
@@ -737,7 +775,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
                         group_sync();
                         if (h == 0) {
                             for (int mb = 0; mb < pl.mb; ++mb) {
-                                const int ch = mb * T2_ROWS + row;
+                                const int ch = mb * T2_ROWS + row;  // (NH == 2 excludes cluster pairs)
                                 const bool ch_ok = ch < cout_last;
                                 const float m = fmaxf(mb == 0 ? part0 : part1, xbuf[mb * T2_ROWS + row]);
                                 const float y = ch_ok ? fmaxf(__fadd_rn(m, bs[ch]), 0.f) : 0.f;
@@ -827,6 +865,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL == 2) cluster_sync_all();  // no CTA leaves while its peer may still store into it
     if (threadIdx.x < 32) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"((uint32_t)pl.tmem_cols)
                      : "memory");
@@ -839,10 +878,11 @@ static int round_up2(int v, int m) { return (v + m - 1) / m * m; }
 
 // Shapes this kernel takes and the shared-memory / TMEM plan for them.  TSM_ERR_INVALID otherwise (the caller falls
 // back to sa_mlp_tc.cu / the fp32 kernel).
-static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int eb, tsm::Tc2Plan* out, int* groups_out) {
+static int tc2_plan_cl(const tsm::SaMlpArgs& a, long long centres, int dense, int eb, int cl, tsm::Tc2Plan* out, int* groups_out) {
     using namespace tsm;
     const int S = a.s;
     if (eb != 2 && eb != 4) return TSM_ERR_INVALID;
+    if (cl != 1 && (cl != 2 || dense || S == T2_ROWS)) return TSM_ERR_INVALID;  // pairs: SA scales, 128 threads per CTA
     const int epc = 16 / eb, ks = 2 * epc;  // operand elements per 16-byte chunk / per K step
     if (a.num_layers < 1 || a.num_layers > T2_MAX_LAYERS) return TSM_ERR_INVALID;
     if (!dense) {
@@ -854,6 +894,7 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int e
     Tc2Plan pl;
     pl.nl = a.num_layers;
     pl.eb = eb;
+    pl.cl = cl;
     if (!dense) {
         pl.cp = round_up2(a.c_feat, epc);
         pl.xyz_chunk = a.use_xyz ? (pl.cp / epc) : -1;
@@ -864,11 +905,16 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int e
         pl.K[0] = round_up2(a.c_feat + a.c1, ks);
     }
     int off = 0, kmax = pl.K[0], nmid = 0;
+    int nfull_prev = 0;
     for (int l = 0; l < pl.nl; ++l) {
         const bool last = l + 1 == pl.nl;
-        pl.Npad[l] = round_up2(a.ch[l + 1], last ? T2_ROWS : 16);
-        if (pl.Npad[l] > 256) return TSM_ERR_INVALID;
-        if (l > 0) pl.K[l] = pl.Npad[l - 1];
+        const int nfull = round_up2(a.ch[l + 1], last ? T2_ROWS : 16);  // all output channels, padded
+        if (nfull > 256) return TSM_ERR_INVALID;
+        // a pair splits every layer's output channels in halves: 16-channel granularity, one 128-block each at the end
+        if (cl == 2 && (last ? nfull != 2 * T2_ROWS : nfull % 32 != 0)) return TSM_ERR_INVALID;
+        pl.Npad[l] = nfull / cl;
+        if (l > 0) pl.K[l] = nfull_prev;
+        nfull_prev = nfull;
         kmax = pl.K[l] > kmax ? pl.K[l] : kmax;
         if (!last) nmid = pl.Npad[l] > nmid ? pl.Npad[l] : nmid;
         pl.w_off[l] = off;
@@ -895,7 +941,7 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int e
     if (pl.grp_cols > 512) return TSM_ERR_INVALID;
     // two tile groups per CTA when the weights allow only one CTA per SM but a second operand buffer still fits
     int groups = 1;
-    if ((227 * 1024) / (smem_for(1) + 2048) < 2 && smem_for(2) <= 227 * 1024 - 64 && 2 * pl.grp_cols <= 512 &&
+    if (cl == 1 && (227 * 1024) / (smem_for(1) + 2048) < 2 && smem_for(2) <= 227 * 1024 - 64 && 2 * pl.grp_cols <= 512 &&
         !tsm_knob(KNOB_MLP_ONE_GROUP))
         groups = 2;
     pl.tmem_cols = pl.grp_cols * groups;
@@ -904,6 +950,14 @@ static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int e
     *out = pl;
     *groups_out = groups;
     return TSM_OK;
+}
+
+// One CTA per tile where the operands fit its shared memory; tf32 SA scales that do not (4-byte weights) go to a cluster
+// pair with half of every layer's output channels per CTA.
+static int tc2_plan(const tsm::SaMlpArgs& a, long long centres, int dense, int eb, tsm::Tc2Plan* out, int* groups_out) {
+    int rc = tc2_plan_cl(a, centres, dense, eb, 1, out, groups_out);
+    if (rc == TSM_ERR_INVALID && eb == 4 && !dense) rc = tc2_plan_cl(a, centres, dense, eb, 2, out, groups_out);
+    return rc;
 }
 
 // The kernel's weight image (bf16 UMMA core matrices incl. the bias steps, the last fp32 bias, the ones operand) for an
@@ -915,11 +969,11 @@ int tsm_mlp_tc2_pack(const tsm::SaMlpArgs& a, int dense, int eb, unsigned char* 
     int groups = 1;
     int rc = tc2_plan(a, 1, dense, eb, &pl, &groups);
     if (rc != TSM_OK) return rc;
-    if (bytes) *bytes = pl.packed_bytes;
+    if (bytes) *bytes = (long long)pl.packed_bytes * pl.cl;
     if (packed) {
         for (int l = 0; l < pl.nl; ++l)
             if (!a.w[l] || !a.bias[l]) return TSM_ERR_INVALID;
-        dim3 pgrid(16, (unsigned)pl.nl + 1);
+        dim3 pgrid(16, (unsigned)pl.nl + 1, (unsigned)pl.cl);
         pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(a, pl, dense, packed);
         TSM_LAUNCH_CHECK();
     }
@@ -988,8 +1042,15 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, int eb, cudaStream_t 
             kern = groups == 2 ? TC2_PICK_PF(2, 1, 1, 1, 2) : TC2_PICK_PF(1, 1, 1, 4, 2);
         }
     } else {  // tf32: one thread per row for SA scales, two for dense MLPs
-        if (dense) kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1, 4> : mlp_tc2_kernel<1, 32, true, 0, 2, 2, 4>;
-        else kern = groups == 2 ? TC2_PICK_PF(2, 1, 1, 1, 4) : TC2_PICK_PF(1, 1, 1, 4, 4);
+        if (dense) {
+            kern = groups == 2 ? mlp_tc2_kernel<2, 32, true, 0, 2, 1, 4> : mlp_tc2_kernel<1, 32, true, 0, 2, 2, 4>;
+        } else if (pl.cl == 2) {
+#define TC2_PICK2(P) (sc == 32 ? mlp_tc2_kernel<1, 32, false, P, 1, 1, 4, 2> : (sc == 16 ? mlp_tc2_kernel<1, 16, false, P, 1, 1, 4, 2> : mlp_tc2_kernel<1, 8, false, P, 1, 1, 4, 2>))
+            kern = pf == 16 ? TC2_PICK2(16) : (pf == 4 ? TC2_PICK2(4) : TC2_PICK2(0));
+#undef TC2_PICK2
+        } else {
+            kern = groups == 2 ? TC2_PICK_PF(2, 1, 1, 1, 4) : TC2_PICK_PF(1, 1, 1, 4, 4);
+        }
     }
 #undef TC2_PICK_PF
 #undef TC2_PICK
@@ -1016,19 +1077,41 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, int eb, cudaStream_t 
     if (const char* e = tsm_knob(KNOB_MLP_OCC)) occ = atoi(e) > 0 && atoi(e) < occ ? atoi(e) : occ;
     long long grid = (long long)tsm_num_sms() * occ;
     if (grid * groups > tiles) grid = (tiles + groups - 1) / groups;
+    if (pl.cl == 2) {  // pairs: both CTAs of a cluster walk the same tiles
+        long long clusters = (long long)(tsm_num_sms() / 2) * occ;
+        if (clusters > tiles) clusters = tiles;
+        grid = 2 * clusters;
+    }
     SaMlpArgs args = a;
     args.status = tsm_status_word(stream);
     const unsigned char* packed = prepacked;
     if (!packed) {
         void* p = nullptr;
-        int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes, stream, &p);
+        int rc = tsm_scratch_get(2, (size_t)pl.packed_bytes * pl.cl, stream, &p);
         if (rc != TSM_OK) return rc;
-        dim3 pgrid(16, (unsigned)pl.nl + 1);
+        dim3 pgrid(16, (unsigned)pl.nl + 1, (unsigned)pl.cl);
         pack_weights2_kernel<<<pgrid, 256, 0, stream>>>(args, pl, dense, (unsigned char*)p);
         TSM_LAUNCH_CHECK();
         packed = (const unsigned char*)p;
     }
-    kern<<<(unsigned)grid, gthreads * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    if (pl.cl == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(gthreads * groups));
+        cfg.dynamicSmemBytes = (size_t)pl.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int ntiles = (int)tiles;
+        TSM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, args, pl, featT, packed, ntiles));
+    } else {
+        kern<<<(unsigned)grid, gthreads * groups, pl.smem_bytes, stream>>>(args, pl, featT, packed, (int)tiles);
+    }
     TSM_LAUNCH_CHECK();
     return TSM_OK;
 }
