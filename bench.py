@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TSMDET_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16", "tf32"])
     ap.add_argument("--depth", type=int, default=int(os.environ.get("TSMDET_BENCH_DEPTH", "8")),
                     help="steps kept in flight (each on its own stream / CUDA graph / buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -447,7 +447,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
         "data": "synthetic", "config": cfg,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(ios[0].h2d_bytes),
                 "d2h_bytes_per_step": int(ios[0].d2h_bytes(rank == 0 and gather)),
@@ -495,6 +495,10 @@ def main():
             line["secondary"] = secondary_configs(dev)
         except Exception as ex:  # noqa: BLE001
             line["secondary"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        try:
+            line["secondary"]["tf32_stack"] = tf32_stack(d, dev, args, (xyz_np, feats_np, boxes_np, scores_np), orc)
+        except Exception as ex:  # noqa: BLE001
+            line["secondary"]["tf32_stack"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         n_cpu = 32  # two per-GPU batches: about 10 s of host work, every core busy in the OpenMP loops over clouds
@@ -566,7 +570,7 @@ def _ncu_facts():
                     rec = json.loads(ln)
                 except ValueError:
                     continue
-                for fam in ("fps_bucket_kernel", "sa_mlp_tc", "bq_grid_query", "bq_grid_build", "nms_lazy", "group_points",
+                for fam in ("fps_bucket_kernel", "sa_mlp_tc", "mlp_tc2_kernel", "bq_grid_query", "bq_grid_build", "nms_lazy", "group_points",
                             "pointwise_mlp_tc", "voxel_centroid"):
                     if fam in rec.get("kernel", ""):
                         facts[fam] = dict(rec, source=name)
@@ -611,7 +615,8 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
             out = torch.empty((b, cout, m), device=dev)
             # as in the pipelined step: layers hand their features on as bf16 rows (no fp32 tensor / transpose between)
             chain_out = img is not None and li + 1 < len(engine.backbone.layers)
-            out_t = torch.empty((b, m, (cout + 7) // 8 * 8), dtype=torch.bfloat16, device=dev) if chain_out else None
+            row_dt, row_q = (torch.bfloat16, 8) if layer.precision == "bf16" else (torch.float32, 4)
+            out_t = torch.empty((b, m, (cout + row_q - 1) // row_q * row_q), dtype=row_dt, device=dev) if chain_out else None
             f_in, t_in = (None, cur_t) if cur_t is not None else (cur_f, None)
             ms_mlp = t(lambda: sa_mlp_maxpool(cur_xyz, new_xyz, f_in, bidx, cnt, layers, out, 0, precision=layer.precision,
                                               packed=img, feat_t=t_in, out_t=out_t))
@@ -669,13 +674,13 @@ def kernel_breakdown(engine, d, dev, args, ms_step):
          "hbm_gbs": k1["gbs"], "hbm_frac": k1["gbs"] / hbm,
          "smem_wavefronts_per_launch": facts.get("fps_bucket_kernel", {}).get("smem_wavefronts"),
          "traffic": facts.get("fps_bucket_kernel", {}).get("dram_bytes")},
-        {"kernel": "sa_mlp_tc_kernel (3 launches: SA L1+L2+L3, tcgen05 bf16)", "bound": "tensor",
+        {"kernel": "mlp_tc2_kernel (3 launches: SA L1+L2+L3, tcgen05 bf16)", "bound": "tensor",
          "achieved": tot["mlp"][2] / tot["mlp"][0] / 1e9, "peak": tens, "unit": "TFLOP/s",
          "frac": tot["mlp"][2] / tot["mlp"][0] / 1e9 / tens, "ms": tot["mlp"][0], "sm_ms": tot["mlp"][1],
          "per_layer": [{"layer": i + 1, "ms": k["ms"], "tflops": k["tflops"], "frac": k["tflops"] / tens}
                        for i, k in enumerate(k for k in kernels if k["name"].startswith("sa_mlp"))],
-         "tensor_pipe_pct": facts.get("sa_mlp_tc", {}).get("tensor_pct"),
-         "traffic": facts.get("sa_mlp_tc", {}).get("dram_bytes")},
+         "tensor_pipe_pct": facts.get("mlp_tc2_kernel", {}).get("tensor_pct"),  # layer 3, ncu --set full (profiles/)
+         "traffic": facts.get("mlp_tc2_kernel", {}).get("dram_bytes")},
         {"kernel": "bq_grid_build + bq_grid_query (3 layers)", "bound": "hbm", "achieved": tot["bq"][2] / tot["bq"][0] / 1e6,
          "peak": hbm, "unit": "GB/s", "frac": tot["bq"][2] / tot["bq"][0] / 1e6 / hbm, "ms": tot["bq"][0],
          "sm_ms": tot["bq"][1], "traffic": facts.get("bq_grid_query", {}).get("dram_bytes")},
@@ -788,6 +793,29 @@ def ref_cuda_baseline(d, dev):
             "what": "unmodified reference CUDA kernels (oracle/_ref, sm_100a build) + reference eager fp32 MLP (cuDNN, TF32 off) "
                     "+ reference nms_gpu, one 16-frame step at a time on the legacy default stream, wall clock with a "
                     "synchronize (its NMS blocks the host anyway), mean of 3"}
+
+
+def tf32_stack(d, dev, args, d_np, orc):
+    """The same SA stack with tf32 tensor-core operands (tcgen05 kind::tf32; layer 3 on a cluster pair): per-layer times
+    measured like roofline.per_kernel, one whole step verified like the headline configuration with the tf32 bars."""
+    import parity
+    import torch
+
+    from tsmdet_b200.pipeline import SABackboneNMS
+
+    torch.manual_seed(0)
+    eng = SABackboneNMS(precision="tf32").to(dev)
+    res = eng.forward_device(*d)
+    torch.cuda.synchronize(dev)
+    m = parity.verify_step(eng, orc, *d_np, res, "tf32", frames=[0, 15])
+    roof, _ = kernel_breakdown(eng, d, dev, args, 1.0)
+    mlp = next(f for f in roof["per_kernel"] if f["bound"] == "tensor")
+    tf32_peak = float(_peaks()["bf16_tflops"]) / 2  # kind::tf32 runs at half the bf16 rate
+    return {"what": "SA L1+L2+L3 with tf32 operands (precision='tf32'), fp32 accumulate; L3 [131,128,128,256] on cluster pairs",
+            "stack_ms": mlp["ms"], "per_layer": [{"layer": k["layer"], "ms": k["ms"], "tflops": k["tflops"],
+                                                   "frac_of_tf32_peak": k["tflops"] / tf32_peak} for k in mlp["per_layer"]],
+            "vs_eager_fp32": {k: m[k] for k in ("max_abs_over_scale", "rel_l2", "max_rel_big")},
+            "indices_and_keep_lists": "bit-exact"}
 
 
 def secondary_configs(dev):
