@@ -204,26 +204,36 @@ def _fps_temp_scratch_contract(orc):
     ("objects65536", synth.cloud_ground_objects, 65536, 900),  # 5 CTAs, largest u16-index cloud
     ("dup70001", synth.cloud_dup_padded, 70001, 600),          # 5 CTAs, indices above 65535 (slice-position mode)
     ("lattice163840", synth.cloud_lattice, 163840, 400),       # 11 CTAs (non-portable cluster size), Waymo test size
-], ids=["dup20000", "lattice40000", "objects65536", "dup70001", "lattice163840"])
+    ("objects20000", synth.cloud_ground_objects, 20000, 4096), # the reference's KITTI test shape (fast_cpc.yaml:52-56)
+    ("uniform30000", synth.cloud_uniform, 30000, 2048),
+], ids=["dup20000", "lattice40000", "objects65536", "dup70001", "lattice163840", "objects20000", "uniform30000"])
 def test_fps_bucket_cluster_equals_cluster_kernel(name, gen, n, m, monkeypatch):
-    """The pruned sampler over a CTA cluster (fps_bucket_cluster.cu, the default for 16385..240000 points) returns
-    exactly what the brute-force cluster kernel returns, including the final min-distances handed back in temp."""
+    """The pruned sampler over a CTA cluster (fps_bucket_cluster.cu, the default for 16385..240000 points) -- with one pick
+    per DSMEM exchange and with rounds of several picks -- returns exactly what the brute-force cluster kernel returns,
+    including the final min-distances handed back in temp."""
     from tsmdet_b200 import pointnet2_batch_cuda as ext
 
     xyz = torch.from_numpy(gen(2, n, 90)).to(_dev())
     outs = []
-    for algo in ("cluster", None):
+    # brute-force cluster kernel | one pick per DSMEM exchange | rounds of several picks (default list length, then 2)
+    for algo, k in (("cluster", None), (None, "1"), (None, None), (None, "2")):
         if algo:
             knob_setenv(monkeypatch, "TSMDET_FPS_ALGO", algo)
         else:
             knob_delenv(monkeypatch, "TSMDET_FPS_ALGO", raising=False)
+        if k:
+            knob_setenv(monkeypatch, "TSMDET_FPSC_K", k)
+        else:
+            knob_delenv(monkeypatch, "TSMDET_FPSC_K", raising=False)
         temp = torch.full((2, n), 1e10, device=_dev())
         idx = torch.zeros((2, m), dtype=torch.int32, device=_dev())
         ext.farthest_point_sampling_wrapper(2, n, m, xyz, temp, idx)
         torch.cuda.synchronize()
         outs.append((idx, temp))
-    assert torch.equal(outs[0][0], outs[1][0]), name
-    assert torch.equal(outs[0][1].view(torch.int32), outs[1][1].view(torch.int32)), name
+    for i in range(1, len(outs)):
+        assert torch.equal(outs[0][0], outs[i][0]), (name, i, int((outs[0][0] != outs[i][0]).sum()),
+                                                     (outs[0][0] != outs[i][0]).nonzero()[:4].tolist())
+        assert torch.equal(outs[0][1].view(torch.int32), outs[i][1].view(torch.int32)), (name, i)
 
 
 def test_fps_weights(orc):
