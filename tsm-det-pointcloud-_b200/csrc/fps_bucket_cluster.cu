@@ -933,9 +933,10 @@ int tsm_fps_bucket_cluster_launch(const tsm::FpsArgs& a, int b, cudaStream_t str
     fps_sort_kernel<<<b, 1024, sort_dyn, stream>>>(n, a.xyz, sorted);
     TSM_LAUNCH_CHECK();
     const bool big = n > 65536;
-    // rounds of several picks per exchange (TSMDET_FPSC_K=1: one pick per exchange): kx list entries per CTA, <= 32 in all
-    int kx = csize <= 8 ? 4 : 2;
-    if (const char* e = tsm_knob(KNOB_FPSC_K)) kx = atoi(e) <= 1 ? 0 : (atoi(e) < kx ? atoi(e) : kx);
+    // rounds of several picks per exchange (TSMDET_FPSC_K=1: one pick per exchange): kx list entries per CTA, <= 32 in all CTAs
+    const int kx_max = 32 / csize < FBM_KA ? 32 / csize : FBM_KA;
+    int kx = kx_max < 6 ? kx_max : 6;  // measured (B200): 20000 -> 4096 on two CTAs 2.37 ms with 4, 2.25 ms with 6 or 8
+    if (const char* e = tsm_knob(KNOB_FPSC_K)) kx = atoi(e) <= 1 ? 0 : (atoi(e) < kx_max ? atoi(e) : kx_max);
     if (per_cta > 15360 || kx * csize > 32) kx = 0;
     using Kern1 = void (*)(const FpsArgs, const float4*, int);
     using KernM = void (*)(const FpsArgs, const float4*, int, int);
