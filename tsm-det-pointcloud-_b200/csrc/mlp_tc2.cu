@@ -392,6 +392,12 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
     const uint32_t a_row_s = a_smem + (uint32_t)row * 16u;
     const bool planar = PF == 0 && featT == nullptr && a.c_feat > 0;  // <= 4 feature channels: read straight from (B,C,N) fp32
     const bool own_xyz = pl.xyz_chunk >= 0 && (NH == 1 || (pl.xyz_chunk & 1) == h);
+    // Register-prefetched feature chunks are split between the two threads of a row (NH == 2) or the two CTAs of a pair
+    // (CL == 2: each gathers every other chunk and stores it into BOTH operand buffers -- half the gather traffic, and
+    // the one-tile-ahead register path instead of cp.async for rows of up to 32 chunks)
+    constexpr int CST = NH * CL;                    // chunk stride of this thread's slots
+    const int coff = CL == 2 ? (int)crank : h;      // its first chunk
+    const uint32_t a_row_peer = CL == 2 ? mapa_u32(a_row_s, crank ^ 1u) : 0u;
     constexpr bool kEarly = PF > 0;  // (planar rows are early too: decided at run time)
     auto load_row = [&](int tile) {
         if constexpr (!DENSE) {
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
 #pragma unroll
                 for (int j = 0; j < PFH; ++j) {
                     pf_row[j] = make_uint4(0u, 0u, 0u, 0u);
-                    if (live && NH * j + h < fchunks) pf_row[j] = __ldg(frow + NH * j + h);
+                    if (live && CST * j + coff < fchunks) pf_row[j] = __ldg(frow + CST * j + coff);
                 }
             } else if (featT != nullptr) {
                 const int fchunks = pl.cp / EPC;
@@ -442,8 +448,12 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             const int fchunks = (planar || featT == nullptr) ? 0 : (pl.cp / EPC);
             if constexpr (PF > 0) {
 #pragma unroll
-                for (int j = 0; j < PFH; ++j)
-                    if (NH * j + h < fchunks) *reinterpret_cast<uint4*>(a_row + (size_t)(NH * j + h) * (T2_ROWS * 16)) = pf_row[j];
+                for (int j = 0; j < PFH; ++j) {
+                    if (CST * j + coff < fchunks) {
+                        *reinterpret_cast<uint4*>(a_row + (size_t)(CST * j + coff) * (T2_ROWS * 16)) = pf_row[j];
+                        if constexpr (CL == 2) st_cluster_v4(a_row_peer + (uint32_t)(CST * j + coff) * (T2_ROWS * 16), pf_row[j]);
+                    }
+                }
             }
             // this thread's chunks behind the features: coordinates, planar features, zero padding
             for (int kc = fchunks + (NH == 2 ? ((fchunks ^ h) & 1) : 0); kc < nchunk0; kc += NH) {
@@ -532,10 +542,15 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             }
         }
         MPROF(0);  // operand build
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         wait_weights();
-        group_sync();
+        if constexpr (CL == 2) {
+            asm volatile("fence.proxy.async;" ::: "memory");  // local and remote stores of the operand
+            cluster_sync_all();                                // both CTAs' halves of the gathered rows are in both buffers
+        } else {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            group_sync();
+        }
         MPROF(1);  // fence + barrier
 
         // ------------------------------------------------------------------ layers 0 .. nl-2: D[row, cout] in TMEM
@@ -638,6 +653,7 @@ __global__ void __launch_bounds__(128 * NH * GROUPS, MINB)
             }
             MPROF(4);  // next tile's loads issued
             wait_mma();
+            if constexpr (CL == 2) cluster_sync_all();  // both CTAs' last MMAs have read the buffers the next gather overwrites
             MPROF(5);  // last MMA wait
             if (!early) {  // cp.async rows: the operand buffer is free again, the copies land during the epilogue below
                 if (tile + tile_step < num_tiles) load_row(tile + tile_step);
@@ -1025,7 +1041,7 @@ int tsm_mlp_tc2(const tsm::SaMlpArgs& a, int b, int dense, int eb, cudaStream_t 
     int nh = dense ? 2 : 1;  // measured (B200, config 2 / config 4): SA L1/L2/L3 48/36/50 us vs 74/48/60, FP MLP 285 vs 233 us
     if (const char* e = tsm_knob(KNOB_MLP_NH)) nh = (atoi(e) == 2 && (eb == 2 || dense)) ? 2 : (dense && eb == 4 ? 2 : 1);
     const int sc = S < 32 ? S : 32;
-    const int fchunks = (!dense && featT) ? (pl.cp / epc) : 0;
+    const int fchunks = (!dense && featT) ? (pl.cp / epc + pl.cl - 1) / pl.cl : 0;  // register-prefetched chunks per CTA
     const int pf = fchunks == 0 ? 0 : (fchunks <= 4 ? 4 : (fchunks <= 16 ? 16 : 0));
     // MINB: one-group CTAs of 128 threads with narrow rows fit 4 per SM in <= 128 registers; 256-thread ones 2
 #define TC2_PICK(G, P, H, B, E)                                                                                       \
