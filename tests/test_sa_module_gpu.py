@@ -68,6 +68,9 @@ CFGS["ns64"] = dict(npoint_list=[96], sample_range_list=[[0, None]], sample_meth
                     radii=[2.0], nsamples=[64], mlps=[[16, 64, 128]])
 CFGS["ns128_wide"] = dict(npoint_list=[40], sample_range_list=[[0, None]], sample_method_list=['d-fps'],
                           radii=[3.0], nsamples=[128], mlps=[[8, 32, 200]])
+# tf32: 261 KB of operands -> a cluster pair with 48 / 80 activation channels per CTA (run-time epilogue widths, SC = 16)
+CFGS["pair_odd"] = dict(npoint_list=[128], sample_range_list=[[0, None]], sample_method_list=['d-fps'],
+                        radii=[1.2], nsamples=[16], mlps=[[64, 96, 160, 256]])
 CFGS["ns8_two_scales"] = dict(npoint_list=[300], sample_range_list=[[0, None]], sample_method_list=['d-fps'],
                               radii=[0.5, 1.0], nsamples=[8, 16], mlps=[[4, 32, 64], [4, 48, 96]])
 
@@ -109,7 +112,7 @@ def test_fused_sa_matches_eager(name, precision, monkeypatch):
     parity.check_metrics(m, precision, f"{name}")
     if precision == "tf32":  # the tensor kernel really ran where the plan says it fits
         imgs = layer._packed_layers(c_in, True)
-        fits = {"kitti_l1": 1, "kitti_l2": 1, "kitti_l3": 1, "ref_layer0": 3, "odd": 0, "ns64": 1, "ns128_wide": 1, "ns8_two_scales": 2}
+        fits = {"kitti_l1": 1, "kitti_l2": 1, "kitti_l3": 1, "ref_layer0": 3, "odd": 0, "ns64": 1, "ns128_wide": 1, "ns8_two_scales": 2, "pair_odd": 1}
         assert sum(i is not None for i in imgs) == fits[name], [None if i is None else i.numel() for i in imgs]
 
 
