@@ -15,7 +15,10 @@
 //    shared memory, completing on the peer's mbarrier (double-buffered by pick parity, no cluster-wide barrier on
 //    the critical path), and every warp picks the cluster winner: largest key, smallest reference rank among
 //    equals.  A pick costs what a single-CTA pick costs plus one DSMEM flight, whatever N is, instead of growing
-//    with N as the brute-force cluster kernel of fps.cu does.
+//    with N as the brute-force cluster kernel of fps.cu does.  (TSMDET_FPSC_K=1; kept as the A/B reference.)
+//  * fps_bucket_cluster_mp_kernel (the default): the same slices, but ROUNDS of several exact picks per exchange --
+//    every CTA publishes its top-KX warp candidates and the bound of the ones it did not publish, and every CTA
+//    makes the same merged decision (see the comment above the kernel).  About half the time per pick.
 #include "fps.cuh"
 
 namespace tsm {
