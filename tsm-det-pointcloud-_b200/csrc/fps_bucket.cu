@@ -356,15 +356,18 @@ __global__ void __launch_bounds__(T, 1)
         return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     };
     auto update = [&](float x1, float y1, float z1) {
+        const unsigned long long nx = f2_pack(-x1, -x1), ny = f2_pack(-y1, -y1), nz = f2_pack(-z1, -z1);
 #pragma unroll
         for (int q = 0; q < C4; ++q) {
             const float4 X = *reinterpret_cast<const float4*>(sx + base + q * 128);
             const float4 Y = *reinterpret_cast<const float4*>(sy + base + q * 128);
             const float4 Z = *reinterpret_cast<const float4*>(sz + base + q * 128);
-            md[q * 4 + 0] = fminf(sqdist3(x1, y1, z1, X.x, Y.x, Z.x), md[q * 4 + 0]);
-            md[q * 4 + 1] = fminf(sqdist3(x1, y1, z1, X.y, Y.y, Z.y), md[q * 4 + 1]);
-            md[q * 4 + 2] = fminf(sqdist3(x1, y1, z1, X.z, Y.z, Z.z), md[q * 4 + 2]);
-            md[q * 4 + 3] = fminf(sqdist3(x1, y1, z1, X.w, Y.w, Z.w), md[q * 4 + 3]);
+            const float2 d01 = sqdist3_x2(nx, ny, nz, X.x, X.y, Y.x, Y.y, Z.x, Z.y);  // FADD2 / FMUL2 / FFMA2: bit-identical
+            const float2 d23 = sqdist3_x2(nx, ny, nz, X.z, X.w, Y.z, Y.w, Z.z, Z.w);  // to sqdist3, half the instructions
+            md[q * 4 + 0] = fminf(d01.x, md[q * 4 + 0]);
+            md[q * 4 + 1] = fminf(d01.y, md[q * 4 + 1]);
+            md[q * 4 + 2] = fminf(d23.x, md[q * 4 + 2]);
+            md[q * 4 + 3] = fminf(d23.y, md[q * 4 + 3]);
         }
     };
     // The lane / warp argmax after an update.  Leaves (wu, wpos, wu2); bit 31 of wpos = "another point of this warp
