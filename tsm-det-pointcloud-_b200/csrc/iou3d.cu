@@ -559,7 +559,13 @@ __global__ void __launch_bounds__(256)
     for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < words_per_frame; e += (size_t)gridDim.x * 256) M[e] = 0ull;
 }
 
-constexpr int NMSL_THREADS = 512;
+// One CTA per frame.  The kernel is latency-bound (24 % issue slots): 512 threads x 109 registers filled an SM's register
+// file, so a frame's NMS held a whole SM for ~0.6 ms; with 256 threads other steps' kernels share the SM -- the
+// pipelined step measured 30.8k -> 31.5k frames/s (128 threads: 31.1k).
+#ifndef TSM_NMSL_THREADS
+#define TSM_NMSL_THREADS 256
+#endif
+constexpr int NMSL_THREADS = TSM_NMSL_THREADS;
 constexpr int NMSL_WARPS = NMSL_THREADS / 32;
 
 __global__ void __launch_bounds__(NMSL_THREADS)
