@@ -13,7 +13,7 @@
  * Numerics: built with gcc -O2 -ffp-contract=off on x86-64 (no FMA contraction,
  * glibc cosf/sinf/atan2f), i.e. the arithmetic g++ gives iou3d_cpu.cpp.  That
  * is bit-identical to the reference's boxes_iou_bev_cpu (pinned by
- * tests/test_oracle_golden.py against oracle/_ref and the committed fixture) and
+ * tests/test_oracle_cpu.py against oracle/_ref and the committed fixture) and
  * equal to the *GPU* kernels only to ~1e-6 (libdevice trig + FMA contraction),
  * so against the GPU this file is a tolerance oracle for IoU values; bit-exact
  * keep-lists are pinned against the reference CUDA extension itself.
