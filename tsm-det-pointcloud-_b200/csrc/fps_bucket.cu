@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(T, 1)
 #ifdef FPSB_PROF
         long long prof_apply = 0, prof_wait = 0, prof_lead = 0, prof_rounds = 0, prof_t00 = clock64();
         long long prof_q[5] = {0, 0, 0, 0, 0};
+        long long pw_hits = 0, pw_rounds = 0, pw_redo = 0, pw_upd = 0, pw_arg = 0, pw_c = 0, pw_u1 = 0;  // per warp: APPLY phase
 #endif
         int round = 0;
         for (int j = 1; j < m; ++round) {
@@ -570,6 +571,10 @@ __global__ void __launch_bounds__(T, 1)
             // (no second, finer test here: the round is bound by the latency of this chain, not by issue slots, so an
             // update that turns out to change nothing is cheaper than a test + warp vote that might avoid it)
             const unsigned wm = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & ((1u << c) - 1u);
+#ifdef FPSB_PROF
+            const long long pw0 = clock_after(wm);
+            long long pw1 = pw0;
+#endif
             if (wm != 0u) {
                 // The warp's record stays valid as long as its candidate point itself is not lowered: updates only lower
                 // min-distances, so the maximum stays where it is and the runner-up key stays an upper bound.  The test
@@ -577,14 +582,33 @@ __global__ void __launch_bounds__(T, 1)
                 const float cx = sx[wpos & 0x7fffffffu], cy = sy[wpos & 0x7fffffffu], cz = sz[wpos & 0x7fffffffu];
                 const float cval = __uint_as_float(wu & 0x7fffffffu);
                 bool redo = (wu & 0x80000000u) == 0u;  // no valid record yet (first round, ineligible warp)
+#ifdef FPSB_PROF
+                const long long pwc = clock_after(__float_as_uint(cx) ^ __float_as_uint(cy) ^ __float_as_uint(cz));
+                pw_c += pwc - pw0;
+#endif
+                // (only the bit positions first..last set: a lone warp pays ~5 cycles per instruction, and scanning all K
+                //  positions cost more than the ~1.2 updates a hit warp applies per round)
 #pragma unroll 1
-                for (int k = 0; k < K; ++k) {
+                for (int k = __ffs(wm) - 1; (wm >> k) != 0u; ++k) {
                     if ((wm >> k) & 1u) {
                         const float4 pk = cand[k];
                         redo |= sqdist3(pk.x, pk.y, pk.z, cx, cy, cz) < cval;
+#ifdef FPSB_PROF
+                        const long long pu0 = clock_after(__float_as_uint(pk.x) ^ __float_as_uint(pk.z));
+#endif
                         update(pk.x, pk.y, pk.z);
+#ifdef FPSB_PROF
+                        uint32_t dep = 0u;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) dep ^= __float_as_uint(md[p]);
+                        pw_u1 += clock_after(dep) - pu0;
+#endif
                     }
                 }
+#ifdef FPSB_PROF
+                pw1 = clock_after(__float_as_uint(md[0]) ^ __float_as_uint(md[P - 1]));
+                pw_hits += __popc(wm); ++pw_rounds; pw_redo += redo ? 1 : 0;
+#endif
                 if (redo) {
                     warp_argmax();
                     if (lane == 0) {
@@ -594,6 +618,10 @@ __global__ void __launch_bounds__(T, 1)
                         rskey[warp] = (wu & ~31u) | (31u - (uint32_t)warp);
                     }
                 }
+#ifdef FPSB_PROF
+                const long long pw2 = clock_after(wu ^ wu2);
+                pw_upd += pw1 - pw0; pw_arg += pw2 - pw1;
+#endif
             }
             if (warp != 0) {
                 asm volatile("bar.arrive %0, %1;" ::"n"(kBarPost), "n"(T) : "memory");
@@ -757,6 +785,9 @@ __global__ void __launch_bounds__(T, 1)
             }
         }
 #ifdef FPSB_PROF
+        if (lane == 0 && cloud == 0)
+            printf("   warp %2d: hit in %lld rounds, %lld updates, %lld argmax;  cycles per hit round: one update %lld; cand coords %lld, updates (incl.) %lld, argmax+post %lld\n", warp,
+                   pw_rounds, pw_hits, pw_redo, pw_u1 / (pw_hits ? pw_hits : 1), pw_c / (pw_rounds ? pw_rounds : 1), pw_upd / (pw_rounds ? pw_rounds : 1), pw_arg / (pw_rounds ? pw_rounds : 1));
         if (tid == 0 && cloud == 0)
             printf("fpsb K=%d n=%d m=%d rounds %lld  cycles/round: apply(warp0) %lld  wait-for-posts %lld  leader %lld  total %lld\n",
                    K, n, m, prof_rounds, prof_apply / prof_rounds, prof_wait / prof_rounds, prof_lead / prof_rounds,
