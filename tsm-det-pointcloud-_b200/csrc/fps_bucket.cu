@@ -71,8 +71,13 @@ __host__ __device__ __forceinline__ size_t bucket_main_bytes(int cap, int thread
     return (mx + 15) & ~(size_t)15;
 }
 
-template <int P>
-__device__ __forceinline__ int slot_index(int s) {  // sorted position -> shared-memory element index
+// sorted position -> shared-memory element index.  A lane owns the elements base + c * 128 + e (chunk c of its warp, e < 4).
+// Lane-compact (CH = false): P consecutive sorted points per LANE (a lane's box is tight: the K = 1 loop skips per lane).
+// Chunk-compact (CH = true): the planes are simply in sorted order, so chunk c of a warp -- the 128 points ONE LDS.128 of
+// the update reads -- is spatially compact and an update can skip whole chunks (multi-pick rounds, see APPLY).
+template <int P, bool CH>
+__device__ __forceinline__ int slot_index(int s) {
+    if (CH) return s;
     const int p = s & (P - 1), l = (s / P) & 31, w = s / (32 * P);
     return w * (32 * P) + (p >> 2) * 128 + l * 4 + (p & 3);
 }
@@ -87,6 +92,8 @@ __global__ void __launch_bounds__(T, 1)
     constexpr int NW = T / 32;
     constexpr int CAP = T * P;
     constexpr int C4 = P / 4;
+    constexpr bool CH = K > 1 && C4 >= 2;  // chunk-compact layout, updates skip half of a warp's chunks at a time
+    constexpr int HC = CH ? C4 / 2 : C4;   // chunks per half
     extern __shared__ __align__(16) unsigned char dyn[];
     float* const sx = reinterpret_cast<float*>(dyn);
     float* const sy = sx + CAP;
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(T, 1)
     __syncthreads();  // the histogram is dead; its bytes become the coordinate planes
     // (6) scatter coordinates + original index to the sorted position; zero the padding slots
     for (int s = n + tid; s < CAP; s += T) {
-        const int e = slot_index<P>(s);
+        const int e = slot_index<P, CH>(s);
         sx[e] = 0.f; sy[e] = 0.f; sz[e] = 0.f; sk[e] = 0;
     }
 #pragma unroll
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(T, 1)
         const int k = tid + i * T;
         if (k < n) {
             const uint32_t s = (i & 1) ? (packed[i >> 1] >> 16) : (packed[i >> 1] & 0xffffu);
-            const int e = slot_index<P>((int)s);
+            const int e = slot_index<P, CH>((int)s);
             sx[e] = __ldg(xyz + 3 * k);
             sy[e] = __ldg(xyz + 3 * k + 1);
             sz[e] = __ldg(xyz + 3 * k + 2);
@@ -264,22 +271,28 @@ __global__ void __launch_bounds__(T, 1)
 
     // ================= per-lane state =================
     const int base = warp * (32 * P) + lane * 4;    // element index of this lane's slot 0
-    const int first = (warp * 32 + lane) * P;       // sorted position of slot 0
+    const int first = (warp * 32 + lane) * P;       // sorted position of slot 0 (lane-compact layout)
+    auto slot_valid = [&](int p) -> bool {          // slot p of this lane holds a point of the cloud
+        return CH ? (base + (p >> 2) * 128 + (p & 3) < n) : (first + p < n);
+    };
     float md[P];
     {
         // Order each lane's P points by ascending reference rank (any order inside a lane is as good as another
         // for the pruning), so that "lowest slot among equal maxima" IS the reference's tie rule inside a lane.
-        // Slots past the cloud's end take the largest ranks and stay last.
+        // Slots past the cloud's end take the largest ranks and stay last.  Chunk-compact layout: the order is established
+        // inside every group of 4 slots only (a point must stay in its chunk); equal maxima in different chunks of one lane
+        // -- different points at equal distances, rare -- are decided by an explicit rank comparison in warp_argmax.
         uint32_t rk[P];
 #pragma unroll
         for (int p = 0; p < P; ++p)
-            rk[p] = (first + p < n) ? ref_rank(sk[base + (p >> 2) * 128 + (p & 3)], L) : (0xffffffe0u + (uint32_t)p);
+            rk[p] = slot_valid(p) ? ref_rank(sk[base + (p >> 2) * 128 + (p & 3)], L) : (0xffffffe0u + (uint32_t)p);
         int dst[P];  // element index each slot's point moves to
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            int before = 0;
+            int before = CH ? (p & ~3) : 0;
 #pragma unroll
-            for (int q = 0; q < P; ++q) before += (rk[q] < rk[p]) ? 1 : 0;
+            for (int q = 0; q < P; ++q)
+                if (!CH || (q >> 2) == (p >> 2)) before += (rk[q] < rk[p]) ? 1 : 0;
             dst[p] = base + (before >> 2) * 128 + (before & 3);
         }
         {
@@ -300,10 +313,11 @@ __global__ void __launch_bounds__(T, 1)
         }
         // (only this thread touches these elements: no barrier needed before it reads them back)
     }
-    {
+#pragma unroll
+    for (int h = 0; h < (CH ? 2 : 1); ++h) {
         float bx0 = __int_as_float(0x7f800000), by0 = bx0, bz0 = bx0, bx1 = -bx0, by1 = -bx0, bz1 = -bx0;
 #pragma unroll
-        for (int c = 0; c < C4; ++c) {
+        for (int c = h * HC; c < (h + 1) * HC; ++c) {
             const float4 X = *reinterpret_cast<const float4*>(sx + base + c * 128);
             const float4 Y = *reinterpret_cast<const float4*>(sy + base + c * 128);
             const float4 Z = *reinterpret_cast<const float4*>(sz + base + c * 128);
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(T, 1)
             for (int e = 0; e < 4; ++e) {
                 const int p = c * 4 + e;
                 float d0 = -2.f;
-                if (first + p < n) {
+                if (slot_valid(p)) {
                     bx0 = fminf(bx0, xs[e]); bx1 = fmaxf(bx1, xs[e]);
                     by0 = fminf(by0, ys[e]); by1 = fmaxf(by1, ys[e]);
                     bz0 = fminf(bz0, zs[e]); bz1 = fmaxf(bz1, zs[e]);
@@ -321,16 +335,18 @@ __global__ void __launch_bounds__(T, 1)
                 md[p] = d0;
             }
         }
-        // one box per 16 lanes (what fits next to the planes): union over the half-warp
+        // one box per 16 lanes (what fits next to the planes): union over the half-warp; chunk-compact layout: one box
+        // per half of the warp's chunks (box 2 * warp + h), union over the warp
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
+        for (int o = CH ? 16 : 8; o > 0; o >>= 1) {
             bx0 = fminf(bx0, __shfl_xor_sync(FULL, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(FULL, bx1, o));
             by0 = fminf(by0, __shfl_xor_sync(FULL, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(FULL, by1, o));
             bz0 = fminf(bz0, __shfl_xor_sync(FULL, bz0, o)); bz1 = fmaxf(bz1, __shfl_xor_sync(FULL, bz1, o));
         }
-        if ((lane & 15) == 0) {
-            sbox4[tid >> 4] = make_float4(bx0, bx1, by0, by1);
-            sbox2[tid >> 4] = make_float2(bz0, bz1);
+        if (CH ? lane == 0 : (lane & 15) == 0) {
+            const int bi = CH ? 2 * warp + h : tid >> 4;
+            sbox4[bi] = make_float4(bx0, bx1, by0, by1);
+            sbox2[bi] = make_float2(bz0, bz1);
         }
     }
     if (tid == 0) {
@@ -355,10 +371,12 @@ __global__ void __launch_bounds__(T, 1)
         const float dz = fmaxf(fmaxf(__fsub_rn(b2.x, z1), __fsub_rn(z1, b2.y)), 0.f);
         return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
     };
-    auto update = [&](float x1, float y1, float z1) {
+    // chunks [q0, q1) of this lane (all of them by default)
+    auto update = [&](float x1, float y1, float z1, const int q0, const int q1) {  // (constants at every call site)
         const unsigned long long nx = f2_pack(-x1, -x1), ny = f2_pack(-y1, -y1), nz = f2_pack(-z1, -z1);
 #pragma unroll
         for (int q = 0; q < C4; ++q) {
+            if (q < q0 || q >= q1) continue;
             const float4 X = *reinterpret_cast<const float4*>(sx + base + q * 128);
             const float4 Y = *reinterpret_cast<const float4*>(sy + base + q * 128);
             const float4 Z = *reinterpret_cast<const float4*>(sz + base + q * 128);
@@ -392,9 +410,20 @@ __global__ void __launch_bounds__(T, 1)
         uint32_t eq = 0u;
 #pragma unroll
         for (int p = 0; p < P; ++p) eq |= (md[p] == lmax) ? (1u << p) : 0u;
-        const int bp = __ffs(eq) - 1;
-        lpos = base + (bp >> 2) * 128 + (bp & 3);
+        int bp = __ffs(eq) - 1;
         const bool several = (eq & (eq - 1u)) != 0u;
+        if (CH && several && (eq & ~((2u << (bp | 3)) - 1u)) != 0u) {
+            // (rare) the maximum sits in several chunks of this lane: slots are in rank order inside a chunk only, so the
+            // lowest maximum of every chunk competes by reference rank
+            uint32_t rest = eq, brk = 0xffffffffu;
+            while (rest) {
+                const int p = __ffs(rest) - 1;
+                rest &= ~(0xfu << (p & ~3));
+                const uint32_t r = ref_rank(sk[base + (p >> 2) * 128 + (p & 3)], L);
+                if (r < brk) { brk = r; bp = p; }
+            }
+        }
+        lpos = base + (bp >> 2) * 128 + (bp & 3);
         // the warp's candidate: one redux, one ballot, one shuffle (bit 31: the lane holds several maxima)
         wu = __reduce_max_sync(FULL, u);
         const unsigned tie = __ballot_sync(FULL, u == wu);
@@ -469,7 +498,7 @@ __global__ void __launch_bounds__(T, 1)
             uint2* const rec = recs + (j & 1) * 32;  // double-buffered: a fast warp may already post pick j+1
             const bool hit = !(box_bound(x1, y1, z1, b4, b2) >= lmax) || j == 1;  // NaN bounds count as hits
             if (__any_sync(FULL, hit)) {
-                update(x1, y1, z1);
+                update(x1, y1, z1, 0, C4);
                 warp_argmax();
             }
             if (lane == 0) rec[warp] = make_uint2(wu, wpos);
@@ -551,7 +580,7 @@ __global__ void __launch_bounds__(T, 1)
             rskey[tid] = 31u - tid;
             posarr[tid] = 0x7fu;
             sk_at[tid] = 0u;
-            whitp[tid] = 1u;  // round 0: every warp applies pick 0
+            whitp[tid] = CH ? 0x0101u : 1u;  // round 0: every warp applies pick 0 (to both halves of its chunks)
             whitp[32 + tid] = 0u;
             whitp[64 + tid] = 0u;
         }
@@ -570,7 +599,9 @@ __global__ void __launch_bounds__(T, 1)
             // ---- APPLY the round's picks (cand[0..c)); j = the first pick the leader decides next
             // (no second, finer test here: the round is bound by the latency of this chain, not by issue slots, so an
             // update that turns out to change nothing is cheaper than a test + warp vote that might avoid it)
-            const unsigned wm = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & ((1u << c) - 1u);
+            // chunk-compact layout: bits 0..7 = picks that may reach the first half of the warp's chunks, 8..15 = the second
+            const unsigned wm2 = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & (((1u << c) - 1u) * (CH ? 0x0101u : 1u));
+            const unsigned wm = CH ? ((wm2 | (wm2 >> 8)) & 0xffu) : wm2;
 #ifdef FPSB_PROF
             const long long pw0 = clock_after(wm);
             long long pw1 = pw0;
@@ -596,7 +627,12 @@ __global__ void __launch_bounds__(T, 1)
 #ifdef FPSB_PROF
                         const long long pu0 = clock_after(__float_as_uint(pk.x) ^ __float_as_uint(pk.z));
 #endif
-                        update(pk.x, pk.y, pk.z);
+                        if (CH) {  // warp-uniform: whole LDS.128 / FADD2 ... groups are skipped, not lanes
+                            if ((wm2 >> k) & 1u) update(pk.x, pk.y, pk.z, 0, HC);
+                            if ((wm2 >> (k + 8)) & 1u) update(pk.x, pk.y, pk.z, HC, C4);
+                        } else {
+                            update(pk.x, pk.y, pk.z, 0, C4);
+                        }
 #ifdef FPSB_PROF
                         uint32_t dep = 0u;
 #pragma unroll
@@ -640,8 +676,9 @@ __global__ void __launch_bounds__(T, 1)
                     for (int k = 0; k < K; ++k) {
                         if (k % 3 != warp - 1) continue;
                         const float4 ck = cand[k];
-                        const bool hit = !(box_bound(ck.x, ck.y, ck.z, g0, h0) >= wmax) || !(box_bound(ck.x, ck.y, ck.z, g1, h1) >= wmax);
-                        hmask |= hit ? (1u << k) : 0u;
+                        const bool hit0 = !(box_bound(ck.x, ck.y, ck.z, g0, h0) >= wmax), hit1 = !(box_bound(ck.x, ck.y, ck.z, g1, h1) >= wmax);
+                        if (CH) hmask |= (hit0 ? (1u << k) : 0u) | (hit1 ? (0x100u << k) : 0u);
+                        else hmask |= (hit0 || hit1) ? (1u << k) : 0u;
                     }
                     whitp[32 * (warp - 1) + lane] = hmask;
                 }
@@ -775,13 +812,12 @@ __global__ void __launch_bounds__(T, 1)
         if (a.temp != nullptr && c > 1) {
             // temp leaves with the min-distances to picks 0..m-2 (the reference never applies its last pick): the last
             // round's picks but the final one are still outstanding
-            const unsigned wm = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & ((1u << (c - 1)) - 1u);
+            const unsigned wm2 = (whitp[warp] | whitp[32 + warp] | whitp[64 + warp]) & (((1u << (c - 1)) - 1u) * (CH ? 0x0101u : 1u));
 #pragma unroll 1
             for (int k = 0; k < K; ++k) {
-                if ((wm >> k) & 1u) {
-                    const float4 pk = cand[k];
-                    update(pk.x, pk.y, pk.z);
-                }
+                const float4 pk = cand[k];
+                if ((wm2 >> k) & 1u) update(pk.x, pk.y, pk.z, 0, HC);
+                if (CH && ((wm2 >> (k + 8)) & 1u)) update(pk.x, pk.y, pk.z, HC, C4);
             }
         }
 #ifdef FPSB_PROF
@@ -806,7 +842,7 @@ __global__ void __launch_bounds__(T, 1)
     if (a.temp) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            if (first + p < n) a.temp[(size_t)cloud * n + sk[base + (p >> 2) * 128 + (p & 3)]] = md[p];
+            if (slot_valid(p)) a.temp[(size_t)cloud * n + sk[base + (p >> 2) * 128 + (p & 3)]] = md[p];
         }
     }
 }

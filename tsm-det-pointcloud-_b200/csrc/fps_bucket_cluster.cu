@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(FBC_T, 1)
                 const float cval = __uint_as_float(wu & 0x7fffffffu);
                 bool redo = (wu & 0x80000000u) == 0u;
 #pragma unroll 1
-                for (int k = 0; k < c; ++k) {
+                for (int k = __ffs(wm) - 1; (wm >> k) != 0u; ++k) {  // first..last set bit only (fps_bucket.cu)
                     if ((wm >> k) & 1u) {
                         const float4 pk = cand[k];
                         redo |= sqdist3(pk.x, pk.y, pk.z, cx, cy, cz) < cval;
