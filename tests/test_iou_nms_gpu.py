@@ -241,3 +241,27 @@ def test_lazy_nms_equals_full_mask_nms(thresh, monkeypatch):
     assert torch.equal(got_num, want_num)
     assert torch.equal(got_sel, want_sel)
     assert int(got_num[3]) == 1 and int(got_num.min()) >= 1
+
+
+@pytest.mark.parametrize("n", [16384, 20000])
+def test_lazy_nms_large_frames(n, monkeypatch):
+    """16384 boxes per frame is the largest power of two the lazy kernel takes (191 KB of shared memory: suppression rows,
+    two blocks of box records, the staged grid); 20000 boxes go to the full-mask pipeline.  Both must agree with the
+    full-mask result, per-frame counts included."""
+    from tsmdet_b200 import iou3d_nms_utils as iu
+
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    frames = [synth.boxes_clustered(n, 900 + i, centres=n // 16) for i in range(2)]
+    boxes = torch.from_numpy(np.stack(frames)).to(dev)
+    counts = torch.tensor([n, n - 777], dtype=torch.int32, device=dev)
+    scores = torch.from_numpy(np.stack([rng.permutation(n).astype(np.float32) for _ in range(2)])).to(dev)
+    scores = torch.where(torch.arange(n, device=dev).unsqueeze(0) < counts.unsqueeze(1), scores,
+                         torch.full_like(scores, float("-inf")))
+    knob_setenv(monkeypatch, "TSMDET_NMS_ALGO", "mask")
+    want_sel, want_num = iu.nms_gpu_batch(boxes, scores, 0.1, counts=counts)
+    knob_delenv(monkeypatch, "TSMDET_NMS_ALGO")
+    got_sel, got_num = iu.nms_gpu_batch(boxes, scores, 0.1, counts=counts)
+    assert torch.equal(got_num, want_num)
+    assert torch.equal(got_sel, want_sel)
+    assert int(got_num.min()) >= 1
