@@ -348,6 +348,105 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// nsample <= 16: the same algorithm with HALF a warp per centre (two centres per warp).  At the first SA layer a ball
+// holds one or two points (the centre itself and maybe a neighbour) and a few dozen candidates, so a whole warp per centre
+// is mostly fixed cost: ncu counts 346 warp-instructions per centre at 80 % issue utilisation -- the kernel is
+// instruction-bound.  A lane owns neighbour cells gl and gl + 16 (candidates may be numbered in any order: the result is
+// the nsample smallest hit indices whatever the order), collectives run on the half-warp's own member mask, lane e of the
+// half ends up with the e-th smallest hit, and the grid is (centres, clouds) so that no 64-bit division is needed.
+template <bool DILATED>
+__global__ void __launch_bounds__(256)
+    bq_grid_query16_kernel(int n, int m, float rin2, float rout2, int nsample, const float* __restrict__ new_xyz,
+                           const int* __restrict__ hdr_all, const int* __restrict__ cell_start_all,
+                           const float4* __restrict__ sorted_all, int* __restrict__ idx_cnt, int* __restrict__ idx) {
+    constexpr int K = 4;
+    constexpr uint32_t NONE = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gl = lane & 15;
+    const unsigned gmask = 0xffffu << (lane & 16);
+    const int cloud = blockIdx.y;
+    const int centre = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    if (centre >= m) return;  // (a whole half-warp leaves together)
+    const GridHdr h = *reinterpret_cast<const GridHdr*>(hdr_all + (size_t)cloud * kHdrInts);
+    if (!h.ok) return;
+    const int* __restrict__ cell_start = cell_start_all + (size_t)cloud * (kGridCells + 1);
+    const float4* __restrict__ sorted = sorted_all + (size_t)cloud * n;
+    const size_t wid = (size_t)cloud * m + centre;
+    const float* q = new_xyz + wid * 3;
+    const float cx = __ldg(q), cy = __ldg(q + 1), cz = __ldg(q + 2);
+    int* const row = idx + wid * nsample;
+
+    const int qx = grid_q(cx, h.lo[0], h.inv[0], h.n[0]), qy = grid_q(cy, h.lo[1], h.inv[1], h.n[1]),
+              qz = grid_q(cz, h.lo[2], h.inv[2], h.n[2]);
+    int beg[2] = {0, 0}, len[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int ci = gl + 16 * s;  // neighbour cell (dz, dy, dx) = (ci / 9 - 1, ci / 3 % 3 - 1, ci % 3 - 1)
+        const int gx = qx + ci % 3 - 1, gy = qy + (ci / 3) % 3 - 1, gz = qz + ci / 9 - 1;
+        if (ci < 27 && gx >= 0 && gx < h.n[0] && gy >= 0 && gy < h.n[1] && gz >= 0 && gz < h.n[2]) {
+            const int c = (gz * h.n[1] + gy) * h.n[0] + gx;
+            beg[s] = __ldg(cell_start + c);
+            len[s] = __ldg(cell_start + c + 1) - beg[s];
+        }
+    }
+    const int loc = len[0] + len[1];
+    int incl = loc;  // inclusive prefix of the lanes' candidate counts within the half-warp
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(gmask, incl, o, 16);
+        if (gl >= o) incl += t;
+    }
+    const int total = __shfl_sync(gmask, incl, 15, 16);
+    const int excl_len0 = ((incl - loc) << 16) | len[0];  // (both < 2^15: a cell holds <= kMaxCell points, 27 cells)
+
+    uint32_t best = NONE;  // lane e of the half: the e-th smallest hit so far
+    for (int base = 0; base < total; base += 16 * K) {
+        uint32_t v[K + 1];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            v[k] = NONE;
+            if (base + k * 16 >= total) continue;  // (uniform in the half) no candidates left for this slot
+            const int j = base + k * 16 + gl;
+            int t = 0;  // owner lane = first lane whose inclusive prefix exceeds j
+#pragma unroll
+            for (int step = 8; step > 0; step >>= 1) {
+                const int val = __shfl_sync(gmask, incl, t + step - 1, 16);
+                if (val <= j) t += step;
+            }
+            t &= 15;
+            const int el = __shfl_sync(gmask, excl_len0, t, 16);
+            const int b0 = __shfl_sync(gmask, beg[0], t, 16), b1 = __shfl_sync(gmask, beg[1], t, 16);
+            const int jj = j - (el >> 16), l0 = el & 0xffff;
+            const int src = jj < l0 ? b0 + jj : b1 + (jj - l0);
+            if (j < total) {
+                const float4 p = sorted[src];
+                const float d2 = sqdist3(p.x, p.y, p.z, cx, cy, cz);
+                const bool hit = DILATED ? (d2 >= rin2 && d2 < rout2) : (d2 < rout2);
+                if (hit) v[k] = (uint32_t)__float_as_int(p.w);
+            }
+        }
+        v[K] = best;
+        uint32_t nb = NONE;
+        for (int e = 0; e < nsample; ++e) {
+            uint32_t mine = v[0];
+#pragma unroll
+            for (int k = 1; k <= K; ++k) mine = min(mine, v[k]);
+            const uint32_t mn = __reduce_min_sync(gmask, mine);
+            if (mn == NONE) break;
+#pragma unroll
+            for (int k = 0; k <= K; ++k)
+                if (v[k] == mn) v[k] = NONE;  // indices are unique: exactly one slot in the half-warp
+            if (gl == e) nb = mn;
+        }
+        best = nb;
+    }
+    const int cnt = __popc(__ballot_sync(gmask, best != NONE) & gmask);
+    if (gl == 0) idx_cnt[wid] = cnt;
+    // row[p] = hit[p mod cnt] (cyclic padding); rows without hits are zeroed
+    const int srcl = cnt > 1 ? gl % cnt : 0;
+    const uint32_t val = __shfl_sync(gmask, best, srcl, 16);
+    if (gl < nsample) row[gl] = cnt ? (int)val : 0;
+}
+
 }  // namespace tsm
 
 int tsm_grid_build(int b, int n, float rout, const float* xyz, cudaStream_t stream, int tag, const int** hdr_out,
@@ -390,7 +489,15 @@ int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout
     const float rin2 = rin * rin, rout2 = rout * rout;  // f32 products, as ball_query_gpu.cu:91, 154-155
     const long long warps = (long long)b * m;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    if (nsample <= 32) {
+    if (nsample <= 16 && kMaxCell * 27 < 32768) {
+        const dim3 grid16((unsigned)((m + 15) / 16), (unsigned)b);
+        if (dilated)
+            bq_grid_query16_kernel<true><<<grid16, 256, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, hdr, cell_start, sorted,
+                                                                    idx_cnt, idx);
+        else
+            bq_grid_query16_kernel<false><<<grid16, 256, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, hdr, cell_start, sorted,
+                                                                     idx_cnt, idx);
+    } else if (nsample <= 32) {
         if (dilated)
             bq_grid_query_kernel<true><<<blocks, 256, 0, stream>>>(b, n, m, rin2, rout2, nsample, new_xyz, hdr,
                                                                    cell_start, sorted, idx_cnt, idx);
