@@ -28,10 +28,13 @@ BQ = [
     (2, 37, 5, None, 100.0, 7, synth.cloud_uniform),          # everything hits; nsample not a power of two
     (2, 2048, 130, None, 1e-3, 16, synth.cloud_uniform),      # nothing but the centre itself
     (1, 16384, 4096, None, 0.8, 32, synth.cloud_ground_objects),  # BASELINE config 1 shape
+    (2, 4096, 333, None, 0.8, 24, synth.cloud_ground_objects),    # half-warp kernel: two results per lane, odd centre count
+    (2, 4096, 511, 0.2, 0.6, 17, synth.cloud_uniform),            # ... nsample just above 16, dilated
+    (1, 2048, 100, None, 3.0, 32, synth.cloud_uniform),           # ... every super-round full of hits
 ]
 
 
-@pytest.mark.parametrize("algo", ["grid", "brute"])
+@pytest.mark.parametrize("algo", ["grid", "warp", "brute"])  # grid: half a warp per centre (nsample <= 32); warp: a whole one
 @pytest.mark.parametrize("case", BQ, ids=[f"bq{i}" for i in range(len(BQ))])
 def test_ball_query(orc, case, algo, monkeypatch):
     """Both query paths: the uniform-grid kernels (ball_query_grid.cu; clouds of >= 512 points whose grid is

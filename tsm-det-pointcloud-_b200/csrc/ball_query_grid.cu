@@ -20,6 +20,7 @@
 // whole cloud) is flagged and left to the brute-force kernels of ball_query.cu, which skip flagged-OK
 // clouds -- no host synchronisation either way.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "grid.cuh"
@@ -348,13 +349,14 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// nsample <= 16: the same algorithm with HALF a warp per centre (two centres per warp).  At the first SA layer a ball
+// nsample <= 16 * R (R = 1, 2): the same algorithm with HALF a warp per centre (two centres per warp).  At the first SA layer a ball
 // holds one or two points (the centre itself and maybe a neighbour) and a few dozen candidates, so a whole warp per centre
 // is mostly fixed cost: ncu counts 346 warp-instructions per centre at 80 % issue utilisation -- the kernel is
 // instruction-bound.  A lane owns neighbour cells gl and gl + 16 (candidates may be numbered in any order: the result is
 // the nsample smallest hit indices whatever the order), collectives run on the half-warp's own member mask, lane e of the
-// half ends up with the e-th smallest hit, and the grid is (centres, clouds) so that no 64-bit division is needed.
-template <bool DILATED>
+// half ends up with the e-th (and, R = 2, the (e + 16)-th) smallest hit, and the grid is (centres, clouds) so that no
+// 64-bit division is needed.
+template <bool DILATED, int R>
 __global__ void __launch_bounds__(256)
     bq_grid_query16_kernel(int n, int m, float rin2, float rout2, int nsample, const float* __restrict__ new_xyz,
                            const int* __restrict__ hdr_all, const int* __restrict__ cell_start_all,
@@ -398,9 +400,11 @@ __global__ void __launch_bounds__(256)
     const int total = __shfl_sync(gmask, incl, 15, 16);
     const int excl_len0 = ((incl - loc) << 16) | len[0];  // (both < 2^15: a cell holds <= kMaxCell points, 27 cells)
 
-    uint32_t best = NONE;  // lane e of the half: the e-th smallest hit so far
+    uint32_t best[R];  // lane e of the half: the (e + 16 i)-th smallest hit so far
+#pragma unroll
+    for (int i = 0; i < R; ++i) best[i] = NONE;
     for (int base = 0; base < total; base += 16 * K) {
-        uint32_t v[K + 1];
+        uint32_t v[K + R];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             v[k] = NONE;
@@ -424,27 +428,43 @@ __global__ void __launch_bounds__(256)
                 if (hit) v[k] = (uint32_t)__float_as_int(p.w);
             }
         }
-        v[K] = best;
-        uint32_t nb = NONE;
+#pragma unroll
+        for (int i = 0; i < R; ++i) v[K + i] = best[i];
+        uint32_t nb[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) nb[i] = NONE;
         for (int e = 0; e < nsample; ++e) {
             uint32_t mine = v[0];
 #pragma unroll
-            for (int k = 1; k <= K; ++k) mine = min(mine, v[k]);
+            for (int k = 1; k < K + R; ++k) mine = min(mine, v[k]);
             const uint32_t mn = __reduce_min_sync(gmask, mine);
             if (mn == NONE) break;
 #pragma unroll
-            for (int k = 0; k <= K; ++k)
+            for (int k = 0; k < K + R; ++k)
                 if (v[k] == mn) v[k] = NONE;  // indices are unique: exactly one slot in the half-warp
-            if (gl == e) nb = mn;
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (gl + 16 * i == e) nb[i] = mn;
         }
-        best = nb;
+#pragma unroll
+        for (int i = 0; i < R; ++i) best[i] = nb[i];
     }
-    const int cnt = __popc(__ballot_sync(gmask, best != NONE) & gmask);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) cnt += __popc(__ballot_sync(gmask, best[i] != NONE) & gmask);
     if (gl == 0) idx_cnt[wid] = cnt;
     // row[p] = hit[p mod cnt] (cyclic padding); rows without hits are zeroed
-    const int srcl = cnt > 1 ? gl % cnt : 0;
-    const uint32_t val = __shfl_sync(gmask, best, srcl, 16);
-    if (gl < nsample) row[gl] = cnt ? (int)val : 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int p = gl + 16 * i;
+        const int src = cnt > 1 ? p % cnt : 0;
+        uint32_t val = __shfl_sync(gmask, best[0], src & 15, 16);
+        if (R > 1) {
+            const uint32_t hi = __shfl_sync(gmask, best[R - 1], src & 15, 16);
+            if (src >= 16) val = hi;
+        }
+        if (p < nsample) row[p] = cnt ? (int)val : 0;
+    }
 }
 
 }  // namespace tsm
@@ -489,14 +509,16 @@ int tsm_ball_query_grid(bool dilated, int b, int n, int m, float rin, float rout
     const float rin2 = rin * rin, rout2 = rout * rout;  // f32 products, as ball_query_gpu.cu:91, 154-155
     const long long warps = (long long)b * m;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    if (nsample <= 16 && kMaxCell * 27 < 32768) {
+    const char* bq_full = tsm_knob(KNOB_BQ_ALGO);  // "warp": a whole warp per centre (A/B, tests)
+    if (nsample <= 32 && kMaxCell * 27 < 32768 && !(bq_full && !strcmp(bq_full, "warp"))) {
         const dim3 grid16((unsigned)((m + 15) / 16), (unsigned)b);
-        if (dilated)
-            bq_grid_query16_kernel<true><<<grid16, 256, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, hdr, cell_start, sorted,
-                                                                    idx_cnt, idx);
-        else
-            bq_grid_query16_kernel<false><<<grid16, 256, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, hdr, cell_start, sorted,
-                                                                     idx_cnt, idx);
+#define BQ16(D, RR) bq_grid_query16_kernel<D, RR><<<grid16, 256, 0, stream>>>(n, m, rin2, rout2, nsample, new_xyz, hdr, cell_start, sorted, idx_cnt, idx)
+        if (nsample <= 16) {
+            if (dilated) BQ16(true, 1); else BQ16(false, 1);
+        } else {
+            if (dilated) BQ16(true, 2); else BQ16(false, 2);
+        }
+#undef BQ16
     } else if (nsample <= 32) {
         if (dilated)
             bq_grid_query_kernel<true><<<blocks, 256, 0, stream>>>(b, n, m, rin2, rout2, nsample, new_xyz, hdr,
