@@ -22,6 +22,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before any CUDA call: see tsmdet_b200/__init__.py (both arms)
 import subprocess
 import sys
 import threading
@@ -337,12 +339,16 @@ def main():
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         runner.fork()
+        t_host = time.perf_counter()
         for _ in range(steps):
             submit()
+        host_ms.append((time.perf_counter() - t_host) * 1e3 / max(1, steps))  # host time to ENQUEUE one step
         runner.join()
         e.record()
         torch.cuda.synchronize(dev)
         return s.elapsed_time(e)
+
+    host_ms = []
 
     def timed_repeats(submit):
         """`--repeats` regions of exactly K steps, each bracketed by barrier + synchronize; per region the MAX over
@@ -466,7 +472,12 @@ def main():
                       "fps": "one CTA per cloud, exact spatial pruning, rounds of up to 8 picks (fps_bucket_kernel); levels "
                              "2/3 CHAINED (look-ups proven exact by level 1's record; the un-chained stand-alone times are "
                              "fps_L2 / fps_L3 in roofline.per_kernel)",
-                      "ms_per_step_single_in_flight": lat[len(lat) // 2], "gather": gather_transport},
+                      "ms_per_step_single_in_flight": lat[len(lat) // 2], "gather": gather_transport,
+                      "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
+                      # host time to ENQUEUE one step (python + graph launch [+ gather kernels]), median over the regions:
+                      # when it approaches ms_per_step the host, not the GPU, sets the pace
+                      "host_enqueue_ms_per_step": {"device": sorted(host_ms[:len(dev_regions)])[len(dev_regions) // 2],
+                                                   "e2e": sorted(host_ms[len(dev_regions):2 * len(dev_regions)])[len(dev_regions) // 2]}},
         "kernels": kernels, "wall_s_timed_region": wall,
     }
     extras = rank == 0 and world == 1 and not args.no_extras

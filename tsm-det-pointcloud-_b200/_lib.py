@@ -10,6 +10,10 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
 
+# more hardware work queues than the CUDA default of 8 (see tsmdet_b200/__init__.py: in-kernel waits of the peer gather
+# must not share a queue with other pipeline lanes); only effective before the process creates its CUDA context
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TSMDET_LIB: load another build of the same C ABI (instrumented builds made by scripts/; never a fallback)
 LIB_PATH = os.environ.get("TSMDET_LIB") or os.path.join(_HERE, "libtsmdet_b200.so")
