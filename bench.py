@@ -522,7 +522,15 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave at once.  Tearing the process down piece by piece (NCCL communicator, the IPC mappings of
+        # every peer's receive rings, 8 captured graphs per rank) took more than a minute after the line was printed in
+        # one 8-GPU run of round 2; nothing below this point is needed, and the driver reclaims a dead process's resources.
+        # (No collective here either: the last one -- the all_reduce of the copy-ceiling regions -- lies seconds back on
+        # every rank, behind the per-kernel timing.)
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _graph_timer(dev, flush_mb: int = 256):
