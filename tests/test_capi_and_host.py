@@ -119,3 +119,17 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_import_sets_hardware_queue_default_and_respects_an_existing_value():
+    """`import tsmdet_b200` asks for 32 hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS) before the process creates its
+    CUDA context -- the in-kernel waits of the peer gather must not share a queue with other pipeline lanes --
+    and leaves a value the user exported alone."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import os, sys; sys.path.insert(0, %r); import tsmdet_b200; print(os.environ['CUDA_DEVICE_MAX_CONNECTIONS'])" % root
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "32"
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "4"
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "4"
