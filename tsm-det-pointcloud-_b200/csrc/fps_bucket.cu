@@ -19,7 +19,10 @@
 //    therefore every pick -- is bit-identical to the brute force;
 //  * one __syncthreads per pick: warps post (key, position) records, every warp reduces the <= 32
 //    records itself (redux.sync), and the reference's tie rule -- among equal maxima the smallest
-//    rank(k) = bitrev(k mod bs) : k / bs -- is evaluated lazily, only when a maximum is shared.
+//    rank(k) = bitrev(k mod bs) : k / bs -- is evaluated lazily, only when a maximum is shared;
+//  * K > 1 (clouds of 8193..16384 points): rounds of up to K exact picks decided by a leader warp, with the
+//    planes in plain sorted order ("chunk-compact": the 128 points one LDS.128 of a warp reads are spatially
+//    compact), one box per half of a warp's chunks, and updates that skip the half a pick cannot reach.
 //
 // One SM per cloud instead of a cluster of eight, and ~2x fewer cycles per pick: see DESIGN.md 4.1.
 #include "fps.cuh"
